@@ -1,0 +1,192 @@
+/* include/rpw_b200.h — C-ABI of the B200-native Recursive Patchwork ground-segmentation path.
+ *
+ * This is the drop-in boundary: plain C, opaque handle, plain pointers and sizes, integer status
+ * codes, no exceptions, no CUDA / torch / Eigen types.  Everything below it is hand-written
+ * sm_100a CUDA (librpw_b200.so); everything above it (the C++ class that mirrors the reference's
+ * header, ROS2 node, bag loader, Python bindings) stays on the host side.
+ *
+ * Reference interface each entry point stands in for (RP = src/recursive_patchwork in the
+ * reference repository):
+ *   rpw_config                 struct PatchworkConfig            RP/include/recursive_patchwork.hpp:25-36
+ *   rpw_create / rpw_destroy   RecursivePatchwork ctor / dtor    RP/include/recursive_patchwork.hpp:49-50
+ *                              + cuda::CudaManager::initialize / cleanup  RP/include/cuda_interface.hpp:14-20
+ *   rpw_set_config/get_config  setConfig / getConfig             RP/include/recursive_patchwork.hpp:66-67
+ *   rpw_segment*               filterGroundPoints                RP/include/recursive_patchwork.hpp:53-54,
+ *                                                                RP/src/recursive_patchwork.cpp:310-426
+ *                              (which subsumes cuda::ops::computeDistances2D / filterPointsByRadius /
+ *                               computeAngles / computePlaneDistances, RP/include/cuda_interface.hpp:73-88)
+ *   rpw_zone_model             ring edges + sector angle         RP/src/recursive_patchwork.cpp:344-352
+ *
+ * There is NO CPU fallback: without a usable CUDA device rpw_create fails with RPW_ERR_NO_DEVICE.
+ *
+ * Threading: a handle owns one device, one stream and its buffers; it is not re-entrant (one
+ * call at a time per handle).  Distinct handles may be used concurrently from distinct threads;
+ * that is how several GPUs (or several in-flight batches on one GPU) are driven.
+ */
+#ifndef RPW_B200_H
+#define RPW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RPW_ABI_VERSION 1
+
+/* Status codes (the reference has no error convention on this path: CUDA errors are printed and
+ * ignored, RP/cuda/cuda_wrapper.cu:119-122; the C++ shim turns non-zero into an exception). */
+enum {
+    RPW_OK = 0,
+    RPW_ERR_BAD_ARG = 1,   /* NULL pointer, bad stride, bad config                           */
+    RPW_ERR_NO_DEVICE = 2, /* no CUDA device / device index out of range / not sm_100         */
+    RPW_ERR_CUDA = 3,      /* a CUDA runtime call or kernel failed; see rpw_last_error        */
+    RPW_ERR_CAPACITY = 4,  /* more points / scans than the handle was created for            */
+    RPW_ERR_ALLOC = 5      /* host or device allocation failed                                */
+};
+
+/* Field-for-field mirror of PatchworkConfig (bool widened to int32).  max_range and th_outlier are
+ * carried for interface fidelity; like the reference, the path never reads them. */
+typedef struct rpw_config {
+    float sensor_height;          /* 1.2   */
+    float max_range;              /* 150   */
+    int32_t num_sectors;          /* 10    */
+    int32_t max_iter;             /* 100   */
+    int32_t adaptive_seed_height; /* 1     */
+    float th_seeds;               /* 0.15  */
+    float th_dist;                /* 0.2   */
+    float th_outlier;             /* 0.08  */
+    float filtering_radius;       /* 150   */
+    int32_t max_split_depth;      /* 1000  */
+} rpw_config;
+
+/* Per-input-point label.  The reference returns two clouds and no labels; labels are the
+ * north-star addition and determine the clouds: ground = points labelled 1 in input order;
+ * non-ground = points labelled 0 in input order followed by points labelled 2 in input order
+ * (RP/src/recursive_patchwork.cpp:402-419); points labelled 3 appear in neither. */
+#define RPW_LABEL_NONGROUND 0u
+#define RPW_LABEL_GROUND 1u
+#define RPW_LABEL_BEYOND 2u  /* finite, sqrt(x^2+y^2) > filtering_radius */
+#define RPW_LABEL_DROPPED 3u /* non-finite coordinate (cleanPoints)      */
+
+/* Per-input-point binning key (debug / parity output). key = ring * num_sectors + sector. */
+#define RPW_KEY_DROPPED 0xFFFFu
+#define RPW_KEY_BEYOND 0xFFFEu
+#define RPW_KEY_UNBINNED 0xFFFDu /* in radius but in no ring/sector (d < 1 m, d == R, angle == 2*pi) */
+
+#define RPW_NUM_RINGS 8 /* RP/src/recursive_patchwork.cpp:345 */
+
+/* How one fitPlaneAndSplit node ended (RP/src/recursive_patchwork.cpp:109-308). */
+#define RPW_NODE_SMALL 1 /* n < 3 or depth > max_split_depth: all non-ground */
+#define RPW_NODE_AREA 2  /* xy bounding box < 25 m^2 at depth > 0: all ground */
+#define RPW_NODE_FLAT 3  /* z range < 0.05 m and n > 10: all ground           */
+#define RPW_NODE_FIT 4   /* leaf: iterated plane mask                          */
+#define RPW_NODE_SPLIT 5 /* split at the upper median of the wider axis        */
+
+/* One node of the recursion, for parity checks (rpw_debug_nodes).  (scan, root, start, n)
+ * identifies it: `start` is the node's offset inside its root patch, in the order in which the
+ * reference concatenates child results (left subtree first). */
+typedef struct rpw_node {
+    int32_t scan;       /* index of the scan inside the batch */
+    int32_t root;       /* ring * num_sectors + sector */
+    int32_t depth;
+    int32_t start;
+    int32_t n;
+    int32_t outcome;    /* RPW_NODE_* */
+    int32_t iters;      /* plane fits inside the iteration loop */
+    int32_t n_inliers;  /* inliers of the mask the final fit ran on */
+    int32_t split_axis; /* 0 x, 1 y, -1 none */
+    float centroid[3];  /* final plane; zeros / (0,0,1) / FLT_MAX when n_inliers < 3 */
+    float normal[3];
+    float residual;
+    float median;       /* split value when outcome == RPW_NODE_SPLIT */
+    float mean_dist;    /* root patch mean range inherited by the node */
+} rpw_node;
+
+typedef struct rpw_stats {
+    uint64_t n_points;    /* input points over the whole call            */
+    uint64_t n_ground;    /* label 1                                     */
+    uint64_t n_nonground; /* label 0                                     */
+    uint64_t n_beyond;    /* label 2                                     */
+    uint64_t n_dropped;   /* label 3                                     */
+    uint32_t n_levels;    /* recursion levels the device worklist ran    */
+    uint32_t n_nodes;     /* fitPlaneAndSplit nodes processed            */
+    uint64_t kernel_launches; /* kernels launched by this call           */
+} rpw_stats;
+
+typedef struct rpw_handle rpw_handle;
+
+/* ---- lifecycle --------------------------------------------------------------------------- */
+void rpw_default_config(rpw_config* out);
+
+/* Ring edges (RPW_NUM_RINGS+1 floats) and sector angle, computed on the host with the same
+ * libm calls as the reference (powf, double division) so that device keys are bit-exact. */
+int rpw_zone_model(const rpw_config* cfg, float* ring_edges9, float* sector_angle);
+
+/* max_total_points: capacity in points summed over one call's batch; max_batch: scans per call.
+ * Device memory used is about 72 bytes per point of capacity. */
+int rpw_create(const rpw_config* cfg, int device, size_t max_total_points, size_t max_batch, rpw_handle** out);
+void rpw_destroy(rpw_handle* h);
+int rpw_set_config(rpw_handle* h, const rpw_config* cfg);
+int rpw_get_config(const rpw_handle* h, rpw_config* out);
+
+/* Use a caller-owned CUDA stream (cudaStream_t passed as void*; NULL = the handle's own stream).
+ * All copies and kernels of later calls are enqueued on it. */
+int rpw_set_stream(rpw_handle* h, void* cuda_stream);
+
+/* Message for the last non-zero status on this handle (h == NULL: last rpw_create failure). */
+const char* rpw_last_error(const rpw_handle* h);
+
+/* ---- the path, host buffers in / host labels out ---------------------------------------- */
+/* One scan.  xyz: n points, first three floats of every `stride_bytes` record (12 = the
+ * reference's Point3D AoS, 16 = float4).  labels_out: n bytes.  stats may be NULL.
+ * Synchronous: returns after labels_out is filled. */
+int rpw_segment(rpw_handle* h, const float* xyz, size_t n, size_t stride_bytes, uint8_t* labels_out, rpw_stats* stats);
+
+/* A batch of scans (frames are independent; RP/include/recursive_patchwork.hpp:70 — the class
+ * holds no per-scan state).  clouds[i] / labels_out[i]: host buffers of scan i. */
+int rpw_segment_batch(rpw_handle* h, const float* const* clouds, const size_t* n, size_t batch, size_t stride_bytes,
+                      uint8_t* const* labels_out, rpw_stats* stats);
+
+/* Same, asynchronous: enqueues H2D copies, kernels and D2H copies on the handle's stream and
+ * returns.  Host buffers must be pinned (rpw_host_alloc) and stay valid until rpw_wait. */
+int rpw_segment_batch_async(rpw_handle* h, const float* const* clouds, const size_t* n, size_t batch, size_t stride_bytes,
+                            uint8_t* const* labels_out);
+int rpw_wait(rpw_handle* h, rpw_stats* stats);
+
+/* One scan, with the two clouds the reference returns, in the reference's order.
+ * ground_xyz / nonground_xyz: caller buffers of 3*n floats each (either may be NULL). */
+int rpw_segment_clouds(rpw_handle* h, const float* xyz, size_t n, size_t stride_bytes, uint8_t* labels_out,
+                       float* ground_xyz, size_t* n_ground, float* nonground_xyz, size_t* n_nonground);
+
+/* ---- the path, device-resident ----------------------------------------------------------- */
+/* d_points: device pointer to packed float4 (x,y,z,ignored) records of all scans back to back;
+ * scan_offsets: HOST array of batch+1 point offsets (scan i = [off[i], off[i+1])); d_labels:
+ * device pointer, off[batch] bytes.  Asynchronous on the handle's stream. */
+int rpw_segment_device(rpw_handle* h, const void* d_points, const uint64_t* scan_offsets, size_t batch, void* d_labels);
+
+/* ---- parity / debug ---------------------------------------------------------------------- */
+/* Binning keys of the last call, per input point, batch order (host buffer, n_total entries). */
+int rpw_debug_keys(rpw_handle* h, uint16_t* keys_out, size_t n_total);
+/* Record recursion nodes during later calls (costs a few stores per node). */
+int rpw_debug_enable_nodes(rpw_handle* h, int enable);
+/* Nodes of the last call; *count receives how many exist even if cap is smaller. */
+int rpw_debug_nodes(rpw_handle* h, rpw_node* out, size_t cap, size_t* count);
+/* Runs the device 3x3 symmetric eigensolver on `count` row-major matrices (host in / host out):
+ * evals (3 per matrix, ascending), evecs (9 per matrix, column c = eigenvector c). */
+int rpw_debug_eig3(rpw_handle* h, const float* mats, size_t count, float* evals, float* evecs);
+/* Runs the device restatement of libm atan2f on `count` (y, x) pairs. */
+int rpw_debug_atan2(rpw_handle* h, const float* y, const float* x, size_t count, float* out);
+
+/* ---- utilities --------------------------------------------------------------------------- */
+void* rpw_host_alloc(size_t bytes); /* pinned host memory (NULL on failure) */
+void rpw_host_free(void* p);
+/* Kernels launched through this handle since creation (bench.py's gpu_launches). */
+uint64_t rpw_kernel_launches(const rpw_handle* h);
+int rpw_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RPW_B200_H */

@@ -1,0 +1,262 @@
+"""ctypes binding of the C-ABI in include/rpw_b200.h (librpw_b200.so).
+
+This is the only way Python reaches the CUDA path.  If the shared library is missing, or no
+sm_100 device is present, everything here raises — there is no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "librpw_b200.so"
+
+RPW_OK, RPW_ERR_BAD_ARG, RPW_ERR_NO_DEVICE, RPW_ERR_CUDA, RPW_ERR_CAPACITY, RPW_ERR_ALLOC = range(6)
+LABEL_NONGROUND, LABEL_GROUND, LABEL_BEYOND, LABEL_DROPPED = 0, 1, 2, 3
+KEY_DROPPED, KEY_BEYOND, KEY_UNBINNED = 0xFFFF, 0xFFFE, 0xFFFD
+NODE_SMALL, NODE_AREA, NODE_FLAT, NODE_FIT, NODE_SPLIT = 1, 2, 3, 4, 5
+
+
+class RpwConfig(C.Structure):
+    """struct rpw_config == PatchworkConfig (RP/include/recursive_patchwork.hpp:25-36)."""
+    _fields_ = [("sensor_height", C.c_float), ("max_range", C.c_float), ("num_sectors", C.c_int32),
+                ("max_iter", C.c_int32), ("adaptive_seed_height", C.c_int32), ("th_seeds", C.c_float),
+                ("th_dist", C.c_float), ("th_outlier", C.c_float), ("filtering_radius", C.c_float),
+                ("max_split_depth", C.c_int32)]
+
+
+class RpwStats(C.Structure):
+    _fields_ = [("n_points", C.c_uint64), ("n_ground", C.c_uint64), ("n_nonground", C.c_uint64),
+                ("n_beyond", C.c_uint64), ("n_dropped", C.c_uint64), ("n_levels", C.c_uint32),
+                ("n_nodes", C.c_uint32), ("kernel_launches", C.c_uint64)]
+
+
+NODE_DTYPE = np.dtype([("scan", "<i4"), ("root", "<i4"), ("depth", "<i4"), ("start", "<i4"), ("n", "<i4"),
+                       ("outcome", "<i4"), ("iters", "<i4"), ("n_inliers", "<i4"), ("split_axis", "<i4"),
+                       ("centroid", "<f4", 3), ("normal", "<f4", 3), ("residual", "<f4"), ("median", "<f4"),
+                       ("mean_dist", "<f4")])
+
+# Every symbol include/rpw_b200.h declares (tests check that the library exports all of them).
+EXPORTS = ["rpw_default_config", "rpw_zone_model", "rpw_create", "rpw_destroy", "rpw_set_config", "rpw_get_config",
+           "rpw_set_stream", "rpw_last_error", "rpw_segment", "rpw_segment_batch", "rpw_segment_batch_async", "rpw_wait",
+           "rpw_segment_clouds", "rpw_segment_device", "rpw_debug_keys", "rpw_debug_enable_nodes", "rpw_debug_nodes",
+           "rpw_debug_eig3", "rpw_debug_atan2", "rpw_host_alloc", "rpw_host_free", "rpw_kernel_launches", "rpw_abi_version"]
+
+_lib = None
+
+
+class RpwError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"rpw error {code}: {msg}")
+        self.code = code
+
+
+def load_library() -> C.CDLL:
+    """Loads librpw_b200.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RpwError(-1, f"{LIB_PATH} is missing: build it with __graft_entry__.build() — there is no CPU fallback")
+    lib = C.CDLL(str(LIB_PATH))
+    vp, sz, u8p, fp = C.c_void_p, C.c_size_t, C.POINTER(C.c_uint8), C.POINTER(C.c_float)
+    cfgp = C.POINTER(RpwConfig)
+    lib.rpw_default_config.argtypes = [cfgp]; lib.rpw_default_config.restype = None
+    lib.rpw_zone_model.argtypes = [cfgp, fp, fp]; lib.rpw_zone_model.restype = C.c_int
+    lib.rpw_create.argtypes = [cfgp, C.c_int, sz, sz, C.POINTER(vp)]; lib.rpw_create.restype = C.c_int
+    lib.rpw_destroy.argtypes = [vp]; lib.rpw_destroy.restype = None
+    lib.rpw_set_config.argtypes = [vp, cfgp]; lib.rpw_set_config.restype = C.c_int
+    lib.rpw_get_config.argtypes = [vp, cfgp]; lib.rpw_get_config.restype = C.c_int
+    lib.rpw_set_stream.argtypes = [vp, vp]; lib.rpw_set_stream.restype = C.c_int
+    lib.rpw_last_error.argtypes = [vp]; lib.rpw_last_error.restype = C.c_char_p
+    lib.rpw_segment.argtypes = [vp, vp, sz, sz, vp, C.POINTER(RpwStats)]; lib.rpw_segment.restype = C.c_int
+    lib.rpw_segment_batch.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), sz, sz, C.POINTER(vp), C.POINTER(RpwStats)]
+    lib.rpw_segment_batch.restype = C.c_int
+    lib.rpw_segment_batch_async.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), sz, sz, C.POINTER(vp)]
+    lib.rpw_segment_batch_async.restype = C.c_int
+    lib.rpw_wait.argtypes = [vp, C.POINTER(RpwStats)]; lib.rpw_wait.restype = C.c_int
+    lib.rpw_segment_clouds.argtypes = [vp, vp, sz, sz, vp, vp, C.POINTER(sz), vp, C.POINTER(sz)]
+    lib.rpw_segment_clouds.restype = C.c_int
+    lib.rpw_segment_device.argtypes = [vp, vp, C.POINTER(C.c_uint64), sz, vp]; lib.rpw_segment_device.restype = C.c_int
+    lib.rpw_debug_keys.argtypes = [vp, vp, sz]; lib.rpw_debug_keys.restype = C.c_int
+    lib.rpw_debug_enable_nodes.argtypes = [vp, C.c_int]; lib.rpw_debug_enable_nodes.restype = C.c_int
+    lib.rpw_debug_nodes.argtypes = [vp, vp, sz, C.POINTER(sz)]; lib.rpw_debug_nodes.restype = C.c_int
+    lib.rpw_debug_eig3.argtypes = [vp, vp, sz, vp, vp]; lib.rpw_debug_eig3.restype = C.c_int
+    lib.rpw_debug_atan2.argtypes = [vp, vp, vp, sz, vp]; lib.rpw_debug_atan2.restype = C.c_int
+    lib.rpw_host_alloc.argtypes = [sz]; lib.rpw_host_alloc.restype = vp
+    lib.rpw_host_free.argtypes = [vp]; lib.rpw_host_free.restype = None
+    lib.rpw_kernel_launches.argtypes = [vp]; lib.rpw_kernel_launches.restype = C.c_uint64
+    lib.rpw_abi_version.argtypes = []; lib.rpw_abi_version.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def default_config() -> RpwConfig:
+    c = RpwConfig()
+    load_library().rpw_default_config(C.byref(c))
+    return c
+
+
+def zone_model(cfg: RpwConfig):
+    edges = (C.c_float * 9)()
+    ang = C.c_float()
+    rc = load_library().rpw_zone_model(C.byref(cfg), edges, C.byref(ang))
+    if rc != RPW_OK:
+        raise RpwError(rc, "rpw_zone_model")
+    return np.array(edges[:], np.float32), np.float32(ang.value)
+
+
+class PinnedArray:
+    """numpy view of pinned host memory from rpw_host_alloc (freed with the object)."""
+
+    def __init__(self, shape, dtype):
+        self._lib = load_library()
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        self.ptr = self._lib.rpw_host_alloc(max(n, 1))
+        if not self.ptr:
+            raise RpwError(RPW_ERR_ALLOC, "rpw_host_alloc failed")
+        buf = (C.c_uint8 * max(n, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def __del__(self):
+        try:
+            if getattr(self, "ptr", None):
+                self.array = None
+                self._lib.rpw_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+class Handle:
+    """Owns one rpw_handle (one device, one stream, its buffers)."""
+
+    def __init__(self, cfg: RpwConfig | None = None, device: int = 0, max_total_points: int = 1 << 20, max_batch: int = 1):
+        self.lib = load_library()
+        self._h = C.c_void_p()
+        rc = self.lib.rpw_create(C.byref(cfg) if cfg is not None else None, device, max_total_points, max_batch, C.byref(self._h))
+        if rc != RPW_OK:
+            msg = self.lib.rpw_last_error(None).decode()
+            self._h = None
+            raise RpwError(rc, msg)
+        self.max_total_points = max_total_points
+        self.max_batch = max_batch
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.rpw_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != RPW_OK:
+            raise RpwError(rc, self.lib.rpw_last_error(self._h).decode())
+
+    # -- configuration ---------------------------------------------------------------------
+    def set_config(self, cfg: RpwConfig):
+        self._check(self.lib.rpw_set_config(self._h, C.byref(cfg)))
+
+    def get_config(self) -> RpwConfig:
+        c = RpwConfig()
+        self._check(self.lib.rpw_get_config(self._h, C.byref(c)))
+        return c
+
+    def set_stream(self, cuda_stream: int | None):
+        self._check(self.lib.rpw_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    # -- the path --------------------------------------------------------------------------
+    @staticmethod
+    def _as_points(points):
+        a = np.ascontiguousarray(points, dtype=np.float32)
+        if a.ndim != 2 or a.shape[1] not in (3, 4):
+            raise ValueError("points must be (n, 3) or (n, 4) float32")
+        return a
+
+    def segment(self, points, want_stats=False):
+        a = self._as_points(points)
+        labels = np.empty(len(a), np.uint8)
+        st = RpwStats()
+        self._check(self.lib.rpw_segment(self._h, a.ctypes.data, len(a), a.shape[1] * 4, labels.ctypes.data, C.byref(st)))
+        return (labels, st) if want_stats else labels
+
+    def segment_batch(self, clouds, want_stats=False, labels_out=None):
+        arrs = [self._as_points(c) for c in clouds]
+        stride = arrs[0].shape[1]
+        if any(a.shape[1] != stride for a in arrs):
+            raise ValueError("all scans of a batch must share one stride")
+        B = len(arrs)
+        labels = labels_out if labels_out is not None else [np.empty(len(a), np.uint8) for a in arrs]
+        cp = (C.c_void_p * B)(*[a.ctypes.data for a in arrs])
+        lp = (C.c_void_p * B)(*[l.ctypes.data for l in labels])
+        ns = (C.c_size_t * B)(*[len(a) for a in arrs])
+        st = RpwStats()
+        self._check(self.lib.rpw_segment_batch(self._h, cp, ns, B, stride * 4, lp, C.byref(st)))
+        return (labels, st) if want_stats else labels
+
+    def segment_batch_async(self, ptrs, ns, stride_bytes, label_ptrs):
+        """Raw asynchronous form: arrays of host pointers (pinned), sizes; pair with wait()."""
+        B = len(ns)
+        cp = (C.c_void_p * B)(*ptrs)
+        lp = (C.c_void_p * B)(*label_ptrs)
+        na = (C.c_size_t * B)(*ns)
+        self._check(self.lib.rpw_segment_batch_async(self._h, cp, na, B, stride_bytes, lp))
+
+    def wait(self):
+        self._check(self.lib.rpw_wait(self._h, None))
+
+    def segment_clouds(self, points):
+        a = self._as_points(points)
+        n = len(a)
+        labels = np.empty(n, np.uint8)
+        g = np.empty((n, 3), np.float32)
+        ng = np.empty((n, 3), np.float32)
+        n_g, n_ng = C.c_size_t(), C.c_size_t()
+        self._check(self.lib.rpw_segment_clouds(self._h, a.ctypes.data, n, a.shape[1] * 4, labels.ctypes.data,
+                                                g.ctypes.data, C.byref(n_g), ng.ctypes.data, C.byref(n_ng)))
+        return g[:n_g.value], ng[:n_ng.value], labels
+
+    def segment_device(self, d_points_ptr: int, scan_offsets, d_labels_ptr: int):
+        off = np.ascontiguousarray(scan_offsets, dtype=np.uint64)
+        self._check(self.lib.rpw_segment_device(self._h, C.c_void_p(d_points_ptr), off.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                len(off) - 1, C.c_void_p(d_labels_ptr)))
+
+    # -- parity / debug --------------------------------------------------------------------
+    def debug_keys(self, n_total: int):
+        k = np.empty(n_total, np.uint16)
+        self._check(self.lib.rpw_debug_keys(self._h, k.ctypes.data, n_total))
+        return k
+
+    def enable_nodes(self, on=True):
+        self._check(self.lib.rpw_debug_enable_nodes(self._h, 1 if on else 0))
+
+    def debug_nodes(self):
+        cnt = C.c_size_t()
+        self._check(self.lib.rpw_debug_nodes(self._h, None, 0, C.byref(cnt)))
+        out = np.zeros(cnt.value, NODE_DTYPE)
+        if cnt.value:
+            self._check(self.lib.rpw_debug_nodes(self._h, out.ctypes.data, cnt.value, C.byref(cnt)))
+        return out
+
+    def debug_eig3(self, mats):
+        m = np.ascontiguousarray(mats, np.float32).reshape(-1, 9)
+        ev = np.empty((len(m), 3), np.float32)
+        vec = np.empty((len(m), 3, 3), np.float32)
+        self._check(self.lib.rpw_debug_eig3(self._h, m.ctypes.data, len(m), ev.ctypes.data, vec.ctypes.data))
+        return ev, vec
+
+    def debug_atan2(self, y, x):
+        y = np.ascontiguousarray(y, np.float32)
+        x = np.ascontiguousarray(x, np.float32)
+        out = np.empty_like(y)
+        self._check(self.lib.rpw_debug_atan2(self._h, y.ctypes.data, x.ctypes.data, y.size, out.ctypes.data))
+        return out
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.rpw_kernel_launches(self._h))

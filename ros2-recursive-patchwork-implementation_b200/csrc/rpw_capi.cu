@@ -1,0 +1,649 @@
+// csrc/rpw_capi.cu — host side of the C-ABI declared in include/rpw_b200.h: handle, buffers,
+// stream plumbing, host<->device copies and the launch sequence K1 -> K1b -> K2 -> K3.
+// There is no CPU fallback in this file or anywhere in the library: without a CUDA device
+// rpw_create fails, and every entry point reports CUDA errors instead of hiding them.
+#include "rpw_kernels.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace rpw;
+
+static thread_local std::string g_create_error;
+
+struct rpw_handle {
+    rpw_config cfg;
+    ZoneModel zm;
+    FitParams fp;
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    size_t cap_points = 0, cap_batch = 0;
+    int P = 0;
+    int levels_cap = 0;
+    uint32_t q_cap = 0;
+    int smem_cap = 0;
+    int fit_blocks = 0;
+    int wave_scans = 0;  // scans per launch group (0 = whole batch)
+
+    // device buffers
+    float* d_in = nullptr;       // staged input (12 or 16 bytes per point)
+    uint16_t* d_keys = nullptr;
+    uint8_t* d_labels = nullptr;
+    float4* d_sortedA = nullptr;
+    float4* d_bufB = nullptr;
+    float4* d_bufC = nullptr;
+    uint8_t* d_gmask = nullptr;
+    uint32_t* d_blk_hist = nullptr;
+    uint32_t* d_patch_start = nullptr;
+    float* d_root_mean = nullptr;
+    NodeRef* d_queue[2] = {nullptr, nullptr};
+    uint32_t* d_counters = nullptr;  // fetch_ctr[levels_cap] | q_count[levels_cap] | stats[8] | overflow | dbg_count
+    uint64_t* d_scan_off = nullptr;
+    uint32_t* d_chunk_base = nullptr;
+    rpw_node* d_dbg_nodes = nullptr;
+    uint32_t dbg_cap = 0;
+    bool dbg_enabled = false;
+
+    // host staging
+    uint64_t* h_meta = nullptr;  // pinned: scan_off[batch+1] then chunk_base[batch+1] (as u32)
+    void* h_stage_in = nullptr;  // pinned, lazily allocated, cap_points*16
+    uint8_t* h_stage_labels = nullptr;
+    uint32_t* h_stats = nullptr;  // pinned 8 words
+
+    // last call
+    std::vector<uint64_t> last_off;
+    size_t last_batch = 0;
+    size_t last_total = 0;
+    std::vector<const float*> pend_src;
+    std::vector<uint8_t*> pend_labels;
+    bool pend_labels_staged = false;
+    uint64_t launches = 0;
+    uint64_t launches_call = 0;
+    std::string err;
+};
+
+#define RPW_FAIL(h, code, ...)                                   \
+    do {                                                         \
+        char _b[512];                                            \
+        snprintf(_b, sizeof(_b), __VA_ARGS__);                   \
+        if (h) (h)->err = _b; else g_create_error = _b;          \
+        return code;                                             \
+    } while (0)
+
+#define RPW_CUDA(h, call)                                                                         \
+    do {                                                                                          \
+        cudaError_t _e = (call);                                                                  \
+        if (_e != cudaSuccess) RPW_FAIL(h, RPW_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" {
+
+int rpw_abi_version(void) { return RPW_ABI_VERSION; }
+
+void rpw_default_config(rpw_config* c) {
+    if (!c) return;
+    // defaults of PatchworkConfig, RP/include/recursive_patchwork.hpp:25-36
+    c->sensor_height = 1.2f;
+    c->max_range = 150.0f;
+    c->num_sectors = 10;
+    c->max_iter = 100;
+    c->adaptive_seed_height = 1;
+    c->th_seeds = 0.15f;
+    c->th_dist = 0.2f;
+    c->th_outlier = 0.08f;
+    c->filtering_radius = 150.0f;
+    c->max_split_depth = 1000;
+}
+
+int rpw_zone_model(const rpw_config* cfg, float* ring_edges9, float* sector_angle) {
+    if (!cfg || !ring_edges9 || !sector_angle) return RPW_ERR_BAD_ARG;
+    // RP/src/recursive_patchwork.cpp:344-352: powf on floats, sector angle in double rounded once.
+    const float r_min = 1.0f, r_max = cfg->filtering_radius;
+    for (int i = 0; i <= RPW_NUM_RINGS; ++i) ring_edges9[i] = r_min * powf(r_max / r_min, (float)i / RPW_NUM_RINGS);
+    *sector_angle = (float)((double)2.0f * 3.14159265358979323846 / (double)cfg->num_sectors);
+    return RPW_OK;
+}
+
+static int check_config(const rpw_config* c, std::string& why) {
+    if (c->num_sectors < 1 || c->num_sectors > kMaxSectors) { why = "num_sectors must be in [1, 128]"; return RPW_ERR_BAD_ARG; }
+    if (!(c->filtering_radius == c->filtering_radius)) { why = "filtering_radius is NaN"; return RPW_ERR_BAD_ARG; }
+    return RPW_OK;
+}
+
+static void apply_config(rpw_handle* h, const rpw_config* c) {
+    h->cfg = *c;
+    rpw_zone_model(c, h->zm.ring_edges, &h->zm.sector_angle);
+    h->zm.radius = c->filtering_radius;
+    h->zm.num_sectors = c->num_sectors;
+    h->zm.num_patches = RPW_NUM_RINGS * c->num_sectors;
+    h->fp.sensor_height = c->sensor_height;
+    h->fp.th_seeds = c->th_seeds;
+    h->fp.th_dist = c->th_dist;
+    h->fp.radius = c->filtering_radius;
+    h->fp.max_iter = c->max_iter;
+    h->fp.adaptive_seed_height = c->adaptive_seed_height;
+    h->fp.max_split_depth = c->max_split_depth;
+}
+
+static void free_patch_buffers(rpw_handle* h) {
+    cudaFree(h->d_blk_hist); h->d_blk_hist = nullptr;
+    cudaFree(h->d_patch_start); h->d_patch_start = nullptr;
+    cudaFree(h->d_root_mean); h->d_root_mean = nullptr;
+}
+
+static int alloc_patch_buffers(rpw_handle* h) {
+    const int P = RPW_NUM_RINGS * h->cfg.num_sectors;
+    h->P = P;
+    const size_t rows = h->cap_points / kBinChunk + h->cap_batch + 1;
+    RPW_CUDA(h, cudaMalloc(&h->d_blk_hist, rows * P * sizeof(uint32_t)));
+    RPW_CUDA(h, cudaMalloc(&h->d_patch_start, h->cap_batch * (size_t)(P + 1) * sizeof(uint32_t)));
+    RPW_CUDA(h, cudaMalloc(&h->d_root_mean, h->cap_batch * (size_t)P * sizeof(float)));
+    return RPW_OK;
+}
+
+static int alloc_level_buffers(rpw_handle* h) {
+    long long lv = (long long)h->cap_points / 10 + 1;
+    if (h->cfg.max_split_depth >= 0 && h->cfg.max_split_depth < lv) lv = h->cfg.max_split_depth;
+    if (lv < 0) lv = 0;
+    h->levels_cap = (int)lv + 4;
+    cudaFree(h->d_counters);
+    h->d_counters = nullptr;
+    const size_t words = (size_t)h->levels_cap * 2 + 16;
+    RPW_CUDA(h, cudaMalloc(&h->d_counters, words * sizeof(uint32_t)));
+    RPW_CUDA(h, cudaMemset(h->d_counters, 0, words * sizeof(uint32_t)));
+    return RPW_OK;
+}
+
+void rpw_destroy(rpw_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_in); cudaFree(h->d_keys); cudaFree(h->d_labels); cudaFree(h->d_sortedA); cudaFree(h->d_bufB);
+    cudaFree(h->d_bufC); cudaFree(h->d_gmask); cudaFree(h->d_queue[0]); cudaFree(h->d_queue[1]); cudaFree(h->d_counters);
+    cudaFree(h->d_scan_off); cudaFree(h->d_chunk_base); cudaFree(h->d_dbg_nodes);
+    free_patch_buffers(h);
+    if (h->h_meta) cudaFreeHost(h->h_meta);
+    if (h->h_stage_in) cudaFreeHost(h->h_stage_in);
+    if (h->h_stage_labels) cudaFreeHost(h->h_stage_labels);
+    if (h->h_stats) cudaFreeHost(h->h_stats);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+int rpw_create(const rpw_config* cfg, int device, size_t max_total_points, size_t max_batch, rpw_handle** out) {
+    if (!out) { g_create_error = "out is NULL"; return RPW_ERR_BAD_ARG; }
+    *out = nullptr;
+    rpw_config c;
+    if (cfg) c = *cfg; else rpw_default_config(&c);
+    std::string why;
+    if (check_config(&c, why) != RPW_OK) { g_create_error = why; return RPW_ERR_BAD_ARG; }
+    if (max_total_points == 0 || max_batch == 0) { g_create_error = "capacity must be non-zero"; return RPW_ERR_BAD_ARG; }
+    if (max_total_points >= 0xFFFF0000ull) { g_create_error = "max_total_points must be below 2^32 - 65536"; return RPW_ERR_BAD_ARG; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)";
+        return RPW_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "device index out of range"; return RPW_ERR_NO_DEVICE; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+        g_create_error = "device is not sm_100 (this library carries sm_100a code only)";
+        return RPW_ERR_NO_DEVICE;
+    }
+    if (!prop.cooperativeLaunch) { g_create_error = "device lacks cooperative launch"; return RPW_ERR_NO_DEVICE; }
+    rpw_handle* h = new (std::nothrow) rpw_handle();
+    if (!h) { g_create_error = "out of host memory"; return RPW_ERR_ALLOC; }
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    h->cap_points = max_total_points;
+    h->cap_batch = max_batch;
+    apply_config(h, &c);
+    int rc = RPW_OK;
+    auto fail = [&](int code) { g_create_error = h->err; rpw_destroy(h); return code; };
+#define TRY(x) do { rc = (x); if (rc != RPW_OK) return fail(rc); } while (0)
+#define TRYC(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(_e); return fail(_e == cudaErrorMemoryAllocation ? RPW_ERR_ALLOC : RPW_ERR_CUDA); } } while (0)
+    TRYC(cudaSetDevice(device));
+    TRYC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    const size_t N = max_total_points;
+    TRYC(cudaMalloc(&h->d_in, N * 16));
+    TRYC(cudaMalloc(&h->d_keys, N * sizeof(uint16_t)));
+    TRYC(cudaMalloc(&h->d_labels, N));
+    TRYC(cudaMalloc(&h->d_sortedA, N * sizeof(float4)));
+    TRYC(cudaMalloc(&h->d_bufB, N * sizeof(float4)));
+    TRYC(cudaMalloc(&h->d_bufC, N * sizeof(float4)));
+    TRYC(cudaMalloc(&h->d_gmask, N));
+    h->q_cap = (uint32_t)(N / 25 + 64);
+    TRYC(cudaMalloc(&h->d_queue[0], (size_t)h->q_cap * sizeof(NodeRef)));
+    TRYC(cudaMalloc(&h->d_queue[1], (size_t)h->q_cap * sizeof(NodeRef)));
+    TRYC(cudaMalloc(&h->d_scan_off, (max_batch + 1) * sizeof(uint64_t)));
+    TRYC(cudaMalloc(&h->d_chunk_base, (max_batch + 1) * sizeof(uint32_t)));
+    TRYC(cudaMallocHost(&h->h_meta, (max_batch + 1) * (sizeof(uint64_t) + sizeof(uint32_t)) + 64));
+    TRYC(cudaMallocHost(&h->h_stats, 16 * sizeof(uint32_t)));
+    TRY(alloc_patch_buffers(h));
+    TRY(alloc_level_buffers(h));
+    // shared-memory budget of the fit kernel: points a block keeps resident
+    int cap = 4096;
+    if (const char* s = getenv("RPW_FIT_SMEM_CAP")) { const int v = atoi(s); if (v >= 256 && v <= 16384) cap = v; }
+    if (const char* s = getenv("RPW_WAVE_SCANS")) { const int v = atoi(s); if (v >= 0) h->wave_scans = v; }
+    h->smem_cap = cap;
+    int bps = 0;
+    TRYC(fit_configure(cap, &bps));
+    if (bps < 1) { h->err = "fit kernel does not fit on an SM"; return fail(RPW_ERR_CUDA); }
+    h->fit_blocks = bps * h->num_sms;
+#undef TRY
+#undef TRYC
+    *out = h;
+    return RPW_OK;
+}
+
+int rpw_set_config(rpw_handle* h, const rpw_config* cfg) {
+    if (!h || !cfg) return RPW_ERR_BAD_ARG;
+    std::string why;
+    if (check_config(cfg, why) != RPW_OK) RPW_FAIL(h, RPW_ERR_BAD_ARG, "%s", why.c_str());
+    RPW_CUDA(h, cudaSetDevice(h->device));
+    RPW_CUDA(h, cudaStreamSynchronize(h->stream));
+    const bool sectors_changed = cfg->num_sectors != h->cfg.num_sectors;
+    const bool depth_changed = cfg->max_split_depth != h->cfg.max_split_depth;
+    apply_config(h, cfg);
+    if (sectors_changed) {
+        free_patch_buffers(h);
+        int rc = alloc_patch_buffers(h);
+        if (rc != RPW_OK) return rc;
+    }
+    if (depth_changed) {
+        int rc = alloc_level_buffers(h);
+        if (rc != RPW_OK) return rc;
+    }
+    return RPW_OK;
+}
+
+int rpw_get_config(const rpw_handle* h, rpw_config* out) {
+    if (!h || !out) return RPW_ERR_BAD_ARG;
+    *out = h->cfg;
+    return RPW_OK;
+}
+
+int rpw_set_stream(rpw_handle* h, void* cuda_stream) {
+    if (!h) return RPW_ERR_BAD_ARG;
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return RPW_OK;
+}
+
+const char* rpw_last_error(const rpw_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+uint64_t rpw_kernel_launches(const rpw_handle* h) { return h ? h->launches : 0; }
+
+void* rpw_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void rpw_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// launch sequence
+// ---------------------------------------------------------------------------------------------
+// Fills the pinned meta block (scan offsets, chunk bases), uploads it if it changed.
+static int upload_meta(rpw_handle* h, const uint64_t* off, size_t batch) {
+    if (batch == 0 || batch > h->cap_batch) RPW_FAIL(h, RPW_ERR_CAPACITY, "batch %zu exceeds the handle's max_batch %zu", batch, h->cap_batch);
+    if (off[batch] - off[0] > h->cap_points) RPW_FAIL(h, RPW_ERR_CAPACITY, "%llu points exceed the handle's capacity %zu", (unsigned long long)(off[batch] - off[0]), h->cap_points);
+    const bool same = h->last_batch == batch && h->last_off.size() == batch + 1 && memcmp(h->last_off.data(), off, (batch + 1) * sizeof(uint64_t)) == 0;
+    if (same) return RPW_OK;
+    // the previous call's asynchronous upload may still be reading h_meta
+    RPW_CUDA(h, cudaStreamSynchronize(h->stream));
+    uint64_t* so = h->h_meta;
+    uint32_t* cb = reinterpret_cast<uint32_t*>(h->h_meta + (h->cap_batch + 1));
+    uint32_t run = 0;
+    for (size_t i = 0; i <= batch; ++i) {
+        so[i] = off[i] - off[0];
+        cb[i] = run;
+        if (i < batch) {
+            if (off[i + 1] < off[i]) RPW_FAIL(h, RPW_ERR_BAD_ARG, "scan offsets must be non-decreasing");
+            run += (uint32_t)((off[i + 1] - off[i] + kBinChunk - 1) / kBinChunk);
+        }
+    }
+    RPW_CUDA(h, cudaMemcpyAsync(h->d_scan_off, so, (batch + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+    RPW_CUDA(h, cudaMemcpyAsync(h->d_chunk_base, cb, (batch + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    h->last_off.assign(so, so + batch + 1);
+    h->last_batch = batch;
+    h->last_total = (size_t)so[batch];
+    return RPW_OK;
+}
+
+// Enqueues K1..K3 for scans [0, batch) whose points are device resident at `d_pts`.
+static int run_pipeline(rpw_handle* h, const float* d_pts, int stride_floats, uint8_t* d_labels, size_t batch) {
+    const uint64_t* so = h->last_off.data();
+    const size_t wave = h->wave_scans > 0 ? (size_t)h->wave_scans : batch;
+    h->launches_call = 0;
+    // stats[0] (levels) and stats[3] (nodes) accumulate over the call's launch groups
+    RPW_CUDA(h, cudaMemsetAsync(h->d_counters + 2 * (size_t)h->levels_cap, 0, sizeof(uint32_t), h->stream));
+    RPW_CUDA(h, cudaMemsetAsync(h->d_counters + 2 * (size_t)h->levels_cap + 3, 0, sizeof(uint32_t), h->stream));
+    for (size_t b0 = 0; b0 < batch; b0 += wave) {
+        const size_t nb = (b0 + wave <= batch) ? wave : batch - b0;
+        uint64_t max_n = 0;
+        for (size_t i = b0; i < b0 + nb; ++i) max_n = so[i + 1] - so[i] > max_n ? so[i + 1] - so[i] : max_n;
+        if (so[b0 + nb] == so[b0]) continue;  // nothing but empty scans
+        const int max_chunks = (int)((max_n + kBinChunk - 1) / kBinChunk);
+        // The kernels index scans relative to the pointers they are given.
+        const uint64_t* d_so = h->d_scan_off + b0;
+        const uint32_t* d_cb = h->d_chunk_base + b0;
+        RPW_CUDA(h, launch_bin(h->stream, stride_floats, d_pts, d_so, d_cb, h->zm, h->d_keys, d_labels, h->d_blk_hist, max_chunks, (int)nb));
+        RPW_CUDA(h, launch_offsets(h->stream, d_so, d_cb, h->d_blk_hist, h->d_patch_start + b0 * (size_t)(h->P + 1), h->P, (int)nb));
+        RPW_CUDA(h, launch_scatter(h->stream, stride_floats, d_pts, d_so, d_cb, h->d_keys, h->d_blk_hist,
+                                   h->d_patch_start + b0 * (size_t)(h->P + 1), h->d_sortedA, h->P, max_chunks, (int)nb));
+        FitArgs A;
+        A.sortedA = h->d_sortedA; A.bufB = h->d_bufB; A.bufC = h->d_bufC; A.gmask = h->d_gmask;
+        A.labels = d_labels;
+        A.patch_start = h->d_patch_start + b0 * (size_t)(h->P + 1);
+        A.root_mean = h->d_root_mean + b0 * (size_t)h->P;
+        A.queue[0] = h->d_queue[0]; A.queue[1] = h->d_queue[1];
+        A.fetch_ctr = h->d_counters;
+        A.q_count = h->d_counters + h->levels_cap;
+        A.stats = h->d_counters + 2 * (size_t)h->levels_cap;
+        A.overflow = A.stats + 8;
+        A.dbg_nodes = h->dbg_enabled ? h->d_dbg_nodes : nullptr;
+        A.dbg_count = A.stats + 9;
+        A.dbg_cap = h->dbg_cap;
+        A.q_cap = h->q_cap;
+        A.n_roots = (int)(nb * (size_t)h->P);
+        A.P = h->P;
+        A.smem_cap = h->smem_cap;
+        A.fp = h->fp;
+        A.scan_base = (uint32_t)b0;
+        RPW_CUDA(h, launch_fit(h->stream, A, h->fit_blocks));
+        h->launches += 4;
+        h->launches_call += 4;
+    }
+    return RPW_OK;
+}
+
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+static int ensure_stage(rpw_handle* h) {
+    if (!h->h_stage_in) RPW_CUDA(h, cudaMallocHost(&h->h_stage_in, h->cap_points * 16));
+    if (!h->h_stage_labels) RPW_CUDA(h, cudaMallocHost(&h->h_stage_labels, h->cap_points));
+    return RPW_OK;
+}
+
+static int reset_dbg(rpw_handle* h) {
+    if (h->dbg_enabled) RPW_CUDA(h, cudaMemsetAsync(h->d_counters + 2 * (size_t)h->levels_cap + 9, 0, sizeof(uint32_t), h->stream));
+    return RPW_OK;
+}
+
+static int fill_stats(rpw_handle* h, rpw_stats* st, uint8_t* const* labels, const size_t* n, size_t batch) {
+    if (!st) return RPW_OK;
+    memset(st, 0, sizeof(*st));
+    RPW_CUDA(h, cudaMemcpyAsync(h->h_stats, h->d_counters + 2 * (size_t)h->levels_cap, 10 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    RPW_CUDA(h, cudaStreamSynchronize(h->stream));
+    st->n_levels = h->h_stats[0];
+    st->n_nodes = h->h_stats[3];
+    st->kernel_launches = h->launches_call;
+    if (h->h_stats[8]) {
+        cudaMemsetAsync(h->d_counters + 2 * (size_t)h->levels_cap + 8, 0, sizeof(uint32_t), h->stream);
+        RPW_FAIL(h, RPW_ERR_CAPACITY, "device worklist overflowed (q_cap %u)", h->q_cap);
+    }
+    uint64_t cnt[4] = {0, 0, 0, 0};
+    for (size_t b = 0; b < batch; ++b) {
+        const uint8_t* l = labels[b];
+        for (size_t i = 0; i < n[b]; ++i) cnt[l[i] & 3]++;
+        st->n_points += n[b];
+    }
+    st->n_nonground = cnt[0]; st->n_ground = cnt[1]; st->n_beyond = cnt[2]; st->n_dropped = cnt[3];
+    return RPW_OK;
+}
+
+extern "C" {
+
+int rpw_segment_batch_async(rpw_handle* h, const float* const* clouds, const size_t* n, size_t batch, size_t stride_bytes,
+                            uint8_t* const* labels_out) {
+    if (!h) return RPW_ERR_BAD_ARG;
+    if (!clouds || !n || !labels_out || batch == 0) RPW_FAIL(h, RPW_ERR_BAD_ARG, "NULL argument or empty batch");
+    if (stride_bytes != 12 && stride_bytes != 16) RPW_FAIL(h, RPW_ERR_BAD_ARG, "stride_bytes must be 12 (xyz) or 16 (xyzw), got %zu", stride_bytes);
+    RPW_CUDA(h, cudaSetDevice(h->device));
+    std::vector<uint64_t> off(batch + 1);
+    off[0] = 0;
+    for (size_t b = 0; b < batch; ++b) {
+        if (n[b] && (!clouds[b] || !labels_out[b])) RPW_FAIL(h, RPW_ERR_BAD_ARG, "scan %zu has a NULL buffer", b);
+        off[b + 1] = off[b] + n[b];
+    }
+    if (batch > h->cap_batch) RPW_FAIL(h, RPW_ERR_CAPACITY, "batch %zu exceeds the handle's max_batch %zu", batch, h->cap_batch);
+    if (off[batch] > h->cap_points) RPW_FAIL(h, RPW_ERR_CAPACITY, "%llu points exceed the handle's capacity %zu", (unsigned long long)off[batch], h->cap_points);
+    if (off[batch] == 0) { h->last_batch = 0; h->last_total = 0; h->last_off.clear(); h->pend_labels.clear(); return RPW_OK; }
+    int rc = upload_meta(h, off.data(), batch);
+    if (rc != RPW_OK) return rc;
+    rc = reset_dbg(h);
+    if (rc != RPW_OK) return rc;
+    // H2D: one copy per run of scans that are contiguous in host memory
+    char* d_in = reinterpret_cast<char*>(h->d_in);
+    for (size_t b = 0; b < batch;) {
+        size_t e = b + 1;
+        const char* base = reinterpret_cast<const char*>(clouds[b]);
+        while (e < batch && reinterpret_cast<const char*>(clouds[e]) == base + (off[e] - off[b]) * stride_bytes) ++e;
+        const size_t bytes = (size_t)(off[e] - off[b]) * stride_bytes;
+        if (bytes) RPW_CUDA(h, cudaMemcpyAsync(d_in + off[b] * stride_bytes, base, bytes, cudaMemcpyHostToDevice, h->stream));
+        b = e;
+    }
+    rc = run_pipeline(h, h->d_in, (int)(stride_bytes / 4), h->d_labels, batch);
+    if (rc != RPW_OK) return rc;
+    for (size_t b = 0; b < batch;) {
+        size_t e = b + 1;
+        while (e < batch && labels_out[e] == labels_out[b] + (off[e] - off[b])) ++e;
+        const size_t bytes = (size_t)(off[e] - off[b]);
+        if (bytes) RPW_CUDA(h, cudaMemcpyAsync(labels_out[b], h->d_labels + off[b], bytes, cudaMemcpyDeviceToHost, h->stream));
+        b = e;
+    }
+    h->pend_labels.assign(labels_out, labels_out + batch);
+    return RPW_OK;
+}
+
+int rpw_wait(rpw_handle* h, rpw_stats* stats) {
+    if (!h) return RPW_ERR_BAD_ARG;
+    RPW_CUDA(h, cudaSetDevice(h->device));
+    RPW_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (stats) {
+        if (h->last_batch == 0) { memset(stats, 0, sizeof(*stats)); return RPW_OK; }
+        std::vector<size_t> n(h->last_batch);
+        for (size_t b = 0; b < h->last_batch; ++b) n[b] = (size_t)(h->last_off[b + 1] - h->last_off[b]);
+        if (h->pend_labels.size() != h->last_batch) RPW_FAIL(h, RPW_ERR_BAD_ARG, "no host labels pending for stats");
+        return fill_stats(h, stats, h->pend_labels.data(), n.data(), h->last_batch);
+    }
+    return RPW_OK;
+}
+
+int rpw_segment_batch(rpw_handle* h, const float* const* clouds, const size_t* n, size_t batch, size_t stride_bytes,
+                      uint8_t* const* labels_out, rpw_stats* stats) {
+    if (!h) return RPW_ERR_BAD_ARG;
+    if (!clouds || !n || !labels_out || batch == 0) RPW_FAIL(h, RPW_ERR_BAD_ARG, "NULL argument or empty batch");
+    if (stride_bytes != 12 && stride_bytes != 16) RPW_FAIL(h, RPW_ERR_BAD_ARG, "stride_bytes must be 12 (xyz) or 16 (xyzw), got %zu", stride_bytes);
+    RPW_CUDA(h, cudaSetDevice(h->device));
+    size_t total = 0;
+    for (size_t b = 0; b < batch; ++b) total += n[b];
+    if (batch > h->cap_batch) RPW_FAIL(h, RPW_ERR_CAPACITY, "batch %zu exceeds the handle's max_batch %zu", batch, h->cap_batch);
+    if (total > h->cap_points) RPW_FAIL(h, RPW_ERR_CAPACITY, "%zu points exceed the handle's capacity %zu", total, h->cap_points);
+    // Pageable host memory is staged through the handle's pinned buffers so that the DMA engine
+    // can run at full rate; pinned caller buffers are used in place.
+    // (only the first non-empty scan is probed: a pageable buffer handed to cudaMemcpyAsync is
+    // still copied correctly, just not at full rate)
+    bool all_pinned = true, probed = false;
+    for (size_t b = 0; b < batch; ++b) {
+        if (n[b] && (!clouds[b] || !labels_out[b])) RPW_FAIL(h, RPW_ERR_BAD_ARG, "scan %zu has a NULL buffer", b);
+        if (n[b] && !probed) { all_pinned = is_pinned(clouds[b]) && is_pinned(labels_out[b]); probed = true; }
+    }
+    int rc;
+    if (all_pinned) {
+        rc = rpw_segment_batch_async(h, clouds, n, batch, stride_bytes, labels_out);
+        if (rc != RPW_OK) return rc;
+        RPW_CUDA(h, cudaStreamSynchronize(h->stream));
+    } else {
+        rc = ensure_stage(h);
+        if (rc != RPW_OK) return rc;
+        RPW_CUDA(h, cudaStreamSynchronize(h->stream));
+        std::vector<const float*> src(batch);
+        std::vector<uint8_t*> dst(batch);
+        size_t o = 0;
+        for (size_t b = 0; b < batch; ++b) {
+            char* s = reinterpret_cast<char*>(h->h_stage_in) + o * stride_bytes;
+            if (n[b]) memcpy(s, clouds[b], n[b] * stride_bytes);
+            src[b] = reinterpret_cast<const float*>(s);
+            dst[b] = h->h_stage_labels + o;
+            o += n[b];
+        }
+        rc = rpw_segment_batch_async(h, src.data(), n, batch, stride_bytes, dst.data());
+        if (rc != RPW_OK) return rc;
+        RPW_CUDA(h, cudaStreamSynchronize(h->stream));
+        for (size_t b = 0; b < batch; ++b) if (n[b]) memcpy(labels_out[b], dst[b], n[b]);
+    }
+    h->pend_labels.assign(labels_out, labels_out + batch);
+    if (total == 0) { if (stats) memset(stats, 0, sizeof(*stats)); return RPW_OK; }
+    return fill_stats(h, stats, labels_out, n, batch);
+}
+
+int rpw_segment(rpw_handle* h, const float* xyz, size_t n, size_t stride_bytes, uint8_t* labels_out, rpw_stats* stats) {
+    if (!h) return RPW_ERR_BAD_ARG;
+    if (n == 0) {  // empty cloud -> empty clouds (RP/src/recursive_patchwork.cpp:316-318)
+        if (stats) memset(stats, 0, sizeof(*stats));
+        return RPW_OK;
+    }
+    const float* c[1] = {xyz};
+    uint8_t* l[1] = {labels_out};
+    return rpw_segment_batch(h, c, &n, 1, stride_bytes, l, stats);
+}
+
+int rpw_segment_clouds(rpw_handle* h, const float* xyz, size_t n, size_t stride_bytes, uint8_t* labels_out,
+                       float* ground_xyz, size_t* n_ground, float* nonground_xyz, size_t* n_nonground) {
+    if (!h) return RPW_ERR_BAD_ARG;
+    if (n_ground) *n_ground = 0;
+    if (n_nonground) *n_nonground = 0;
+    if (n == 0) return RPW_OK;
+    std::vector<uint8_t> tmp;
+    uint8_t* lab = labels_out;
+    if (!lab) { tmp.resize(n); lab = tmp.data(); }
+    int rc = rpw_segment(h, xyz, n, stride_bytes, lab, nullptr);
+    if (rc != RPW_OK) return rc;
+    // Cloud assembly in the reference's order (RP/src/recursive_patchwork.cpp:402-419): ground in
+    // input order; non-ground in input order, then the beyond-radius points in input order.
+    const size_t sf = stride_bytes / 4;
+    size_t g = 0, ng = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const float* p = xyz + i * sf;
+        if (lab[i] == RPW_LABEL_GROUND) { if (ground_xyz) { ground_xyz[3 * g] = p[0]; ground_xyz[3 * g + 1] = p[1]; ground_xyz[3 * g + 2] = p[2]; } ++g; }
+        else if (lab[i] == RPW_LABEL_NONGROUND) { if (nonground_xyz) { nonground_xyz[3 * ng] = p[0]; nonground_xyz[3 * ng + 1] = p[1]; nonground_xyz[3 * ng + 2] = p[2]; } ++ng; }
+    }
+    for (size_t i = 0; i < n; ++i) {
+        if (lab[i] != RPW_LABEL_BEYOND) continue;
+        const float* p = xyz + i * sf;
+        if (nonground_xyz) { nonground_xyz[3 * ng] = p[0]; nonground_xyz[3 * ng + 1] = p[1]; nonground_xyz[3 * ng + 2] = p[2]; }
+        ++ng;
+    }
+    if (n_ground) *n_ground = g;
+    if (n_nonground) *n_nonground = ng;
+    return RPW_OK;
+}
+
+int rpw_segment_device(rpw_handle* h, const void* d_points, const uint64_t* scan_offsets, size_t batch, void* d_labels) {
+    if (!h) return RPW_ERR_BAD_ARG;
+    if (!d_points || !scan_offsets || !d_labels || batch == 0) RPW_FAIL(h, RPW_ERR_BAD_ARG, "NULL argument or empty batch");
+    RPW_CUDA(h, cudaSetDevice(h->device));
+    int rc = upload_meta(h, scan_offsets, batch);
+    if (rc != RPW_OK) return rc;
+    if (h->last_total == 0) return RPW_OK;
+    rc = reset_dbg(h);
+    if (rc != RPW_OK) return rc;
+    h->pend_labels.clear();
+    const float* pts = reinterpret_cast<const float*>(d_points) + scan_offsets[0] * 4;
+    return run_pipeline(h, pts, 4, reinterpret_cast<uint8_t*>(d_labels) + scan_offsets[0], batch);
+}
+
+int rpw_debug_keys(rpw_handle* h, uint16_t* keys_out, size_t n_total) {
+    if (!h || !keys_out) return RPW_ERR_BAD_ARG;
+    if (n_total > h->last_total) RPW_FAIL(h, RPW_ERR_BAD_ARG, "last call had %zu points", h->last_total);
+    RPW_CUDA(h, cudaSetDevice(h->device));
+    RPW_CUDA(h, cudaMemcpyAsync(keys_out, h->d_keys, n_total * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->stream));
+    RPW_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RPW_OK;
+}
+
+int rpw_debug_enable_nodes(rpw_handle* h, int enable) {
+    if (!h) return RPW_ERR_BAD_ARG;
+    RPW_CUDA(h, cudaSetDevice(h->device));
+    if (enable && !h->d_dbg_nodes) {
+        size_t cap = h->cap_points / 8 + h->cap_batch * (size_t)h->P * 2 + 1024;
+        if (cap > (1u << 22)) cap = 1u << 22;
+        RPW_CUDA(h, cudaMalloc(&h->d_dbg_nodes, cap * sizeof(rpw_node)));
+        h->dbg_cap = (uint32_t)cap;
+    }
+    h->dbg_enabled = enable != 0;
+    return RPW_OK;
+}
+
+int rpw_debug_nodes(rpw_handle* h, rpw_node* out, size_t cap, size_t* count) {
+    if (!h || !count) return RPW_ERR_BAD_ARG;
+    if (!h->dbg_enabled) RPW_FAIL(h, RPW_ERR_BAD_ARG, "node recording is not enabled");
+    RPW_CUDA(h, cudaSetDevice(h->device));
+    uint32_t c = 0;
+    RPW_CUDA(h, cudaMemcpyAsync(&c, h->d_counters + 2 * (size_t)h->levels_cap + 9, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    RPW_CUDA(h, cudaStreamSynchronize(h->stream));
+    *count = c;
+    size_t take = c < h->dbg_cap ? c : h->dbg_cap;
+    if (take > cap) take = cap;
+    if (out && take) {
+        RPW_CUDA(h, cudaMemcpyAsync(out, h->d_dbg_nodes, take * sizeof(rpw_node), cudaMemcpyDeviceToHost, h->stream));
+        RPW_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    return RPW_OK;
+}
+
+int rpw_debug_eig3(rpw_handle* h, const float* mats, size_t count, float* evals, float* evecs) {
+    if (!h || !mats || !evals || !evecs) return RPW_ERR_BAD_ARG;
+    if (count == 0) return RPW_OK;
+    RPW_CUDA(h, cudaSetDevice(h->device));
+    float *dm = nullptr, *dv = nullptr, *dq = nullptr;
+    RPW_CUDA(h, cudaMalloc(&dm, count * 9 * sizeof(float)));
+    RPW_CUDA(h, cudaMalloc(&dv, count * 3 * sizeof(float)));
+    RPW_CUDA(h, cudaMalloc(&dq, count * 9 * sizeof(float)));
+    RPW_CUDA(h, cudaMemcpyAsync(dm, mats, count * 9 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    RPW_CUDA(h, launch_eig3(h->stream, dm, count, dv, dq));
+    h->launches++;
+    RPW_CUDA(h, cudaMemcpyAsync(evals, dv, count * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    RPW_CUDA(h, cudaMemcpyAsync(evecs, dq, count * 9 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    RPW_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(dm); cudaFree(dv); cudaFree(dq);
+    return RPW_OK;
+}
+
+int rpw_debug_atan2(rpw_handle* h, const float* y, const float* x, size_t count, float* out) {
+    if (!h || !y || !x || !out) return RPW_ERR_BAD_ARG;
+    if (count == 0) return RPW_OK;
+    RPW_CUDA(h, cudaSetDevice(h->device));
+    float *dy = nullptr, *dx = nullptr, *dout = nullptr;
+    RPW_CUDA(h, cudaMalloc(&dy, count * sizeof(float)));
+    RPW_CUDA(h, cudaMalloc(&dx, count * sizeof(float)));
+    RPW_CUDA(h, cudaMalloc(&dout, count * sizeof(float)));
+    RPW_CUDA(h, cudaMemcpyAsync(dy, y, count * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    RPW_CUDA(h, cudaMemcpyAsync(dx, x, count * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    RPW_CUDA(h, launch_atan2(h->stream, dy, dx, count, dout));
+    h->launches++;
+    RPW_CUDA(h, cudaMemcpyAsync(out, dout, count * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    RPW_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(dy); cudaFree(dx); cudaFree(dout);
+    return RPW_OK;
+}
+
+}  // extern "C"

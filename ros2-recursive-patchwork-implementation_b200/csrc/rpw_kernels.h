@@ -1,0 +1,58 @@
+// csrc/rpw_kernels.h — interface between the kernels (rpw_kernels.cu) and the C-ABI host code
+// (rpw_capi.cu).  Internal; the public boundary is include/rpw_b200.h.
+#pragma once
+
+#include "rpw_b200.h"
+#include "rpw_device.cuh"
+
+namespace rpw {
+
+typedef rpw_node rpw_node_rec;
+
+// One fitPlaneAndSplit node on the device worklist: a contiguous run of its level's point buffer.
+struct __align__(16) NodeRef {
+    uint32_t start;  // first slot (global index into the sorted / partition buffers)
+    uint32_t n;
+    uint32_t root;   // scan * P + patch
+    uint32_t pad;
+};
+
+struct FitArgs {
+    const float4* sortedA;     // level 0: (x, y, z, bits of global input index), patch-major, input order inside a patch
+    float4* bufB;              // odd levels: partitioned children (x, y, z, -)
+    float4* bufC;              // even levels >= 2
+    uint8_t* gmask;            // per-slot mask scratch for nodes that do not fit in shared memory
+    uint8_t* labels;           // per input point
+    const uint32_t* patch_start;  // [batch][P + 1]
+    float* root_mean;          // [batch * P] mean range of the root patch (Q4)
+    NodeRef* queue[2];         // next-level queues, ping-pong by level parity
+    uint32_t* q_count;         // [levels_cap] nodes enqueued for level l
+    uint32_t* fetch_ctr;       // [levels_cap] dynamic fetch cursor of level l
+    uint32_t* stats;           // [0] levels run (out) [1] nodes processed (accumulator) [2] block arrival [3] nodes (out)
+    uint32_t* overflow;        // set if a queue would overflow
+    rpw_node_rec* dbg_nodes;   // optional
+    uint32_t* dbg_count;
+    uint32_t dbg_cap;
+    uint32_t q_cap;
+    int n_roots;               // batch * P
+    int P;
+    int smem_cap;              // points a block can hold in shared memory
+    uint32_t scan_base;        // index of the launch group's first scan inside the call's batch (debug records)
+    FitParams fp;
+};
+
+size_t fit_smem_bytes(int smem_cap);
+cudaError_t fit_configure(int smem_cap, int* blocks_per_sm);
+
+cudaError_t launch_bin(cudaStream_t st, int stride_floats, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
+                       const ZoneModel& zm, uint16_t* keys, uint8_t* labels, uint32_t* blk_hist, int max_chunks, int batch);
+cudaError_t launch_offsets(cudaStream_t st, const uint64_t* scan_off, const uint32_t* chunk_base, uint32_t* blk_hist,
+                           uint32_t* patch_start, int P, int batch);
+cudaError_t launch_scatter(cudaStream_t st, int stride_floats, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
+                           const uint16_t* keys, const uint32_t* blk_hist, const uint32_t* patch_start, float4* sorted, int P,
+                           int max_chunks, int batch);
+cudaError_t launch_fit(cudaStream_t st, const FitArgs& args, int grid_blocks);
+cudaError_t launch_eig3(cudaStream_t st, const float* mats, size_t count, float* evals, float* evecs);
+cudaError_t launch_atan2(cudaStream_t st, const float* y, const float* x, size_t count, float* out);
+
+}  // namespace rpw
