@@ -179,6 +179,19 @@ int rpw_debug_eig3(rpw_handle* h, const float* mats, size_t count, float* evals,
 /* Runs the device restatement of libm atan2f on `count` (y, x) pairs. */
 int rpw_debug_atan2(rpw_handle* h, const float* y, const float* x, size_t count, float* out);
 
+/* ---- measurement -------------------------------------------------------------------------- */
+/* Device time per kernel, measured with CUDA events recorded on the handle's stream around every
+ * launch (bench.py's roofline numbers).  Kernel ids: 0 bin, 1 offsets, 2 scatter, 3 fit. */
+#define RPW_PROF_KERNELS 4
+typedef struct rpw_profile {
+    double ms[RPW_PROF_KERNELS];          /* accumulated since rpw_profile_enable */
+    uint64_t launches[RPW_PROF_KERNELS];
+    uint32_t fit_grid_blocks;             /* persistent grid of the fit kernel */
+    uint32_t fit_smem_points;             /* points a fit block keeps in shared memory */
+} rpw_profile;
+int rpw_profile_enable(rpw_handle* h, int enable); /* also resets the accumulators */
+int rpw_profile_read(rpw_handle* h, rpw_profile* out);
+
 /* ---- utilities --------------------------------------------------------------------------- */
 void* rpw_host_alloc(size_t bytes); /* pinned host memory (NULL on failure) */
 void rpw_host_free(void* p);

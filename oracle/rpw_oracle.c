@@ -280,6 +280,28 @@ float rpwo_atan2f_restated(float y, float x) {
     }
 }
 
+/* Counts inputs on which the restatement and the host libm disagree bitwise.  Inputs: xorshift64
+ * stream from `seed`; two thirds uniform in [-range, range]^2 (the coordinates a scan has), one
+ * third arbitrary finite bit patterns. */
+uint64_t rpwo_atan2f_selfcheck(uint64_t n, uint64_t seed, float range) {
+    uint64_t s = seed ? seed : 88172645463325252ULL, bad = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+        float x = (float)((int32_t)(s & 0xffffff) - 0x800000) * (range / 8388608.0f);
+        s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+        float y = (float)((int32_t)(s & 0xffffff) - 0x800000) * (range / 8388608.0f);
+        if (i % 3 == 1) {
+            x = i2f((int32_t)(s >> 32));
+            s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+            y = i2f((int32_t)(s >> 32));
+            if (!isfinite(x) || !isfinite(y)) continue;
+        }
+        const float a = atan2f(y, x), b = rpwo_atan2f_restated(y, x);
+        if (f2i(a) != f2i(b)) bad++;
+    }
+    return bad;
+}
+
 /* ------------------------------------------------------------------------------------------
  * fitPlanePCA, RP/src/recursive_patchwork.cpp:77-107
  * ---------------------------------------------------------------------------------------- */

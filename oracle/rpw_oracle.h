@@ -99,6 +99,7 @@ int rpwo_eig3_f32(const float a[9], float evals[3], float evecs[9]);
 /* glibc-2.39 atan2f restated in IEEE float operations (see rpw_oracle.c); used to prove that
  * the device's sector angle can be made bit-identical to the host libm's. */
 float rpwo_atan2f_restated(float y, float x);
+uint64_t rpwo_atan2f_selfcheck(uint64_t n, uint64_t seed, float range);
 
 /* seconds per call over `reps` calls (wall clock); labels only. */
 double rpwo_time_scan(const rpwo_config* cfg, const float* xyz, size_t n, size_t stride, int reps);

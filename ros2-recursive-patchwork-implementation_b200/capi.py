@@ -32,6 +32,13 @@ class RpwStats(C.Structure):
                 ("n_nodes", C.c_uint32), ("kernel_launches", C.c_uint64)]
 
 
+class RpwProfile(C.Structure):
+    _fields_ = [("ms", C.c_double * 4), ("launches", C.c_uint64 * 4), ("fit_grid_blocks", C.c_uint32),
+                ("fit_smem_points", C.c_uint32)]
+
+
+PROF_KERNELS = ("bin", "offsets", "scatter", "fit")
+
 NODE_DTYPE = np.dtype([("scan", "<i4"), ("root", "<i4"), ("depth", "<i4"), ("start", "<i4"), ("n", "<i4"),
                        ("outcome", "<i4"), ("iters", "<i4"), ("n_inliers", "<i4"), ("split_axis", "<i4"),
                        ("centroid", "<f4", 3), ("normal", "<f4", 3), ("residual", "<f4"), ("median", "<f4"),
@@ -41,7 +48,7 @@ NODE_DTYPE = np.dtype([("scan", "<i4"), ("root", "<i4"), ("depth", "<i4"), ("sta
 EXPORTS = ["rpw_default_config", "rpw_zone_model", "rpw_create", "rpw_destroy", "rpw_set_config", "rpw_get_config",
            "rpw_set_stream", "rpw_last_error", "rpw_segment", "rpw_segment_batch", "rpw_segment_batch_async", "rpw_wait",
            "rpw_segment_clouds", "rpw_segment_device", "rpw_debug_keys", "rpw_debug_enable_nodes", "rpw_debug_nodes",
-           "rpw_debug_eig3", "rpw_debug_atan2", "rpw_host_alloc", "rpw_host_free", "rpw_kernel_launches", "rpw_abi_version"]
+           "rpw_debug_eig3", "rpw_debug_atan2", "rpw_profile_enable", "rpw_profile_read", "rpw_host_alloc", "rpw_host_free", "rpw_kernel_launches", "rpw_abi_version"]
 
 _lib = None
 
@@ -84,6 +91,8 @@ def load_library() -> C.CDLL:
     lib.rpw_debug_nodes.argtypes = [vp, vp, sz, C.POINTER(sz)]; lib.rpw_debug_nodes.restype = C.c_int
     lib.rpw_debug_eig3.argtypes = [vp, vp, sz, vp, vp]; lib.rpw_debug_eig3.restype = C.c_int
     lib.rpw_debug_atan2.argtypes = [vp, vp, vp, sz, vp]; lib.rpw_debug_atan2.restype = C.c_int
+    lib.rpw_profile_enable.argtypes = [vp, C.c_int]; lib.rpw_profile_enable.restype = C.c_int
+    lib.rpw_profile_read.argtypes = [vp, C.POINTER(RpwProfile)]; lib.rpw_profile_read.restype = C.c_int
     lib.rpw_host_alloc.argtypes = [sz]; lib.rpw_host_alloc.restype = vp
     lib.rpw_host_free.argtypes = [vp]; lib.rpw_host_free.restype = None
     lib.rpw_kernel_launches.argtypes = [vp]; lib.rpw_kernel_launches.restype = C.c_uint64
@@ -256,6 +265,17 @@ class Handle:
         x = np.ascontiguousarray(x, np.float32)
         out = np.empty_like(y)
         self._check(self.lib.rpw_debug_atan2(self._h, y.ctypes.data, x.ctypes.data, y.size, out.ctypes.data))
+        return out
+
+    def profile_enable(self, on=True):
+        self._check(self.lib.rpw_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self) -> dict:
+        p = RpwProfile()
+        self._check(self.lib.rpw_profile_read(self._h, C.byref(p)))
+        out = {k: dict(ms=p.ms[i], launches=int(p.launches[i])) for i, k in enumerate(PROF_KERNELS)}
+        out["fit_grid_blocks"] = int(p.fit_grid_blocks)
+        out["fit_smem_points"] = int(p.fit_smem_points)
         return out
 
     def kernel_launches(self) -> int:

@@ -44,6 +44,8 @@ struct rpw_handle {
     uint32_t* d_blk_hist = nullptr;
     uint32_t* d_patch_start = nullptr;
     float* d_root_mean = nullptr;
+    uint32_t* d_patch_total = nullptr;  // [P] batch-wide points per patch
+    uint32_t* d_patch_order = nullptr;  // [P] patches, largest first
     NodeRef* d_queue[2] = {nullptr, nullptr};
     uint32_t* d_counters = nullptr;  // fetch_ctr[levels_cap] | q_count[levels_cap] | stats[8] | overflow | dbg_count
     uint64_t* d_scan_off = nullptr;
@@ -67,6 +69,14 @@ struct rpw_handle {
     bool pend_labels_staged = false;
     uint64_t launches = 0;
     uint64_t launches_call = 0;
+
+    // optional per-kernel timing (rpw_profile_*): CUDA events bracketing every launch
+    bool prof_enabled = false;
+    std::vector<cudaEvent_t> prof_ev;   // pairs
+    std::vector<int> prof_kind;         // kernel id per pair
+    size_t prof_used = 0;
+    double prof_ms[RPW_PROF_KERNELS] = {0, 0, 0, 0};
+    uint64_t prof_launches[RPW_PROF_KERNELS] = {0, 0, 0, 0};
     std::string err;
 };
 
@@ -137,6 +147,8 @@ static void free_patch_buffers(rpw_handle* h) {
     cudaFree(h->d_blk_hist); h->d_blk_hist = nullptr;
     cudaFree(h->d_patch_start); h->d_patch_start = nullptr;
     cudaFree(h->d_root_mean); h->d_root_mean = nullptr;
+    cudaFree(h->d_patch_total); h->d_patch_total = nullptr;
+    cudaFree(h->d_patch_order); h->d_patch_order = nullptr;
 }
 
 static int alloc_patch_buffers(rpw_handle* h) {
@@ -146,6 +158,8 @@ static int alloc_patch_buffers(rpw_handle* h) {
     RPW_CUDA(h, cudaMalloc(&h->d_blk_hist, rows * P * sizeof(uint32_t)));
     RPW_CUDA(h, cudaMalloc(&h->d_patch_start, h->cap_batch * (size_t)(P + 1) * sizeof(uint32_t)));
     RPW_CUDA(h, cudaMalloc(&h->d_root_mean, h->cap_batch * (size_t)P * sizeof(float)));
+    RPW_CUDA(h, cudaMalloc(&h->d_patch_total, (size_t)P * sizeof(uint32_t)));
+    RPW_CUDA(h, cudaMalloc(&h->d_patch_order, (size_t)P * sizeof(uint32_t)));
     return RPW_OK;
 }
 
@@ -174,6 +188,7 @@ void rpw_destroy(rpw_handle* h) {
     if (h->h_stage_in) cudaFreeHost(h->h_stage_in);
     if (h->h_stage_labels) cudaFreeHost(h->h_stage_labels);
     if (h->h_stats) cudaFreeHost(h->h_stats);
+    for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -232,7 +247,7 @@ int rpw_create(const rpw_config* cfg, int device, size_t max_total_points, size_
     TRY(alloc_patch_buffers(h));
     TRY(alloc_level_buffers(h));
     // shared-memory budget of the fit kernel: points a block keeps resident
-    int cap = 4096;
+    int cap = 8192;
     if (const char* s = getenv("RPW_FIT_SMEM_CAP")) { const int v = atoi(s); if (v >= 256 && v <= 16384) cap = v; }
     if (const char* s = getenv("RPW_WAVE_SCANS")) { const int v = atoi(s); if (v >= 0) h->wave_scans = v; }
     h->smem_cap = cap;
@@ -294,6 +309,41 @@ void rpw_host_free(void* p) { if (p) cudaFreeHost(p); }
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------
+// per-kernel timing
+// ---------------------------------------------------------------------------------------------
+static int prof_fold(rpw_handle* h) {
+    if (h->prof_used == 0) return RPW_OK;
+    RPW_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i < h->prof_used; ++i) {
+        float ms = 0.f;
+        RPW_CUDA(h, cudaEventElapsedTime(&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]));
+        h->prof_ms[h->prof_kind[i]] += ms;
+        h->prof_launches[h->prof_kind[i]]++;
+    }
+    h->prof_used = 0;
+    return RPW_OK;
+}
+
+struct ProfScope {
+    rpw_handle* h;
+    size_t slot = (size_t)-1;
+    ProfScope(rpw_handle* h_, int kind) : h(h_) {
+        if (!h->prof_enabled) return;
+        if (h->prof_used * 2 >= h->prof_ev.size()) {
+            if (h->prof_ev.size() >= 2 * 4096) { if (prof_fold(h) != RPW_OK) return; }
+            else {
+                for (int k = 0; k < 128; ++k) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return; h->prof_ev.push_back(e); }
+                h->prof_kind.resize(h->prof_ev.size() / 2);
+            }
+        }
+        slot = h->prof_used++;
+        h->prof_kind[slot] = kind;
+        cudaEventRecord(h->prof_ev[2 * slot], h->stream);
+    }
+    ~ProfScope() { if (slot != (size_t)-1) cudaEventRecord(h->prof_ev[2 * slot + 1], h->stream); }
+};
+
+// ---------------------------------------------------------------------------------------------
 // launch sequence
 // ---------------------------------------------------------------------------------------------
 // Fills the pinned meta block (scan offsets, chunk bases), uploads it if it changed.
@@ -340,10 +390,13 @@ static int run_pipeline(rpw_handle* h, const float* d_pts, int stride_floats, ui
         // The kernels index scans relative to the pointers they are given.
         const uint64_t* d_so = h->d_scan_off + b0;
         const uint32_t* d_cb = h->d_chunk_base + b0;
-        RPW_CUDA(h, launch_bin(h->stream, stride_floats, d_pts, d_so, d_cb, h->zm, h->d_keys, d_labels, h->d_blk_hist, max_chunks, (int)nb));
-        RPW_CUDA(h, launch_offsets(h->stream, d_so, d_cb, h->d_blk_hist, h->d_patch_start + b0 * (size_t)(h->P + 1), h->P, (int)nb));
+        { ProfScope ps(h, 0);
+        RPW_CUDA(h, launch_bin(h->stream, stride_floats, d_pts, d_so, d_cb, h->zm, h->d_keys, d_labels, h->d_blk_hist, h->d_patch_total, max_chunks, (int)nb)); }
+        { ProfScope ps(h, 1);
+        RPW_CUDA(h, launch_offsets(h->stream, d_so, d_cb, h->d_blk_hist, h->d_patch_start + b0 * (size_t)(h->P + 1), h->d_patch_total, h->P, (int)nb)); }
+        { ProfScope ps(h, 2);
         RPW_CUDA(h, launch_scatter(h->stream, stride_floats, d_pts, d_so, d_cb, h->d_keys, h->d_blk_hist,
-                                   h->d_patch_start + b0 * (size_t)(h->P + 1), h->d_sortedA, h->P, max_chunks, (int)nb));
+                                   h->d_patch_start + b0 * (size_t)(h->P + 1), h->d_sortedA, h->d_patch_total, h->d_patch_order, h->P, max_chunks, (int)nb)); }
         FitArgs A;
         A.sortedA = h->d_sortedA; A.bufB = h->d_bufB; A.bufC = h->d_bufC; A.gmask = h->d_gmask;
         A.labels = d_labels;
@@ -359,11 +412,14 @@ static int run_pipeline(rpw_handle* h, const float* d_pts, int stride_floats, ui
         A.dbg_cap = h->dbg_cap;
         A.q_cap = h->q_cap;
         A.n_roots = (int)(nb * (size_t)h->P);
+        A.n_scans = (int)nb;
+        A.patch_order = h->d_patch_order;
         A.P = h->P;
         A.smem_cap = h->smem_cap;
         A.fp = h->fp;
         A.scan_base = (uint32_t)b0;
-        RPW_CUDA(h, launch_fit(h->stream, A, h->fit_blocks));
+        { ProfScope ps(h, 3);
+        RPW_CUDA(h, launch_fit(h->stream, A, h->fit_blocks)); }
         h->launches += 4;
         h->launches_call += 4;
     }
@@ -643,6 +699,27 @@ int rpw_debug_atan2(rpw_handle* h, const float* y, const float* x, size_t count,
     RPW_CUDA(h, cudaMemcpyAsync(out, dout, count * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     RPW_CUDA(h, cudaStreamSynchronize(h->stream));
     cudaFree(dy); cudaFree(dx); cudaFree(dout);
+    return RPW_OK;
+}
+
+int rpw_profile_enable(rpw_handle* h, int enable) {
+    if (!h) return RPW_ERR_BAD_ARG;
+    RPW_CUDA(h, cudaSetDevice(h->device));
+    int rc = prof_fold(h);
+    if (rc != RPW_OK) return rc;
+    h->prof_enabled = enable != 0;
+    for (int k = 0; k < RPW_PROF_KERNELS; ++k) { h->prof_ms[k] = 0; h->prof_launches[k] = 0; }
+    return RPW_OK;
+}
+
+int rpw_profile_read(rpw_handle* h, rpw_profile* out) {
+    if (!h || !out) return RPW_ERR_BAD_ARG;
+    RPW_CUDA(h, cudaSetDevice(h->device));
+    int rc = prof_fold(h);
+    if (rc != RPW_OK) return rc;
+    for (int k = 0; k < RPW_PROF_KERNELS; ++k) { out->ms[k] = h->prof_ms[k]; out->launches[k] = h->prof_launches[k]; }
+    out->fit_grid_blocks = (uint32_t)h->fit_blocks;
+    out->fit_smem_points = (uint32_t)h->smem_cap;
     return RPW_OK;
 }
 

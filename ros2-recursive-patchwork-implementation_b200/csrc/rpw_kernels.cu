@@ -40,9 +40,13 @@ template <int STRIDE>
 __global__ void __launch_bounds__(kBinThreads) rpw_bin_kernel(const float* __restrict__ pts, const uint64_t* __restrict__ scan_off,
                                                              const uint32_t* __restrict__ chunk_base, ZoneModel zm,
                                                              uint16_t* __restrict__ keys, uint8_t* __restrict__ labels,
-                                                             uint32_t* __restrict__ blk_hist) {
+                                                             uint32_t* __restrict__ blk_hist, uint32_t* __restrict__ patch_total) {
     extern __shared__ uint32_t s_hist[];
     const int b = blockIdx.y, chunk = blockIdx.x;
+    // batch-wide points-per-patch totals (scheduling order of the fit kernel) start from zero;
+    // the offsets kernel, which runs after this one, accumulates them
+    if (b == 0 && chunk == 0)
+        for (int p = threadIdx.x; p < zm.num_patches; p += kBinThreads) patch_total[p] = 0;
     const uint64_t off = scan_off[b];
     const uint32_t n = (uint32_t)(scan_off[b + 1] - off);
     const uint32_t base = (uint32_t)chunk * kBinChunk;
@@ -79,7 +83,8 @@ __global__ void __launch_bounds__(kBinThreads) rpw_bin_kernel(const float* __res
 // patch_start[b][p] = scan base + exclusive prefix over patches; patch_start[b][P] = end.
 // =============================================================================================
 __global__ void __launch_bounds__(256) rpw_offsets_kernel(const uint64_t* __restrict__ scan_off, const uint32_t* __restrict__ chunk_base,
-                                                         uint32_t* __restrict__ blk_hist, uint32_t* __restrict__ patch_start, int P) {
+                                                         uint32_t* __restrict__ blk_hist, uint32_t* __restrict__ patch_start,
+                                                         uint32_t* __restrict__ patch_total, int P) {
     extern __shared__ uint32_t s_cnt[];  // P + 1
     const int b = blockIdx.x;
     const uint64_t off = scan_off[b];
@@ -103,6 +108,7 @@ __global__ void __launch_bounds__(256) rpw_offsets_kernel(const uint64_t* __rest
             run += v;
         }
         s_cnt[p] = run;
+        if (run) atomicAdd(&patch_total[p], run);
     }
     __syncthreads();
     if (threadIdx.x < 32) {
@@ -134,11 +140,26 @@ __global__ void __launch_bounds__(kBinThreads) rpw_scatter_kernel(const float* _
                                                                  const uint32_t* __restrict__ chunk_base,
                                                                  const uint16_t* __restrict__ keys, const uint32_t* __restrict__ blk_hist,
                                                                  const uint32_t* __restrict__ patch_start, float4* __restrict__ sorted,
+                                                                 const uint32_t* __restrict__ patch_total, uint32_t* __restrict__ patch_order,
                                                                  int P) {
     extern __shared__ uint32_t s_off[];  // [warps][P]
     constexpr int kWarps = kBinThreads / 32;
     constexpr int kPerWarp = kBinChunk / kWarps;
     const int b = blockIdx.y, chunk = blockIdx.x;
+    if (b == 0 && chunk == 0) {
+        // Longest-processing-time-first order for the fit kernel's worklist: patches ranked by
+        // their batch-wide point totals, largest first (ties by patch index).  Big far-ring
+        // patches are also the ones whose plane fit iterates longest, so they must start early.
+        for (int p = threadIdx.x; p < P; p += kBinThreads) s_off[p] = patch_total[p];
+        __syncthreads();
+        for (int p = threadIdx.x; p < P; p += kBinThreads) {
+            const uint32_t t = s_off[p];
+            uint32_t rank = 0;
+            for (int q = 0; q < P; ++q) { const uint32_t u = s_off[q]; rank += (u > t) || (u == t && q < p); }
+            patch_order[rank] = (uint32_t)p;
+        }
+        __syncthreads();
+    }
     const uint64_t off = scan_off[b];
     const uint32_t n = (uint32_t)(scan_off[b + 1] - off);
     const uint32_t base = (uint32_t)chunk * kBinChunk;
@@ -675,10 +696,11 @@ __global__ void __launch_bounds__(kFitThreads, 2) rpw_fit_kernel(FitArgs A) {
         __syncthreads();
         const uint32_t id = s_fetch;
         if (id >= n_roots) break;
-        const uint32_t b = id / (uint32_t)A.P, p = id % (uint32_t)A.P;
+        // largest patches first: id walks (patch rank, scan)
+        const uint32_t b = id % (uint32_t)A.n_scans, p = A.patch_order[id / (uint32_t)A.n_scans];
         const uint32_t* ps = A.patch_start + (size_t)b * (A.P + 1) + p;
         NodeRef nd;
-        nd.start = ps[0]; nd.n = ps[1] - ps[0]; nd.root = id; nd.pad = 0;
+        nd.start = ps[0]; nd.n = ps[1] - ps[0]; nd.root = b * (uint32_t)A.P + p; nd.pad = 0;
         if (nd.n == 0) continue;  // :380
         run_node(A, nd, 0, S);
         n_done++;
@@ -745,27 +767,28 @@ size_t fit_smem_bytes(int smem_cap) {
 }
 
 cudaError_t launch_bin(cudaStream_t st, int stride_floats, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
-                       const ZoneModel& zm, uint16_t* keys, uint8_t* labels, uint32_t* blk_hist, int max_chunks, int batch) {
+                       const ZoneModel& zm, uint16_t* keys, uint8_t* labels, uint32_t* blk_hist, uint32_t* patch_total,
+                       int max_chunks, int batch) {
     dim3 grid(max_chunks, batch);
     const size_t smem = (size_t)zm.num_patches * 4;
-    if (stride_floats == 4) rpw_bin_kernel<4><<<grid, kBinThreads, smem, st>>>(pts, scan_off, chunk_base, zm, keys, labels, blk_hist);
-    else rpw_bin_kernel<3><<<grid, kBinThreads, smem, st>>>(pts, scan_off, chunk_base, zm, keys, labels, blk_hist);
+    if (stride_floats == 4) rpw_bin_kernel<4><<<grid, kBinThreads, smem, st>>>(pts, scan_off, chunk_base, zm, keys, labels, blk_hist, patch_total);
+    else rpw_bin_kernel<3><<<grid, kBinThreads, smem, st>>>(pts, scan_off, chunk_base, zm, keys, labels, blk_hist, patch_total);
     return cudaGetLastError();
 }
 
 cudaError_t launch_offsets(cudaStream_t st, const uint64_t* scan_off, const uint32_t* chunk_base, uint32_t* blk_hist,
-                           uint32_t* patch_start, int P, int batch) {
-    rpw_offsets_kernel<<<batch, 256, (size_t)(P + 1) * 4, st>>>(scan_off, chunk_base, blk_hist, patch_start, P);
+                           uint32_t* patch_start, uint32_t* patch_total, int P, int batch) {
+    rpw_offsets_kernel<<<batch, 256, (size_t)(P + 1) * 4, st>>>(scan_off, chunk_base, blk_hist, patch_start, patch_total, P);
     return cudaGetLastError();
 }
 
 cudaError_t launch_scatter(cudaStream_t st, int stride_floats, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
-                           const uint16_t* keys, const uint32_t* blk_hist, const uint32_t* patch_start, float4* sorted, int P,
-                           int max_chunks, int batch) {
+                           const uint16_t* keys, const uint32_t* blk_hist, const uint32_t* patch_start, float4* sorted,
+                           const uint32_t* patch_total, uint32_t* patch_order, int P, int max_chunks, int batch) {
     dim3 grid(max_chunks, batch);
     const size_t smem = (size_t)(kBinThreads / 32) * P * 4;
-    if (stride_floats == 4) rpw_scatter_kernel<4><<<grid, kBinThreads, smem, st>>>(pts, scan_off, chunk_base, keys, blk_hist, patch_start, sorted, P);
-    else rpw_scatter_kernel<3><<<grid, kBinThreads, smem, st>>>(pts, scan_off, chunk_base, keys, blk_hist, patch_start, sorted, P);
+    if (stride_floats == 4) rpw_scatter_kernel<4><<<grid, kBinThreads, smem, st>>>(pts, scan_off, chunk_base, keys, blk_hist, patch_start, sorted, patch_total, patch_order, P);
+    else rpw_scatter_kernel<3><<<grid, kBinThreads, smem, st>>>(pts, scan_off, chunk_base, keys, blk_hist, patch_start, sorted, patch_total, patch_order, P);
     return cudaGetLastError();
 }
 

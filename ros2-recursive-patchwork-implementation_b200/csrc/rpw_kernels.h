@@ -24,6 +24,7 @@ struct FitArgs {
     uint8_t* gmask;            // per-slot mask scratch for nodes that do not fit in shared memory
     uint8_t* labels;           // per input point
     const uint32_t* patch_start;  // [batch][P + 1]
+    const uint32_t* patch_order;  // [P] patches by batch-wide size, largest first
     float* root_mean;          // [batch * P] mean range of the root patch (Q4)
     NodeRef* queue[2];         // next-level queues, ping-pong by level parity
     uint32_t* q_count;         // [levels_cap] nodes enqueued for level l
@@ -35,6 +36,7 @@ struct FitArgs {
     uint32_t dbg_cap;
     uint32_t q_cap;
     int n_roots;               // batch * P
+    int n_scans;               // scans in this launch group
     int P;
     int smem_cap;              // points a block can hold in shared memory
     uint32_t scan_base;        // index of the launch group's first scan inside the call's batch (debug records)
@@ -45,12 +47,13 @@ size_t fit_smem_bytes(int smem_cap);
 cudaError_t fit_configure(int smem_cap, int* blocks_per_sm);
 
 cudaError_t launch_bin(cudaStream_t st, int stride_floats, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
-                       const ZoneModel& zm, uint16_t* keys, uint8_t* labels, uint32_t* blk_hist, int max_chunks, int batch);
+                       const ZoneModel& zm, uint16_t* keys, uint8_t* labels, uint32_t* blk_hist, uint32_t* patch_total,
+                       int max_chunks, int batch);
 cudaError_t launch_offsets(cudaStream_t st, const uint64_t* scan_off, const uint32_t* chunk_base, uint32_t* blk_hist,
-                           uint32_t* patch_start, int P, int batch);
+                           uint32_t* patch_start, uint32_t* patch_total, int P, int batch);
 cudaError_t launch_scatter(cudaStream_t st, int stride_floats, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
-                           const uint16_t* keys, const uint32_t* blk_hist, const uint32_t* patch_start, float4* sorted, int P,
-                           int max_chunks, int batch);
+                           const uint16_t* keys, const uint32_t* blk_hist, const uint32_t* patch_start, float4* sorted,
+                           const uint32_t* patch_total, uint32_t* patch_order, int P, int max_chunks, int batch);
 cudaError_t launch_fit(cudaStream_t st, const FitArgs& args, int grid_blocks);
 cudaError_t launch_eig3(cudaStream_t st, const float* mats, size_t count, float* evals, float* evecs);
 cudaError_t launch_atan2(cudaStream_t st, const float* y, const float* x, size_t count, float* out);

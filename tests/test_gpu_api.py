@@ -1,0 +1,125 @@
+"""GPU tests of the boundary's behaviour: degenerate inputs, strides, batches, capacity errors,
+the device-resident entry point, the clouds the reference returns, and the Python mirror class."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def h(gpu_handle_factory):
+    return gpu_handle_factory(None, 1 << 19, 8)
+
+
+def test_native_library_is_the_one_running(rpw, h):
+    before = h.kernel_launches()
+    h.segment(rpw.synth.testsuite_cloud(1, 1000))
+    assert h.kernel_launches() - before == 4  # bin, offsets, scatter, fit
+
+
+def test_degenerate_inputs(rpw, h, oracle):
+    cfg = rpw.PatchworkConfig()
+    h.set_config(cfg.to_c())
+    assert len(h.segment(np.zeros((0, 3), np.float32))) == 0
+    for pts in (np.array([[3, 4, 0], [5, 1, 0.1]], np.float32),          # < 3 in-zone points
+                np.full((5, 3), np.nan, np.float32),                      # nothing survives cleaning
+                np.array([[1e4, 0, 0]] * 4, np.float32),                  # all beyond the radius
+                np.array([[0.5, 0.1, 0], [80.0, 0, 0], [10, -1e-9, 0], [10, 1, 0], [11, 1, 0]], np.float32),
+                np.array([[10, 1, 0], [10, 1, 0], [10, 1, 0], [10, 1, 0]], np.float32)):  # identical points
+        got = h.segment(pts)
+        want = oracle.run(cfg, pts)["labels"]
+        assert np.array_equal(got, want), (pts, got, want)
+
+
+def test_stride_12_and_16_agree(rpw, h):
+    pts = rpw.synth.spinning_scan(1003)
+    a = h.segment(pts)
+    b = h.segment(np.ascontiguousarray(pts[:, :3]))
+    assert np.array_equal(a, b)
+
+
+def test_batch_equals_singles_and_ragged_sizes(rpw, h):
+    cfg = rpw.PatchworkConfig(filtering_radius=80.0)
+    h.set_config(cfg.to_c())
+    scans = [rpw.synth.spinning_scan(1100, 64, 500), rpw.synth.testsuite_cloud(9, 7), np.zeros((0, 4), np.float32),
+             rpw.synth.spinning_scan(1101, 64, 1875), rpw.synth.testsuite_cloud(10, 4097)]
+    singles = [h.segment(s) if len(s) else np.zeros(0, np.uint8) for s in scans]
+    batch = h.segment_batch(scans)
+    for a, b in zip(singles, batch):
+        assert np.array_equal(a, b)
+
+
+def test_capacity_and_argument_errors(rpw, gpu_handle_factory):
+    small = gpu_handle_factory(None, 1000, 2)
+    with pytest.raises(rpw.RpwError) as e:
+        small.segment(rpw.synth.testsuite_cloud(1, 2000))
+    assert e.value.code == rpw.capi.RPW_ERR_CAPACITY
+    with pytest.raises(rpw.RpwError) as e:
+        small.segment_batch([rpw.synth.testsuite_cloud(1, 10)] * 3)
+    assert e.value.code == rpw.capi.RPW_ERR_CAPACITY
+    bad = rpw.PatchworkConfig(num_sectors=0)
+    with pytest.raises(rpw.RpwError) as e:
+        small.set_config(bad.to_c())
+    assert e.value.code == rpw.capi.RPW_ERR_BAD_ARG
+    # the handle still works afterwards
+    assert len(small.segment(rpw.synth.testsuite_cloud(1, 900))) == 900
+
+
+def test_device_resident_entry_point(rpw, h):
+    import torch
+    cfg = rpw.PatchworkConfig(filtering_radius=80.0)
+    h.set_config(cfg.to_c())
+    scans = [rpw.synth.spinning_scan(1200 + i, 64, 600) for i in range(3)]
+    want = h.segment_batch(scans)
+    off = np.zeros(4, np.uint64)
+    off[1:] = np.cumsum([len(s) for s in scans])
+    d_pts = torch.from_numpy(np.concatenate(scans)).cuda()
+    d_lab = torch.full((int(off[-1]),), 255, dtype=torch.uint8, device="cuda")
+    s = torch.cuda.Stream()
+    h.set_stream(s.cuda_stream)
+    h.segment_device(d_pts.data_ptr(), off, d_lab.data_ptr())
+    s.synchronize()
+    h.set_stream(None)
+    got = d_lab.cpu().numpy()
+    assert np.array_equal(got, np.concatenate(want))
+
+
+def test_clouds_follow_reference_order(rpw, h, oracle):
+    cfg = rpw.PatchworkConfig(filtering_radius=40.0)
+    h.set_config(cfg.to_c())
+    pts = rpw.synth.testsuite_cloud(77, 6000)
+    g, ng, labels = h.segment_clouds(pts)
+    o = oracle.run(cfg, pts)["labels"]
+    assert np.array_equal(labels, o)
+    p = pts[:, :3]
+    assert np.array_equal(g, p[o == 1])
+    assert np.array_equal(ng, np.concatenate([p[o == 0], p[o == 2]]))
+
+
+def test_python_mirror_class(rpw, oracle):
+    cfg = rpw.PatchworkConfig(sensor_height=1.2, filtering_radius=50.0, num_sectors=8, max_iter=50)  # testBasicFunctionality's config
+    rp = rpw.RecursivePatchwork(cfg, max_points=1 << 16)
+    pts = rpw.synth.testsuite_cloud(5, 5000)[:, :3]
+    ground, non_ground = rp.filterGroundPoints(pts)
+    # the reference test's own assertions (RP/test/test_recursive_patchwork.cpp:74-76)
+    assert len(ground) + len(non_ground) <= len(pts) and len(ground) > 0 and len(non_ground) > 0
+    o = oracle.run(cfg, pts)["labels"]
+    assert len(ground) == int((o == 1).sum()) and len(non_ground) == int(np.isin(o, (0, 2)).sum())
+    g0, n0 = rp.filterGroundPoints(np.zeros((0, 3), np.float32))
+    assert len(g0) == 0 and len(n0) == 0
+    rp.setConfig(rpw.PatchworkConfig())
+    assert rp.getConfig().filtering_radius == 150.0
+    assert len(rp.cleanPoints(np.array([[1, 2, 3], [np.nan, 0, 0]], np.float32))) == 1
+    rp.close()
+
+
+def test_set_config_changes_sector_count(rpw, h, oracle):
+    pts = rpw.synth.testsuite_cloud(12, 8000)
+    for S in (10, 24, 3, 10):
+        cfg = rpw.PatchworkConfig(num_sectors=S, filtering_radius=70.0)
+        h.set_config(cfg.to_c())
+        got = h.segment(pts)
+        keys = h.debug_keys(len(pts))
+        o = oracle.run(cfg, pts)
+        assert np.array_equal(keys, o["keys"])
+        assert (got == o["labels"]).mean() >= 0.999

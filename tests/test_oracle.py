@@ -1,0 +1,126 @@
+"""CPU tests: the oracle (plain-C restatement) against the golden vectors, against the reference's
+own translation units when they were built (oracle/_ref), and its restated third-party math
+(Eigen 3.4.0 eigensolver, glibc atan2f) against independent implementations."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import golden_util
+
+
+def clouds(points, labels):
+    p = points[:, :3]
+    return p[labels == 1], np.concatenate([p[labels == 0], p[labels == 2]])
+
+
+@pytest.mark.parametrize("name", golden_util.names())
+def test_oracle_reproduces_golden_labels(name, rpw, oracle):
+    g = golden_util.load(name, rpw.PatchworkConfig)
+    out = oracle.run(g["cfg"], g["points"])
+    assert np.array_equal(out["labels"], g["labels"]), f"{name}: {(out['labels'] != g['labels']).sum()} labels differ"
+    assert int((out["labels"] == 1).sum()) == g["n_ground"]
+    assert int(np.isin(out["labels"], (0, 2)).sum()) == g["n_non_ground"]
+
+
+def test_golden_covers_edge_cases(rpw):
+    have = golden_util.names()
+    for must in ("edge_two_points", "edge_nan_inf_beyond", "edge_duplicates", "c1_10000_s42_splits"):
+        assert must in have
+    g = golden_util.load("edge_nan_inf_beyond", rpw.PatchworkConfig)
+    assert set(np.unique(g["labels"])) == {0, 1, 2, 3}
+
+
+@pytest.mark.parametrize("case", ["c1_3000", "c1_10000_splits", "c1_r50_s8", "c1_nonadaptive", "c2_19k", "c5_49k", "c4_small", "shallow_depth"])
+def test_oracle_bit_identical_to_reference_clouds(case, rpw, oracle, ref):
+    """The parity pin: the reference's own code (compiled unmodified) and the restatement must
+    return bit-identical ground / non-ground clouds (order included)."""
+    if ref is None:
+        pytest.skip("oracle/_ref not built (needs /root/reference); golden fixtures cover this box")
+    PC, S = rpw.PatchworkConfig, rpw.synth
+    cfg, pts = {
+        "c1_3000": (PC(), S.testsuite_cloud(101, 3000)),
+        "c1_10000_splits": (PC(), S.testsuite_cloud(42, 10000)),
+        "c1_r50_s8": (PC(filtering_radius=50.0, num_sectors=8, max_iter=50), S.testsuite_cloud(102, 5000)),
+        "c1_nonadaptive": (PC(adaptive_seed_height=False, th_seeds=0.3), S.testsuite_cloud(103, 8000)),
+        "c2_19k": (PC(filtering_radius=80.0), S.spinning_scan(1001, 64, 300)),
+        "c5_49k": (PC(filtering_radius=80.0), S.spinning_scan(3001, 128, 384, 1)),
+        "c4_small": (PC(), S.solidstate_merged(2001, 120, 90)),
+        "shallow_depth": (PC(filtering_radius=80.0, max_split_depth=2), S.spinning_scan(3002, 128, 384, 1)),
+    }[case]
+    r = ref.run(cfg, pts)
+    o = oracle.run(cfg, pts)
+    g, ng = clouds(pts, o["labels"])
+    assert g.shape == r["ground"].shape and np.array_equal(g.view(np.uint32), r["ground"].view(np.uint32))
+    assert ng.shape == r["non_ground"].shape and np.array_equal(ng.view(np.uint32), r["non_ground"].view(np.uint32))
+    assert np.array_equal(o["labels"], r["labels"])
+
+
+def test_split_permutation_semantics(rpw, oracle):
+    """leaves tile the root patch in concatenation order; the cloud with three
+    collapse-splits (census in BASELINE.md) must show them."""
+    cfg = rpw.PatchworkConfig()
+    out = oracle.run(cfg, rpw.synth.testsuite_cloud(42, 10000), want_nodes=True)
+    st, nodes = out["stats"], out["nodes"]
+    assert st["n_splits"] == 3 and st["n_splits_collapse"] == 3 and st["max_depth"] == 2
+    for root in np.unique(nodes["root"]):
+        nd = nodes[nodes["root"] == root]
+        leaves = nd[nd["outcome"] != 5]
+        order = np.argsort(leaves["start"])
+        ends = leaves["start"][order] + leaves["n"][order]
+        assert leaves["start"][order][0] == 0 and np.array_equal(ends[:-1], leaves["start"][order][1:])
+        assert ends[-1] == nd[nd["depth"] == 0]["n"][0]
+
+
+def test_degenerate_inputs(rpw, oracle):
+    cfg = rpw.PatchworkConfig()
+    assert len(oracle.run(cfg, np.zeros((0, 3), np.float32))["labels"]) == 0
+    two = np.array([[3, 4, 0], [5, 1, 0.1]], np.float32)
+    assert list(oracle.run(cfg, two)["labels"]) == [0, 0]  # < 3 in-zone points: ({}, cleaned)
+    bad = np.full((5, 3), np.nan, np.float32)
+    assert list(oracle.run(cfg, bad)["labels"]) == [3] * 5
+    far = np.array([[1e4, 0, 0]] * 4, np.float32)
+    assert list(oracle.run(cfg, far)["labels"]) == [2] * 4
+
+
+def test_unbinned_points(rpw, oracle):
+    """d < 1 m, d == R and a wrapped angle of exactly 2*pi pass the radius filter but sit
+    in no patch."""
+    cfg = rpw.PatchworkConfig(filtering_radius=80.0)
+    pts = np.array([[0.5, 0.1, 0], [80.0, 0, 0], [10, -1e-9, 0], [10, 1, 0]], np.float32)
+    k = oracle.run(cfg, pts)["keys"]
+    assert list(k[:3]) == [0xFFFD] * 3 and k[3] < 80
+
+
+def test_eig3_restatement_vs_numpy(oracle):
+    rng = np.random.default_rng(1)
+    A = rng.normal(size=(500, 3, 3))
+    A = A @ A.transpose(0, 2, 1)
+    A[:250, 2, :] *= 1e-2
+    A[:250, :, 2] *= 1e-2  # plane-like: one small eigenvalue
+    A = ((A + A.transpose(0, 2, 1)) / 2).astype(np.float32)
+    ev, vec = oracle.eig3(A)
+    w, v = np.linalg.eigh(A.astype(np.float64))
+    assert np.allclose(ev, w, rtol=2e-5, atol=2e-5 * np.abs(w).max(axis=1, keepdims=True))
+    gap = np.minimum(w[:, 1] - w[:, 0], 1e30) / np.abs(w).max(axis=1)
+    ok = gap > 1e-3
+    cosang = np.abs(np.einsum("ni,ni->n", vec[:, :, 0].astype(np.float64), v[:, :, 0]))
+    assert np.all(np.arccos(np.clip(cosang[ok], 0, 1)) < 1e-3)
+    assert np.allclose(np.linalg.norm(vec[:, :, 0], axis=1), 1, atol=1e-5)
+
+
+def test_atan2f_restatement_is_libm(oracle):
+    """The device computes the sector angle with this sequence; it must equal the host libm the
+    reference links (glibc) bit for bit."""
+    oracle.lib.rpwo_atan2f_selfcheck.restype = C.c_uint64
+    bad = oracle.lib.rpwo_atan2f_selfcheck(C.c_uint64(30_000_000), C.c_uint64(12345), C.c_float(160.0))
+    assert bad == 0
+
+
+def test_zone_model_matches_host_library(rpw, oracle):
+    for R, S in ((150.0, 10), (80.0, 10), (50.0, 8), (33.3, 37)):
+        cfg = rpw.PatchworkConfig(filtering_radius=R, num_sectors=S)
+        e1, a1 = rpw.capi.zone_model(cfg.to_c())
+        import oracle_lib
+        e2, a2 = oracle.zone_model(oracle_lib.to_cfg(cfg))
+        assert np.array_equal(e1.view(np.uint32), e2.view(np.uint32)) and np.float32(a1) == np.float32(a2)
