@@ -1,0 +1,223 @@
+// host/recursive_patchwork.hpp — drop-in C++ front end for the B200 segmentation path.
+//
+// Source-compatible with the public surface of the reference's
+// src/recursive_patchwork/include/recursive_patchwork.hpp (namespace, type names, member
+// functions, argument meaning, default values), so the reference's callers — main.cpp:193,268,286,
+// recursive_patchwork_node.cpp:40,91 and test_recursive_patchwork.cpp:65-68,86-89,151-155 — build
+// against it unchanged as far as the segmentation class is concerned.  Differences:
+//   * no Eigen in this header: the class holds an opaque C-ABI handle (include/rpw_b200.h) instead
+//     of running the algorithm on the host; librpw_b200.so must be linked;
+//   * failures (no CUDA device, CUDA error, capacity) surface as std::runtime_error — the ROS2
+//     node already wraps its callback in try/catch(std::exception) (recursive_patchwork_node.cpp:66,105);
+//     there is no CPU fallback;
+//   * filterGroundPoints has a labels-returning sibling (the north-star addition);
+//   * nothing is printed on the hot path (the reference logs 3-5 lines per cuda::ops call).
+// Header-only on purpose: the host side stays trivial and the whole product is behind the C-ABI.
+#pragma once
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <limits>
+#include <memory>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "rpw_b200.h"
+
+namespace recursive_patchwork {
+
+class PointCloudProcessor;
+class LidarFusion;
+class RosbagLoader;
+class Visualization;
+
+// 12-byte AoS point, the layout the C-ABI takes with stride_bytes = 12.
+struct Point3D {
+    float x, y, z;
+    Point3D() : x(0), y(0), z(0) {}
+    Point3D(float px, float py, float pz) : x(px), y(py), z(pz) {}
+};
+static_assert(sizeof(Point3D) == 12, "Point3D must stay a packed xyz triple");
+
+// Same fields, order and defaults as the reference struct; convertible to rpw_config.
+struct PatchworkConfig {
+    float sensor_height = 1.2f;
+    float max_range = 150.0f;         // carried, never read by the path (as in the reference)
+    int num_sectors = 10;
+    int max_iter = 100;
+    bool adaptive_seed_height = true;
+    float th_seeds = 0.15f;
+    float th_dist = 0.2f;
+    float th_outlier = 0.08f;         // carried, never read by the path
+    float filtering_radius = 150.0f;
+    int max_split_depth = 1000;
+
+    rpw_config toC() const {
+        rpw_config c;
+        c.sensor_height = sensor_height; c.max_range = max_range; c.num_sectors = num_sectors; c.max_iter = max_iter;
+        c.adaptive_seed_height = adaptive_seed_height ? 1 : 0; c.th_seeds = th_seeds; c.th_dist = th_dist;
+        c.th_outlier = th_outlier; c.filtering_radius = filtering_radius; c.max_split_depth = max_split_depth;
+        return c;
+    }
+};
+
+struct LidarConfig {
+    int lidar_id;
+    std::string topic_name;
+    float rotation_angle;  // degrees
+    float ego_radius = 2.5f;
+};
+
+class RecursivePatchwork {
+public:
+    explicit RecursivePatchwork(const PatchworkConfig& config = PatchworkConfig{}, int device = 0)
+        : config_(config), device_(device) {}
+    ~RecursivePatchwork() { release(); }
+    RecursivePatchwork(const RecursivePatchwork&) = delete;
+    RecursivePatchwork& operator=(const RecursivePatchwork&) = delete;
+
+    // ---- main processing --------------------------------------------------------------------
+    // (ground, non-ground) exactly as the reference orders them: ground in input order;
+    // non-ground in input order followed by the beyond-radius points in input order.
+    std::pair<std::vector<Point3D>, std::vector<Point3D>> filterGroundPoints(const std::vector<Point3D>& points) {
+        std::vector<std::uint8_t> labels;
+        return filterGroundPoints(points, labels);
+    }
+
+    // Same, also returning one label per input point (RPW_LABEL_*).
+    std::pair<std::vector<Point3D>, std::vector<Point3D>> filterGroundPoints(const std::vector<Point3D>& points,
+                                                                             std::vector<std::uint8_t>& labels) {
+        std::pair<std::vector<Point3D>, std::vector<Point3D>> out;
+        labels.assign(points.size(), RPW_LABEL_DROPPED);
+        if (points.empty()) return out;  // empty in, two empty clouds out
+        ensure(points.size());
+        check(rpw_segment(handle_, &points[0].x, points.size(), sizeof(Point3D), labels.data(), nullptr));
+        std::size_t n_ground = 0, n_non = 0, n_beyond = 0;
+        for (std::uint8_t l : labels) { n_ground += l == RPW_LABEL_GROUND; n_non += l == RPW_LABEL_NONGROUND; n_beyond += l == RPW_LABEL_BEYOND; }
+        out.first.reserve(n_ground);
+        out.second.reserve(n_non + n_beyond);
+        for (std::size_t i = 0; i < points.size(); ++i) {
+            if (labels[i] == RPW_LABEL_GROUND) out.first.push_back(points[i]);
+            else if (labels[i] == RPW_LABEL_NONGROUND) out.second.push_back(points[i]);
+        }
+        if (n_beyond)
+            for (std::size_t i = 0; i < points.size(); ++i)
+                if (labels[i] == RPW_LABEL_BEYOND) out.second.push_back(points[i]);
+        return out;
+    }
+
+    // Labels only (no cloud assembly): the cheapest call for a caller that indexes its own data.
+    std::vector<std::uint8_t> segmentLabels(const std::vector<Point3D>& points) {
+        std::vector<std::uint8_t> labels(points.size());
+        if (points.empty()) return labels;
+        ensure(points.size());
+        check(rpw_segment(handle_, &points[0].x, points.size(), sizeof(Point3D), labels.data(), nullptr));
+        return labels;
+    }
+
+    // Post-filter of the standalone app (reference recursive_patchwork.cpp:428-465): non-ground
+    // points outside the ego radius whose height is within base_tol of target_height, preceded by
+    // a random subsample of at most 2000 ground points.  Host-side; the subsample is unseeded in
+    // the reference too, so only sizes are reproducible.
+    std::vector<Point3D> sampleGroundAndObstacles(const std::vector<Point3D>& points, float target_height = 1.1f,
+                                                  float base_tol = 0.5f) {
+        auto clouds = filterGroundPoints(points);
+        std::vector<Point3D>& ground = clouds.first;
+        if (clouds.second.empty()) return ground;
+        std::vector<Point3D> obstacles;
+        for (const Point3D& p : clouds.second) {
+            if (!(std::sqrt(p.x * p.x + p.y * p.y) > 2.5f)) continue;  // ego vehicle
+            if (std::abs(p.z - target_height) <= base_tol) obstacles.push_back(p);
+        }
+        std::vector<Point3D> result;
+        const std::size_t want = std::min<std::size_t>(2000, ground.size());
+        if (ground.size() <= want) {
+            result = ground;
+        } else {
+            std::mt19937 gen{std::random_device{}()};
+            std::uniform_int_distribution<std::size_t> pick(0, ground.size() - 1);
+            std::vector<bool> taken(ground.size(), false);
+            result.reserve(want + obstacles.size());
+            while (result.size() < want) {
+                const std::size_t i = pick(gen);
+                if (!taken[i]) { taken[i] = true; result.push_back(ground[i]); }
+            }
+        }
+        result.insert(result.end(), obstacles.begin(), obstacles.end());
+        return result;
+    }
+
+    // ---- utilities (host side, same behaviour as the reference's) ---------------------------
+    std::vector<Point3D> cleanPoints(const std::vector<Point3D>& points) {
+        std::vector<Point3D> kept;
+        kept.reserve(points.size());
+        for (const Point3D& p : points)
+            if (std::isfinite(p.x) && std::isfinite(p.y) && std::isfinite(p.z)) kept.push_back(p);
+        return kept;
+    }
+
+    std::vector<Point3D> rotatePoints2D(const std::vector<Point3D>& points, float angle_degrees) {
+        const float a = angle_degrees * static_cast<float>(M_PI) / 180.0f;
+        const float c = std::cos(a), s = std::sin(a);
+        std::vector<Point3D> out;
+        out.reserve(points.size());
+        for (const Point3D& p : points) out.emplace_back(p.x * c - p.y * s, p.x * s + p.y * c, p.z);
+        return out;
+    }
+
+    // ---- configuration ---------------------------------------------------------------------
+    void setConfig(const PatchworkConfig& config) {
+        config_ = config;
+        if (handle_) { const rpw_config c = config_.toC(); check(rpw_set_config(handle_, &c)); }
+    }
+    const PatchworkConfig& getConfig() const { return config_; }
+
+    // Pre-size the device buffers (otherwise they grow on demand).
+    void reserve(std::size_t max_points) { ensure(max_points); }
+
+private:
+    PatchworkConfig config_;
+    int device_ = 0;
+    rpw_handle* handle_ = nullptr;
+    std::size_t capacity_ = 0;
+
+    void release() {
+        if (handle_) rpw_destroy(handle_);
+        handle_ = nullptr;
+        capacity_ = 0;
+    }
+    void ensure(std::size_t n) {
+        if (handle_ && n <= capacity_) return;
+        std::size_t cap = std::max<std::size_t>(n + n / 4, std::size_t(1) << 18);
+        release();
+        const rpw_config c = config_.toC();
+        const int rc = rpw_create(&c, device_, cap, 1, &handle_);
+        if (rc != RPW_OK) {
+            handle_ = nullptr;
+            throw std::runtime_error(std::string("RecursivePatchwork (B200): ") + rpw_last_error(nullptr));
+        }
+        capacity_ = cap;
+    }
+    void check(int rc) const {
+        if (rc != RPW_OK) throw std::runtime_error(std::string("RecursivePatchwork (B200): ") + rpw_last_error(handle_));
+    }
+};
+
+// Wall-clock helper with the reference's interface.
+class Timer {
+public:
+    Timer() : start_(clock::now()) {}
+    double elapsed() const { return std::chrono::duration<double>(clock::now() - start_).count(); }
+    void reset() { start_ = clock::now(); }
+
+private:
+    using clock = std::chrono::steady_clock;
+    clock::time_point start_;
+};
+
+}  // namespace recursive_patchwork
