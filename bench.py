@@ -163,7 +163,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scans", type=int, default=256, help="scans per step per GPU")
+    ap.add_argument("--scans", type=int, default=512, help="scans per step per GPU (BASELINE configs[2]: 4096 scans over 8 GPUs)")
+    ap.add_argument("--solver", default="eigen_qr", choices=["eigen_qr", "closed_form"],
+                    help="plane-normal solver: eigen_qr = reference-faithful default, closed_form = faster (see include/rpw_b200.h)")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="handles the end-to-end arm ping-pongs over (copy/compute overlap)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -195,6 +198,8 @@ def main():
     offsets[1:] = np.cumsum(n_pts)
 
     h = rpw.Handle(cfg.to_c(), local_rank, total, B)
+    solver_id = rpw.capi.SOLVER_EIGEN_QR if args.solver == "eigen_qr" else rpw.capi.SOLVER_CLOSED_FORM
+    h.set_plane_solver(solver_id)
     # a real (non-NULL) stream: the C-ABI reads NULL as "the handle's own stream", and CUDA events
     # only see the stream they are recorded on
     stream = torch.cuda.Stream(device=dev)
@@ -243,21 +248,53 @@ def main():
     # sanity: labels of the resident arm equal a host-path call on the first scan
     lab_dev = d_labels[: n_pts[0]].cpu().numpy()
 
+    # ---- alternative solver, same timed loop (reported beside the headline, not instead of it) ----
+    other_id = rpw.capi.SOLVER_CLOSED_FORM if solver_id == rpw.capi.SOLVER_EIGEN_QR else rpw.capi.SOLVER_EIGEN_QR
+    h.set_plane_solver(other_id)
+    for _ in range(3):
+        step_resident()
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+    e1.record(stream)
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    other_value = world * B * args.steps / (float(t.item()) * 1e-3)
+    h.set_plane_solver(solver_id)
+
     # ---- end-to-end arm: pinned host xyz (12 B/pt, the reference's Point3D layout) -> labels ----
+    # The public C-ABI call a user makes (rpw_segment_batch_async + rpw_wait) on host buffers; the
+    # batch is cut into chunks that ping-pong over a few handles so that the H2D copy of one chunk,
+    # the kernels of another and the D2H copy of a third overlap.
     pin_in = rpw.capi.PinnedArray((total, 3), np.float32)
     pin_in.array[:] = host_f4[:, :3]
     pin_out = rpw.capi.PinnedArray((total,), np.uint8)
-    in_ptrs = [pin_in.ptr + int(offsets[i]) * 12 for i in range(B)]
-    out_ptrs = [pin_out.ptr + int(offsets[i]) for i in range(B)]
+    n_chunks = max(1, min(args.e2e_chunks, B))
+    bounds = [round(i * B / n_chunks) for i in range(n_chunks + 1)]
+    chunks = []
+    for c in range(n_chunks):
+        lo, hi = bounds[c], bounds[c + 1]
+        if hi <= lo:
+            continue
+        hc = rpw.Handle(cfg.to_c(), local_rank, int(offsets[hi] - offsets[lo]), hi - lo)
+        hc.set_plane_solver(solver_id)
+        chunks.append((hc, [pin_in.ptr + int(offsets[i]) * 12 for i in range(lo, hi)], n_pts[lo:hi],
+                       [pin_out.ptr + int(offsets[i]) for i in range(lo, hi)]))
 
     def step_e2e():
-        h.segment_batch_async(in_ptrs, n_pts, 12, out_ptrs)
-        h.wait()
+        for hc, ip, ns, op in chunks:
+            hc.segment_batch_async(ip, ns, 12, op)
+        for hc, _, _, _ in chunks:
+            hc.wait()
 
     for _ in range(3):
         step_e2e()
     assert np.array_equal(pin_out.array[: n_pts[0]], lab_dev), "host-path and device-path labels differ"
     e2e_steps = max(3, args.steps // 2)
+    launches_e2e0 = sum(hc.kernel_launches() for hc, _, _, _ in chunks)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -268,6 +305,8 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * e2e_steps / float(t.item())
+    for hc, _, _, _ in chunks:
+        hc.close()
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -301,7 +340,10 @@ def main():
                          "algorithmic_bytes_per_point": ALG_BYTES_PER_POINT, "ms_per_launch": fit_ms},
             "kernels": kernels,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": total * 12, "d2h_bytes_per_step": total,
-                    "api": "rpw_segment_batch_async + rpw_wait (C-ABI), pinned host xyz stride 12 in, labels out", "steps": e2e_steps},
+                    "api": f"rpw_segment_batch_async + rpw_wait (C-ABI) over {len(chunks)} handles, pinned host xyz stride 12 in, labels out",
+                    "steps": e2e_steps},
+            "solver": args.solver,
+            "other_solver": {"name": "closed_form" if solver_id == rpw.capi.SOLVER_EIGEN_QR else "eigen_qr", "value": other_value, "unit": UNIT},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

@@ -131,6 +131,21 @@ void rpw_destroy(rpw_handle* h);
 int rpw_set_config(rpw_handle* h, const rpw_config* cfg);
 int rpw_get_config(const rpw_handle* h, rpw_config* out);
 
+/* How the plane normal (smallest-eigenvalue eigenvector of the inlier covariance,
+ * RP/src/recursive_patchwork.cpp:89-90) is computed on the device.
+ *   RPW_SOLVER_EIGEN_QR (default): the operation sequence of Eigen 3.4.0's
+ *     SelfAdjointEigenSolver<Matrix3f> in float — given the same covariance bits it returns the
+ *     reference's bits, so even chaotic patches (two-layer clutter, where a 1e-6 rad change of
+ *     one normal sends the fit to a different fixed point) reproduce the reference's labels.
+ *   RPW_SOLVER_CLOSED_FORM: closed-form FP64 eigenvector, ~1.4x faster end to end and more accurate
+ *     than the reference's float QR, but it is not the reference's rounding: identical labels on
+ *     ordinary scans, 99.5 % on the worst chaotic synthetic scene — the same spread the reference
+ *     shows between its own -O2 and -O3 -ffast-math builds.
+ * Environment override at rpw_create: RPW_PLANE_SOLVER=0|1. */
+#define RPW_SOLVER_EIGEN_QR 0
+#define RPW_SOLVER_CLOSED_FORM 1
+int rpw_set_plane_solver(rpw_handle* h, int solver);
+
 /* Use a caller-owned CUDA stream (cudaStream_t passed as void*; NULL = the handle's own stream).
  * All copies and kernels of later calls are enqueued on it. */
 int rpw_set_stream(rpw_handle* h, void* cuda_stream);
@@ -176,8 +191,20 @@ int rpw_debug_nodes(rpw_handle* h, rpw_node* out, size_t cap, size_t* count);
 /* Runs the device 3x3 symmetric eigensolver on `count` row-major matrices (host in / host out):
  * evals (3 per matrix, ascending), evecs (9 per matrix, column c = eigenvector c). */
 int rpw_debug_eig3(rpw_handle* h, const float* mats, size_t count, float* evals, float* evecs);
+/* Runs the plane-normal solver the fit kernel uses on `count` scatter matrices (6 floats each:
+ * xx yx yy zx zy zz; one warp per matrix): mode 0 = closed-form FP64 smallest eigenvector, mode 1 = Eigen's QR sequence
+ * (generic form, the one rpw_debug_eig3 runs), mode 2 = the same sequence restructured for latency (what the
+ * fit kernel runs by default; bit-identical to mode 1).  normals3: unit normals with z >= 0; cycles: SM cycles
+ * one call took. */
+int rpw_debug_normal(rpw_handle* h, const float* scatter6, size_t count, int mode, float* normals3, uint32_t* cycles);
 /* Runs the device restatement of libm atan2f on `count` (y, x) pairs. */
 int rpw_debug_atan2(rpw_handle* h, const float* y, const float* x, size_t count, float* out);
+
+/* Cycle accounting inside the fit kernel (thread 0 of every block; summed over blocks).  Reads and
+ * clears the 16 counters, then enables/disables the accounting for later calls.  Slots: 0 load+bbox,
+ * 1 seeds, 2 covariance pass, 3 eigensolve, 4 distance/mask pass, 5 final fit, 6 leaf label write,
+ * 7 split, 8 fetch, 9 grid barrier, 10 nodes, 11 plane-fit iterations. */
+int rpw_debug_fit_timing(rpw_handle* h, int enable, uint64_t* cycles16);
 
 /* ---- measurement -------------------------------------------------------------------------- */
 /* Device time per kernel, measured with CUDA events recorded on the handle's stream around every

@@ -15,6 +15,7 @@ LIB_PATH = PKG / "librpw_b200.so"
 RPW_OK, RPW_ERR_BAD_ARG, RPW_ERR_NO_DEVICE, RPW_ERR_CUDA, RPW_ERR_CAPACITY, RPW_ERR_ALLOC = range(6)
 LABEL_NONGROUND, LABEL_GROUND, LABEL_BEYOND, LABEL_DROPPED = 0, 1, 2, 3
 KEY_DROPPED, KEY_BEYOND, KEY_UNBINNED = 0xFFFF, 0xFFFE, 0xFFFD
+SOLVER_EIGEN_QR, SOLVER_CLOSED_FORM = 0, 1
 NODE_SMALL, NODE_AREA, NODE_FLAT, NODE_FIT, NODE_SPLIT = 1, 2, 3, 4, 5
 
 
@@ -46,9 +47,9 @@ NODE_DTYPE = np.dtype([("scan", "<i4"), ("root", "<i4"), ("depth", "<i4"), ("sta
 
 # Every symbol include/rpw_b200.h declares (tests check that the library exports all of them).
 EXPORTS = ["rpw_default_config", "rpw_zone_model", "rpw_create", "rpw_destroy", "rpw_set_config", "rpw_get_config",
-           "rpw_set_stream", "rpw_last_error", "rpw_segment", "rpw_segment_batch", "rpw_segment_batch_async", "rpw_wait",
+           "rpw_set_plane_solver", "rpw_set_stream", "rpw_last_error", "rpw_segment", "rpw_segment_batch", "rpw_segment_batch_async", "rpw_wait",
            "rpw_segment_clouds", "rpw_segment_device", "rpw_debug_keys", "rpw_debug_enable_nodes", "rpw_debug_nodes",
-           "rpw_debug_eig3", "rpw_debug_atan2", "rpw_profile_enable", "rpw_profile_read", "rpw_host_alloc", "rpw_host_free", "rpw_kernel_launches", "rpw_abi_version"]
+           "rpw_debug_eig3", "rpw_debug_normal", "rpw_debug_atan2", "rpw_debug_fit_timing", "rpw_profile_enable", "rpw_profile_read", "rpw_host_alloc", "rpw_host_free", "rpw_kernel_launches", "rpw_abi_version"]
 
 _lib = None
 
@@ -75,6 +76,7 @@ def load_library() -> C.CDLL:
     lib.rpw_destroy.argtypes = [vp]; lib.rpw_destroy.restype = None
     lib.rpw_set_config.argtypes = [vp, cfgp]; lib.rpw_set_config.restype = C.c_int
     lib.rpw_get_config.argtypes = [vp, cfgp]; lib.rpw_get_config.restype = C.c_int
+    lib.rpw_set_plane_solver.argtypes = [vp, C.c_int]; lib.rpw_set_plane_solver.restype = C.c_int
     lib.rpw_set_stream.argtypes = [vp, vp]; lib.rpw_set_stream.restype = C.c_int
     lib.rpw_last_error.argtypes = [vp]; lib.rpw_last_error.restype = C.c_char_p
     lib.rpw_segment.argtypes = [vp, vp, sz, sz, vp, C.POINTER(RpwStats)]; lib.rpw_segment.restype = C.c_int
@@ -90,7 +92,9 @@ def load_library() -> C.CDLL:
     lib.rpw_debug_enable_nodes.argtypes = [vp, C.c_int]; lib.rpw_debug_enable_nodes.restype = C.c_int
     lib.rpw_debug_nodes.argtypes = [vp, vp, sz, C.POINTER(sz)]; lib.rpw_debug_nodes.restype = C.c_int
     lib.rpw_debug_eig3.argtypes = [vp, vp, sz, vp, vp]; lib.rpw_debug_eig3.restype = C.c_int
+    lib.rpw_debug_normal.argtypes = [vp, vp, sz, C.c_int, vp, vp]; lib.rpw_debug_normal.restype = C.c_int
     lib.rpw_debug_atan2.argtypes = [vp, vp, vp, sz, vp]; lib.rpw_debug_atan2.restype = C.c_int
+    lib.rpw_debug_fit_timing.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64)]; lib.rpw_debug_fit_timing.restype = C.c_int
     lib.rpw_profile_enable.argtypes = [vp, C.c_int]; lib.rpw_profile_enable.restype = C.c_int
     lib.rpw_profile_read.argtypes = [vp, C.POINTER(RpwProfile)]; lib.rpw_profile_read.restype = C.c_int
     lib.rpw_host_alloc.argtypes = [sz]; lib.rpw_host_alloc.restype = vp
@@ -177,6 +181,10 @@ class Handle:
         self._check(self.lib.rpw_get_config(self._h, C.byref(c)))
         return c
 
+    def set_plane_solver(self, solver: int):
+        """SOLVER_EIGEN_QR (0, default, reference-faithful) or SOLVER_CLOSED_FORM (1, faster)."""
+        self._check(self.lib.rpw_set_plane_solver(self._h, int(solver)))
+
     def set_stream(self, cuda_stream: int | None):
         self._check(self.lib.rpw_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
 
@@ -260,12 +268,26 @@ class Handle:
         self._check(self.lib.rpw_debug_eig3(self._h, m.ctypes.data, len(m), ev.ctypes.data, vec.ctypes.data))
         return ev, vec
 
+    def debug_normal(self, scatter6, mode=0):
+        m = np.ascontiguousarray(scatter6, np.float32).reshape(-1, 6)
+        nrm = np.empty((len(m), 3), np.float32)
+        cyc = np.empty(len(m), np.uint32)
+        self._check(self.lib.rpw_debug_normal(self._h, m.ctypes.data, len(m), mode, nrm.ctypes.data, cyc.ctypes.data))
+        return nrm, cyc
+
     def debug_atan2(self, y, x):
         y = np.ascontiguousarray(y, np.float32)
         x = np.ascontiguousarray(x, np.float32)
         out = np.empty_like(y)
         self._check(self.lib.rpw_debug_atan2(self._h, y.ctypes.data, x.ctypes.data, y.size, out.ctypes.data))
         return out
+
+    def fit_timing(self, enable=True):
+        """Reads+clears the fit kernel's cycle counters, then switches the accounting on/off."""
+        out = (C.c_uint64 * 16)()
+        self._check(self.lib.rpw_debug_fit_timing(self._h, 1 if enable else 0, out))
+        names = ["load", "seeds", "cov", "eig", "dist", "final", "label", "split", "fetch", "gridsync", "nodes", "iters", "cov_reduce", "dist_reduce", "qr_only"]
+        return {k: int(out[i]) for i, k in enumerate(names)}
 
     def profile_enable(self, on=True):
         self._check(self.lib.rpw_profile_enable(self._h, 1 if on else 0))

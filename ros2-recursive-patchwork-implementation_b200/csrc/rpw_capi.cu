@@ -25,6 +25,8 @@ struct rpw_handle {
     int num_sms = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};  // the fit size classes run concurrently
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     size_t cap_points = 0, cap_batch = 0;
     int P = 0;
     int levels_cap = 0;
@@ -32,6 +34,7 @@ struct rpw_handle {
     int smem_cap = 0;
     int fit_blocks = 0;
     int wave_scans = 0;  // scans per launch group (0 = whole batch)
+    int solver = RPW_SOLVER_EIGEN_QR;
 
     // device buffers
     float* d_in = nullptr;       // staged input (12 or 16 bytes per point)
@@ -51,6 +54,8 @@ struct rpw_handle {
     uint64_t* d_scan_off = nullptr;
     uint32_t* d_chunk_base = nullptr;
     rpw_node* d_dbg_nodes = nullptr;
+    unsigned long long* d_timing = nullptr;  // [16], allocated by rpw_debug_fit_timing
+    bool timing_enabled = false;
     uint32_t dbg_cap = 0;
     bool dbg_enabled = false;
 
@@ -141,6 +146,7 @@ static void apply_config(rpw_handle* h, const rpw_config* c) {
     h->fp.max_iter = c->max_iter;
     h->fp.adaptive_seed_height = c->adaptive_seed_height;
     h->fp.max_split_depth = c->max_split_depth;
+    h->fp.exact_eig = h->solver == RPW_SOLVER_EIGEN_QR ? 1 : 0;
 }
 
 static void free_patch_buffers(rpw_handle* h) {
@@ -182,13 +188,15 @@ void rpw_destroy(rpw_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_in); cudaFree(h->d_keys); cudaFree(h->d_labels); cudaFree(h->d_sortedA); cudaFree(h->d_bufB);
     cudaFree(h->d_bufC); cudaFree(h->d_gmask); cudaFree(h->d_queue[0]); cudaFree(h->d_queue[1]); cudaFree(h->d_counters);
-    cudaFree(h->d_scan_off); cudaFree(h->d_chunk_base); cudaFree(h->d_dbg_nodes);
+    cudaFree(h->d_scan_off); cudaFree(h->d_chunk_base); cudaFree(h->d_dbg_nodes); cudaFree(h->d_timing);
     free_patch_buffers(h);
     if (h->h_meta) cudaFreeHost(h->h_meta);
     if (h->h_stage_in) cudaFreeHost(h->h_stage_in);
     if (h->h_stage_labels) cudaFreeHost(h->h_stage_labels);
     if (h->h_stats) cudaFreeHost(h->h_stats);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+    for (int k = 0; k < 3; ++k) { if (h->side[k]) cudaStreamDestroy(h->side[k]); if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]); }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -221,6 +229,7 @@ int rpw_create(const rpw_config* cfg, int device, size_t max_total_points, size_
     h->num_sms = prop.multiProcessorCount;
     h->cap_points = max_total_points;
     h->cap_batch = max_batch;
+    if (const char* s = getenv("RPW_PLANE_SOLVER")) h->solver = atoi(s) == RPW_SOLVER_CLOSED_FORM ? RPW_SOLVER_CLOSED_FORM : RPW_SOLVER_EIGEN_QR;
     apply_config(h, &c);
     int rc = RPW_OK;
     auto fail = [&](int code) { g_create_error = h->err; rpw_destroy(h); return code; };
@@ -229,6 +238,11 @@ int rpw_create(const rpw_config* cfg, int device, size_t max_total_points, size_
     TRYC(cudaSetDevice(device));
     TRYC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
+    for (int k = 0; k < 3; ++k) {
+        TRYC(cudaStreamCreateWithFlags(&h->side[k], cudaStreamNonBlocking));
+        TRYC(cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming));
+    }
+    TRYC(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     const size_t N = max_total_points;
     TRYC(cudaMalloc(&h->d_in, N * 16));
     TRYC(cudaMalloc(&h->d_keys, N * sizeof(uint16_t)));
@@ -279,6 +293,14 @@ int rpw_set_config(rpw_handle* h, const rpw_config* cfg) {
         int rc = alloc_level_buffers(h);
         if (rc != RPW_OK) return rc;
     }
+    return RPW_OK;
+}
+
+int rpw_set_plane_solver(rpw_handle* h, int solver) {
+    if (!h) return RPW_ERR_BAD_ARG;
+    if (solver != RPW_SOLVER_EIGEN_QR && solver != RPW_SOLVER_CLOSED_FORM) RPW_FAIL(h, RPW_ERR_BAD_ARG, "unknown plane solver %d", solver);
+    h->solver = solver;
+    h->fp.exact_eig = solver == RPW_SOLVER_EIGEN_QR ? 1 : 0;
     return RPW_OK;
 }
 
@@ -410,6 +432,7 @@ static int run_pipeline(rpw_handle* h, const float* d_pts, int stride_floats, ui
         A.dbg_nodes = h->dbg_enabled ? h->d_dbg_nodes : nullptr;
         A.dbg_count = A.stats + 9;
         A.dbg_cap = h->dbg_cap;
+        A.timing = h->timing_enabled ? h->d_timing : nullptr;
         A.q_cap = h->q_cap;
         A.n_roots = (int)(nb * (size_t)h->P);
         A.n_scans = (int)nb;
@@ -418,10 +441,28 @@ static int run_pipeline(rpw_handle* h, const float* d_pts, int stride_floats, ui
         A.smem_cap = h->smem_cap;
         A.fp = h->fp;
         A.scan_base = (uint32_t)b0;
-        { ProfScope ps(h, 3);
-        RPW_CUDA(h, launch_fit(h->stream, A, h->fit_blocks)); }
-        h->launches += 4;
-        h->launches_call += 4;
+        {
+            ProfScope ps(h, 3);
+            // level 0: three size classes on side streams (largest first), joined back before
+            // the cooperative kernel that walks the deeper levels
+            static const char* dbg_mask = getenv("RPW_DBG_CLASS_MASK");   // experiments: bit k = run class k
+            static const char* dbg_serial = getenv("RPW_DBG_SERIAL");
+            const int mask = dbg_mask ? atoi(dbg_mask) : 7;
+            if (dbg_serial) {
+                for (int k = 0; k < 3; ++k) if (mask & (1 << (2 - k))) RPW_CUDA(h, launch_fit_roots(h->stream, A, 2 - k));
+            } else {
+            RPW_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
+            for (int k = 0; k < 3; ++k) {
+                RPW_CUDA(h, cudaStreamWaitEvent(h->side[k], h->ev_fork, 0));
+                if (mask & (1 << (2 - k))) RPW_CUDA(h, launch_fit_roots(h->side[k], A, 2 - k));
+                RPW_CUDA(h, cudaEventRecord(h->ev_join[k], h->side[k]));
+            }
+            for (int k = 0; k < 3; ++k) RPW_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join[k], 0));
+            }
+            RPW_CUDA(h, launch_fit_levels(h->stream, A, h->fit_blocks));
+        }
+        h->launches += 7;
+        h->launches_call += 7;
     }
     return RPW_OK;
 }
@@ -684,6 +725,25 @@ int rpw_debug_eig3(rpw_handle* h, const float* mats, size_t count, float* evals,
     return RPW_OK;
 }
 
+int rpw_debug_normal(rpw_handle* h, const float* scatter6, size_t count, int mode, float* normals3, uint32_t* cycles) {
+    if (!h || !scatter6 || !normals3 || !cycles) return RPW_ERR_BAD_ARG;
+    if (count == 0) return RPW_OK;
+    RPW_CUDA(h, cudaSetDevice(h->device));
+    float *ds = nullptr, *dn = nullptr;
+    uint32_t* dc = nullptr;
+    RPW_CUDA(h, cudaMalloc(&ds, count * 6 * sizeof(float)));
+    RPW_CUDA(h, cudaMalloc(&dn, count * 3 * sizeof(float)));
+    RPW_CUDA(h, cudaMalloc(&dc, count * sizeof(uint32_t)));
+    RPW_CUDA(h, cudaMemcpyAsync(ds, scatter6, count * 6 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    RPW_CUDA(h, launch_normal(h->stream, ds, count, mode, dn, dc));
+    h->launches++;
+    RPW_CUDA(h, cudaMemcpyAsync(normals3, dn, count * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    RPW_CUDA(h, cudaMemcpyAsync(cycles, dc, count * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    RPW_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(ds); cudaFree(dn); cudaFree(dc);
+    return RPW_OK;
+}
+
 int rpw_debug_atan2(rpw_handle* h, const float* y, const float* x, size_t count, float* out) {
     if (!h || !y || !x || !out) return RPW_ERR_BAD_ARG;
     if (count == 0) return RPW_OK;
@@ -699,6 +759,20 @@ int rpw_debug_atan2(rpw_handle* h, const float* y, const float* x, size_t count,
     RPW_CUDA(h, cudaMemcpyAsync(out, dout, count * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     RPW_CUDA(h, cudaStreamSynchronize(h->stream));
     cudaFree(dy); cudaFree(dx); cudaFree(dout);
+    return RPW_OK;
+}
+
+int rpw_debug_fit_timing(rpw_handle* h, int enable, uint64_t* cycles16) {
+    if (!h) return RPW_ERR_BAD_ARG;
+    RPW_CUDA(h, cudaSetDevice(h->device));
+    if (!h->d_timing) {
+        RPW_CUDA(h, cudaMalloc(&h->d_timing, 16 * sizeof(unsigned long long)));
+        RPW_CUDA(h, cudaMemset(h->d_timing, 0, 16 * sizeof(unsigned long long)));
+    }
+    RPW_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (cycles16) RPW_CUDA(h, cudaMemcpy(cycles16, h->d_timing, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    RPW_CUDA(h, cudaMemset(h->d_timing, 0, 16 * sizeof(unsigned long long)));
+    h->timing_enabled = enable != 0;
     return RPW_OK;
 }
 

@@ -5,11 +5,13 @@
 //   K1b rpw_offsets_kernel  per-scan exclusive scan of the block histograms -> stable offsets
 //   K2  rpw_scatter_kernel  stable counting-sort scatter of (x, y, z, input index) into
 //                           ring/sector patch segments (input order inside every patch, Q1)
-//   K3  rpw_fit_kernel      persistent cooperative kernel: level-synchronous device worklist over
-//                           fitPlaneAndSplit nodes (RP/src/recursive_patchwork.cpp:109-308);
+//   K3a rpw_fit_roots_kernel  fitPlaneAndSplit at depth 0 (RP/src/recursive_patchwork.cpp:109-308), one
+//                           block per ring/sector patch, three size classes running concurrently;
 //                           per node: early-outs, seeds, iterated PCA plane fit with a register
 //                           3x3 eigensolve, residual mask, split (variance axis, exact radix-select
 //                           median, stable partition), child enqueue, label scatter
+//   K3b rpw_fit_levels_kernel persistent cooperative kernel: level-synchronous device worklist over
+//                           the children of split nodes (depth >= 1), no host round trips
 //   dbg rpw_eig3_kernel / rpw_atan2_kernel   unit-test entry points for the device math
 //
 // All of it is HBM/L2/shared-memory bound integer-and-float SIMT work; there is no dense
@@ -216,41 +218,86 @@ __global__ void __launch_bounds__(kBinThreads) rpw_scatter_kernel(const float* _
 // =============================================================================================
 struct FitSmem {
     float* x; float* y; float* z; uint8_t* m;
-    float* red;        // 2 * kFitWarps * kRedMax floats (ping-pong)
+    float* red;        // 2 * (TT / 32) * kRedMax floats (ping-pong)
     uint32_t* hist;    // 256
     uint32_t* misc;    // small broadcast area
 };
 
-constexpr int kRedMax = 8;
+constexpr int kRedMax = 16;
+constexpr int kCapTiny = 1024;   // points a 64-thread block keeps in shared memory
+constexpr int kCapSmall = 4096;  // points a 128-thread block keeps in shared memory
 
 // Sum of K floats over the block; every thread receives the totals (bitwise identical in all
-// threads: butterfly shuffles of a commutative op).  One __syncthreads per call; the scratch
-// area alternates so that back-to-back calls do not race.
-template <int K>
+// threads).  One __syncthreads per call; the scratch area alternates so that back-to-back calls do
+// not race.  Inside a warp the K running sums are reduce-scattered (at every butterfly step a lane
+// hands half of its values to its partner and keeps the other half), so K values cost about K + 4
+// shuffles instead of 5 K; after the barrier every warp folds the 8 per-warp partials and
+// broadcasts the totals with one shuffle each.
+template <int TT, int K>
 __device__ __forceinline__ void block_sum(float (&v)[K], float* red, int& phase) {
+    static_assert(K <= 16, "block_sum handles at most 16 values");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], d);
-    }
-    float* r = red + phase * (kFitWarps * kRedMax);
+    float* r = red + phase * ((TT / 32) * 16);
     phase ^= 1;
-    if (lane == 0) {
+    if (K <= 2) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) r[warp * kRedMax + k] = v[k];
+        for (int k = 0; k < K; ++k) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], d);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) r[warp * 16 + k] = v[k];
+        }
+    } else {
+        float w[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) w[k] = k < K ? v[k] : 0.f;
+        // 16 -> 8 -> 4 -> 2 -> 1 values per lane; lane bit (4,3,2,1) selects the half that is kept
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool up = lane & 16;
+            const float send = up ? w[j] : w[j + 8];
+            const float keep = up ? w[j + 8] : w[j];
+            w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool up = lane & 8;
+            const float send = up ? w[j] : w[j + 4];
+            const float keep = up ? w[j + 4] : w[j];
+            w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const bool up = lane & 4;
+            const float send = up ? w[j] : w[j + 2];
+            const float keep = up ? w[j + 2] : w[j];
+            w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        {
+            const bool up = lane & 2;
+            const float send = up ? w[0] : w[1];
+            const float keep = up ? w[1] : w[0];
+            w[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+        w[0] += __shfl_xor_sync(0xffffffffu, w[0], 1);
+        // the value index this lane ended up with: bit4 -> 8, bit3 -> 4, bit2 -> 2, bit1 -> 1
+        const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+        if ((lane & 1) == 0) r[warp * 16 + idx] = w[0];
     }
     __syncthreads();
+    // fold the per-warp partials: lane l sums value (l & 15) over warps (l >> 4) * 4 .. + 3
+    const int val = lane & 15, half = lane >> 4;
+    float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        float t = r[(lane & (kFitWarps - 1)) * kRedMax + k];
+    for (int q = 0; q < (TT / 32) / 2; ++q) t += r[(half * ((TT / 32) / 2) + q) * 16 + val];
+    t += __shfl_xor_sync(0xffffffffu, t, 16);
 #pragma unroll
-        for (int d = kFitWarps / 2; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
-        v[k] = t;
-    }
+    for (int k = 0; k < K; ++k) v[k] = __shfl_sync(0xffffffffu, t, k);
 }
 
-template <int K>
+template <int TT, int K>
 __device__ __forceinline__ void block_min(float (&v)[K], float* red, int& phase) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -258,7 +305,7 @@ __device__ __forceinline__ void block_min(float (&v)[K], float* red, int& phase)
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) v[k] = fminf(v[k], __shfl_xor_sync(0xffffffffu, v[k], d));
     }
-    float* r = red + phase * (kFitWarps * kRedMax);
+    float* r = red + phase * ((TT / 32) * kRedMax);
     phase ^= 1;
     if (lane == 0) {
 #pragma unroll
@@ -267,14 +314,15 @@ __device__ __forceinline__ void block_min(float (&v)[K], float* red, int& phase)
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        float t = r[(lane & (kFitWarps - 1)) * kRedMax + k];
+        float t = r[(lane & ((TT / 32) - 1)) * kRedMax + k];
 #pragma unroll
-        for (int d = kFitWarps / 2; d > 0; d >>= 1) t = fminf(t, __shfl_xor_sync(0xffffffffu, t, d));
+        for (int d = (TT / 32) / 2; d > 0; d >>= 1) t = fminf(t, __shfl_xor_sync(0xffffffffu, t, d));
         v[k] = t;
     }
 }
 
 // min over the block of a 64-bit key; all threads get the result.
+template <int TT>
 __device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v, float* red, int& phase) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -282,13 +330,13 @@ __device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v
         const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, d);
         v = o < v ? o : v;
     }
-    unsigned long long* r = reinterpret_cast<unsigned long long*>(red + phase * (kFitWarps * kRedMax));
+    unsigned long long* r = reinterpret_cast<unsigned long long*>(red + phase * ((TT / 32) * kRedMax));
     phase ^= 1;
     if (lane == 0) r[warp] = v;
     __syncthreads();
-    unsigned long long t = r[lane & (kFitWarps - 1)];
+    unsigned long long t = r[lane & ((TT / 32) - 1)];
 #pragma unroll
-    for (int d = kFitWarps / 2; d > 0; d >>= 1) {
+    for (int d = (TT / 32) / 2; d > 0; d >>= 1) {
         const unsigned long long o = __shfl_xor_sync(0xffffffffu, t, d);
         t = o < t ? o : t;
     }
@@ -316,15 +364,15 @@ struct NodeView {
 
 // k-th smallest (0-based) of one coordinate over the node: exact 4x8-bit radix select.
 // Reference: std::sort + index (RP/src/recursive_patchwork.cpp:156-159, :259-260, :267-268).
-template <bool SMEM>
+template <int TT, bool SMEM>
 __device__ float radix_select(const NodeView<SMEM>& nv, uint32_t n, int axis, uint32_t k) {
     uint32_t* hist = nv.s.hist;
     uint32_t* misc = nv.s.misc;
     uint32_t prefix = 0, pmask = 0;
     for (int shift = 24; shift >= 0; shift -= 8) {
-        for (int i = threadIdx.x; i < 256; i += kFitThreads) hist[i] = 0;
+        for (int i = threadIdx.x; i < 256; i += TT) hist[i] = 0;
         __syncthreads();
-        for (uint32_t i = threadIdx.x; i < n; i += kFitThreads) {
+        for (uint32_t i = threadIdx.x; i < n; i += TT) {
             const uint32_t u = f2ord(nv.coord(i, axis));
             if ((u & pmask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
         }
@@ -381,20 +429,85 @@ __device__ __forceinline__ void dbg_record(const FitArgs& A, const NodeRef& nd, 
 // Labels of a whole node set to one value (early-outs; RP/src/recursive_patchwork.cpp:111-113,
 // :126-129, :138-140).  Slot j of the node labels input point sortedA[start + j].w — the
 // positional read-back of SURVEY Q1.
+template <int TT>
 __device__ __forceinline__ void label_const(const FitArgs& A, const NodeRef& nd, uint8_t v) {
-    for (uint32_t i = threadIdx.x; i < nd.n; i += kFitThreads)
+    for (uint32_t i = threadIdx.x; i < nd.n; i += TT)
         A.labels[__float_as_uint(A.sortedA[nd.start + i].w)] = v;
 }
 
-template <bool SMEM>
+// Strided loop over a node's points, four rows per trip: the loads of a trip are issued together
+// before any of its arithmetic (memory-level parallelism instead of one dependent chain per row).
+// body(i, x, y, z, m) sees point i with its current mask byte.
+constexpr int kUnroll = 4;
+template <int TT, bool SMEM, bool WITH_MASK, typename F>
+__device__ __forceinline__ void for_points(const NodeView<SMEM>& nv, uint32_t n, F body) {
+    uint32_t i = threadIdx.x;
+    for (; i + (kUnroll - 1) * TT < n; i += kUnroll * TT) {
+        float x[kUnroll], y[kUnroll], z[kUnroll];
+        uint8_t m[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            nv.get(i + u * TT, x[u], y[u], z[u]);
+            m[u] = WITH_MASK ? nv.mask(i + u * TT) : (uint8_t)1;
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) body(i + u * TT, x[u], y[u], z[u], m[u]);
+    }
+    for (; i < n; i += TT) {
+        float x, y, z;
+        nv.get(i, x, y, z);
+        body(i, x, y, z, WITH_MASK ? nv.mask(i) : (uint8_t)1);
+    }
+}
+
+// Optional cycle accounting (rpw_debug_fit_timing): thread 0 of every block adds the cycles it spent
+// in each section of process_node to A.timing[section].  Sections: 0 load+bbox, 1 seeds, 2 covariance
+// pass + reduce, 3 eigensolve + broadcast, 4 distance/mask pass + reduce, 5 final fit, 6 leaf label
+// write, 7 split, 8 fetch / between nodes, 9 grid barrier, 10 nodes, 11 plane-fit iterations.
+struct Tick {
+    unsigned long long* t;
+    long long last;
+    __device__ __forceinline__ Tick(unsigned long long* timing) : t(timing), last(0) { if (t && threadIdx.x == 0) last = clock64(); }
+    __device__ __forceinline__ void operator()(int slot) {
+        if (t && threadIdx.x == 0) { const long long now = clock64(); atomicAdd(t + slot, (unsigned long long)(now - last)); last = now; }
+    }
+    __device__ __forceinline__ void count(int slot, unsigned v) { if (t && threadIdx.x == 0) atomicAdd(t + slot, (unsigned long long)v); }
+};
+
+// Plane normal from the scatter sums of the current inliers (fitPlanePCA, :86-95): smallest-
+// eigenvalue eigenvector, flipped to z >= 0.  Computed by warp 0, broadcast through shared memory.
+template <bool EXACT>
+__device__ __forceinline__ void plane_normal(const float (&cv)[6], float cnt, float* bc, float& nx, float& ny, float& nz,
+                                             unsigned long long* timing = nullptr) {
+    if (threadIdx.x < 32) {
+        float ax, ay, az;
+        if (EXACT) {
+            const float d = cnt - 1.f;  // computeCovariance divides by n-1 (point_cloud_processor.cpp:84)
+            const float c0 = cv[0] / d, c1 = cv[1] / d, c2 = cv[2] / d, c3 = cv[3] / d, c4 = cv[4] / d, c5 = cv[5] / d;
+            long long t0 = 0;
+            if (timing && threadIdx.x == 0) t0 = clock64();
+            eig3_smallest_qr(c0, c1, c2, c3, c4, c5, ax, ay, az);
+            if (timing && threadIdx.x == 0) atomicAdd(timing + 14, (unsigned long long)(clock64() - t0));
+        } else {
+            smallest_eigvec_psd(cv[0], cv[1], cv[2], cv[3], cv[4], cv[5], ax, ay, az);
+        }
+        if (az < 0.f) { ax = -ax; ay = -ay; az = -az; }  // :93-95
+        if (threadIdx.x == 0) { bc[0] = ax; bc[1] = ay; bc[2] = az; }
+    }
+    __syncthreads();
+    nx = bc[0]; ny = bc[1]; nz = bc[2];
+}
+
+template <int TT, bool SMEM, bool EXACT>
 __device__ void process_node(const FitArgs& A, const NodeRef nd, const int depth, FitSmem S) {
     const FitParams& fp = A.fp;
     const uint32_t n = nd.n;
     const int tid = threadIdx.x;
     int phase = 0;
+    Tick tick(A.timing);
 
     if (n < 3 || depth > fp.max_split_depth) {  // :111-113
-        label_const(A, nd, 0);
+        label_const<TT>(A, nd, 0);
         if (tid == 0) dbg_record(A, nd, depth, RPW_NODE_SMALL, 0, 0, -1, 0, 0, 0, 0, 0, 1, FLT_MAX, 0, 0);
         return;
     }
@@ -406,31 +519,40 @@ __device__ void process_node(const FitArgs& A, const NodeRef nd, const int depth
     // ---- pass 1: load, bounding box, (root only) mean range ------------------------------
     float mm[6] = {FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX};  // min x,y,z, min -x,-y,-z
     float sd[1] = {0.f};
-    for (uint32_t i = tid; i < n; i += kFitThreads) {
-        const float4 v = depth == 0 ? __ldg(nv.src + i) : __ldcg(nv.src + i);
-        if (SMEM) { S.x[i] = v.x; S.y[i] = v.y; S.z[i] = v.z; }
-        mm[0] = fminf(mm[0], v.x); mm[1] = fminf(mm[1], v.y); mm[2] = fminf(mm[2], v.z);
-        mm[3] = fminf(mm[3], -v.x); mm[4] = fminf(mm[4], -v.y); mm[5] = fminf(mm[5], -v.z);
-        if (depth == 0) sd[0] += range2d(v.x, v.y);
+    {
+        auto take = [&](uint32_t i, const float4 v) {
+            if (SMEM) { S.x[i] = v.x; S.y[i] = v.y; S.z[i] = v.z; }
+            mm[0] = fminf(mm[0], v.x); mm[1] = fminf(mm[1], v.y); mm[2] = fminf(mm[2], v.z);
+            mm[3] = fminf(mm[3], -v.x); mm[4] = fminf(mm[4], -v.y); mm[5] = fminf(mm[5], -v.z);
+            if (depth == 0) sd[0] += range2d(v.x, v.y);
+        };
+        uint32_t i = tid;
+        for (; i + 3 * TT < n; i += 4 * TT) {
+            const float4 v0 = __ldcg(nv.src + i), v1 = __ldcg(nv.src + i + TT);
+            const float4 v2 = __ldcg(nv.src + i + 2 * TT), v3 = __ldcg(nv.src + i + 3 * TT);
+            take(i, v0); take(i + TT, v1); take(i + 2 * TT, v2); take(i + 3 * TT, v3);
+        }
+        for (; i < n; i += TT) take(i, __ldcg(nv.src + i));
     }
-    block_min<6>(mm, S.red, phase);
+    block_min<TT, 6>(mm, S.red, phase);
     float mean_dist;
     if (depth == 0) {
-        block_sum<1>(sd, S.red, phase);
+        block_sum<TT, 1>(sd, S.red, phase);
         mean_dist = sd[0] / (float)n;  // :383-387
         if (tid == 0) A.root_mean[nd.root] = mean_dist;
     } else {
         mean_dist = __ldcg(A.root_mean + nd.root);  // Q4: inherited unchanged
     }
+    tick(0);
     const float x_min = mm[0], x_max = -mm[3], y_min = mm[1], y_max = -mm[4], z_min = mm[2], z_max = -mm[5];
     const float area = (x_max - x_min) * (y_max - y_min);
     if (area < 25.0f && depth > 0) {  // :126-129
-        label_const(A, nd, 1);
+        label_const<TT>(A, nd, 1);
         if (tid == 0) dbg_record(A, nd, depth, RPW_NODE_AREA, 0, 0, -1, 0, 0, 0, 0, 0, 1, FLT_MAX, 0, mean_dist);
         return;
     }
     if ((z_max - z_min) < 0.05f && n > 10) {  // :138-140
-        label_const(A, nd, 1);
+        label_const<TT>(A, nd, 1);
         if (tid == 0) dbg_record(A, nd, depth, RPW_NODE_FLAT, 0, 0, -1, 0, 0, 0, 0, 0, 1, FLT_MAX, 0, mean_dist);
         return;
     }
@@ -443,39 +565,37 @@ __device__ void process_node(const FitArgs& A, const NodeRef nd, const int depth
         z_th = fp.sensor_height + 0.2f * rel_dist;
     } else {
         const uint32_t idx = (uint32_t)(0.1f * (float)n);
-        z_th = radix_select<SMEM>(nv, n, 2, idx) + fp.th_seeds;
+        z_th = radix_select<TT, SMEM>(nv, n, 2, idx) + fp.th_seeds;
     }
     const float tau = fp.th_dist * (1.0f + 0.2f * rel_dist);  // :203
 
     // ---- seeds (:163-182) -------------------------------------------------------------------
     float acc[4] = {0.f, 0.f, 0.f, 0.f};  // count, sum x, sum y, sum z over the mask
-    for (uint32_t i = tid; i < n; i += kFitThreads) {
-        float x, y, z;
-        nv.get(i, x, y, z);
-        const uint8_t m = z < z_th;
-        nv.set_mask(i, m);
-        if (m) { acc[0] += 1.f; acc[1] += x; acc[2] += y; acc[3] += z; }
-    }
-    block_sum<4>(acc, S.red, phase);
+    for_points<TT, SMEM, false>(nv, n, [&](uint32_t i, float x, float y, float z, uint8_t) {
+        const bool m = z < z_th;
+        nv.set_mask(i, m ? 1 : 0);
+        acc[0] += m ? 1.f : 0.f; acc[1] += m ? x : 0.f; acc[2] += m ? y : 0.f; acc[3] += m ? z : 0.f;
+    });
+    block_sum<TT, 4>(acc, S.red, phase);
     if (acc[0] < 3.f) {
         // the three lowest-z points, lowest index first among equal z (std::partial_sort at
         // :175-176 leaves ties unspecified)
         uint32_t chosen[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
         for (int r = 0; r < 3; ++r) {
             unsigned long long best = ~0ull;
-            for (uint32_t i = tid; i < n; i += kFitThreads) {
+            for (uint32_t i = tid; i < n; i += TT) {
                 if (i == chosen[0] || i == chosen[1]) continue;
                 const unsigned long long key = ((unsigned long long)f2ord(nv.coord(i, 2)) << 32) | i;
                 best = key < best ? key : best;
             }
-            best = block_min_u64(best, S.red, phase);
+            best = block_min_u64<TT>(best, S.red, phase);
             chosen[r] = (uint32_t)(best & 0xFFFFFFFFu);
         }
         // ascending index so that the 3-term sums follow the reference's order
         if (chosen[0] > chosen[1]) { const uint32_t t = chosen[0]; chosen[0] = chosen[1]; chosen[1] = t; }
         if (chosen[1] > chosen[2]) { const uint32_t t = chosen[1]; chosen[1] = chosen[2]; chosen[2] = t; }
         if (chosen[0] > chosen[1]) { const uint32_t t = chosen[0]; chosen[0] = chosen[1]; chosen[1] = t; }
-        for (uint32_t i = tid; i < n; i += kFitThreads) nv.set_mask(i, (i == chosen[0] || i == chosen[1] || i == chosen[2]) ? 1 : 0);
+        for (uint32_t i = tid; i < n; i += TT) nv.set_mask(i, (i == chosen[0] || i == chosen[1] || i == chosen[2]) ? 1 : 0);
         acc[0] = 3.f; acc[1] = acc[2] = acc[3] = 0.f;
         for (int r = 0; r < 3; ++r) {
             float x, y, z;
@@ -484,130 +604,134 @@ __device__ void process_node(const FitArgs& A, const NodeRef nd, const int depth
         }
     }
 
+    tick(1);
     // ---- iterated plane fit (:185-217) -------------------------------------------------------
+    // One pass per iteration: the distance pass that builds the next mask also accumulates that
+    // mask's first and second moments about the CURRENT centroid; the next centroid is mu + s/n and
+    // the next scatter matrix is S' - s s^T / n (the shift s/n is small, so nothing cancels badly).
+    // Only the very first fit (seeds) needs a separate covariance pass.
     float cnt = acc[0];
     float cx = acc[1] / cnt, cy = acc[2] / cnt, cz = acc[3] / cnt;  // computeCentroid
     float nx = 0.f, ny = 0.f, nz = 1.f, residual = FLT_MAX;
+    float cv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // scatter of the current mask about (cx, cy, cz): xx yx yy zx zy zz
+    bool have_cv = false;
     int iters = 0;
     bool have_final = false;  // final plane (:220-228) already known
     float* bc = reinterpret_cast<float*>(S.misc + 8);
+    auto covariance_pass = [&]() {  // computeCovariance about the centroid (point_cloud_processor.cpp:72-86)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) cv[k] = 0.f;
+        for_points<TT, SMEM, true>(nv, n, [&](uint32_t, float x, float y, float z, uint8_t m) {
+            // masked-out points contribute exact zeros
+            const float dx = m ? x - cx : 0.f, dy = m ? y - cy : 0.f, dz = m ? z - cz : 0.f;
+            cv[0] = fmaf(dx, dx, cv[0]); cv[1] = fmaf(dy, dx, cv[1]); cv[2] = fmaf(dy, dy, cv[2]);
+            cv[3] = fmaf(dz, dx, cv[3]); cv[4] = fmaf(dz, dy, cv[4]); cv[5] = fmaf(dz, dz, cv[5]);
+        });
+        block_sum<TT, 6>(cv, S.red, phase);
+        have_cv = true;
+    };
     for (int iter = 0; iter < fp.max_iter; ++iter) {
         if (cnt < 3.f) break;  // :196 — collapsed mask is kept (Q3)
-        // computeCovariance about the centroid (point_cloud_processor.cpp:72-86)
-        float cv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (uint32_t i = tid; i < n; i += kFitThreads) {
-            if (nv.mask(i)) {
-                float x, y, z;
-                nv.get(i, x, y, z);
-                const float dx = x - cx, dy = y - cy, dz = z - cz;
-                cv[0] = fmaf(dx, dx, cv[0]); cv[1] = fmaf(dy, dx, cv[1]); cv[2] = fmaf(dy, dy, cv[2]);
-                cv[3] = fmaf(dz, dx, cv[3]); cv[4] = fmaf(dz, dy, cv[4]); cv[5] = fmaf(dz, dz, cv[5]);
-            }
-        }
-        block_sum<6>(cv, S.red, phase);
-        if (tid < 32) {
-            const float d = cnt - 1.f;
-            const Eig3 E = eig3_sym(cv[0] / d, cv[1] / d, cv[2] / d, cv[3] / d, cv[4] / d, cv[5] / d);
-            float ax = E.vec[0][0], ay = E.vec[1][0], az = E.vec[2][0];
-            if (az < 0.f) { ax = -ax; ay = -ay; az = -az; }  // :93-95
-            if (tid == 0) { bc[0] = ax; bc[1] = ay; bc[2] = az; }
-        }
-        __syncthreads();
-        nx = bc[0]; ny = bc[1]; nz = bc[2];
+        if (!have_cv) covariance_pass();
+        tick(2);
+        plane_normal<EXACT>(cv, cnt, bc, nx, ny, nz, A.timing);
         iters++;
-        // distances, new mask, convergence, next centroid, residual of the fit just made
-        float st[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // new count, sum x, y, z, changed, sum |dist| over old mask
-        for (uint32_t i = tid; i < n; i += kFitThreads) {
-            float x, y, z;
-            nv.get(i, x, y, z);
-            const float dist = plane_dist(x, y, z, cx, cy, cz, nx, ny, nz);
-            const uint8_t om = nv.mask(i);
-            const uint8_t nm = dist < tau;
-            if (om) st[5] += dist;
-            if (nm != om) { st[4] = 1.f; nv.set_mask(i, nm); }
-            if (nm) { st[0] += 1.f; st[1] += x; st[2] += y; st[3] += z; }
-        }
-        block_sum<6>(st, S.red, phase);
+        tick(3);
+        // distances, new mask, convergence, residual of the fit just made, moments of the new mask
+        float st[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for_points<TT, SMEM, true>(nv, n, [&](uint32_t i, float x, float y, float z, uint8_t om) {
+            const float dx = x - cx, dy = y - cy, dz = z - cz;
+            const float p0 = dx * nx, p1 = dy * ny, p2 = dz * nz;
+            const float dist = fabsf(p0 + (p1 + p2));  // Eigen's dot order, see plane_dist
+            const bool nm = dist < tau;
+            st[5] += om ? dist : 0.f;
+            if (nm != (om != 0)) { st[4] = 1.f; nv.set_mask(i, nm ? 1 : 0); }
+            const float ex = nm ? dx : 0.f, ey = nm ? dy : 0.f, ez = nm ? dz : 0.f;
+            st[0] += nm ? 1.f : 0.f; st[1] += ex; st[2] += ey; st[3] += ez;
+            st[6] = fmaf(ex, ex, st[6]); st[7] = fmaf(ey, ex, st[7]); st[8] = fmaf(ey, ey, st[8]);
+            st[9] = fmaf(ez, ex, st[9]); st[10] = fmaf(ez, ey, st[10]); st[11] = fmaf(ez, ez, st[11]);
+        });
+        tick(4);
+        block_sum<TT, 12>(st, S.red, phase);
+        tick(13);
         if (st[4] == 0.f) {  // :215 converged: the final fit repeats this one
             residual = st[5] / cnt;
             have_final = true;
             break;
         }
         cnt = st[0];
-        if (cnt >= 3.f) { cx = st[1] / cnt; cy = st[2] / cnt; cz = st[3] / cnt; }
+        if (cnt >= 3.f) {
+            const float mx = st[1] / cnt, my = st[2] / cnt, mz = st[3] / cnt;  // centroid shift
+            cv[0] = fmaf(-st[1], mx, st[6]); cv[1] = fmaf(-st[2], mx, st[7]); cv[2] = fmaf(-st[2], my, st[8]);
+            cv[3] = fmaf(-st[3], mx, st[9]); cv[4] = fmaf(-st[3], my, st[10]); cv[5] = fmaf(-st[3], mz, st[11]);
+            cx += mx; cy += my; cz += mz;
+            have_cv = true;
+        }
     }
     // ---- final fit (:220-228) ----------------------------------------------------------------
     if (!have_final) {
         if (cnt >= 3.f) {
-            float cv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            for (uint32_t i = tid; i < n; i += kFitThreads) {
-                if (nv.mask(i)) {
-                    float x, y, z;
-                    nv.get(i, x, y, z);
-                    const float dx = x - cx, dy = y - cy, dz = z - cz;
-                    cv[0] = fmaf(dx, dx, cv[0]); cv[1] = fmaf(dy, dx, cv[1]); cv[2] = fmaf(dy, dy, cv[2]);
-                    cv[3] = fmaf(dz, dx, cv[3]); cv[4] = fmaf(dz, dy, cv[4]); cv[5] = fmaf(dz, dz, cv[5]);
-                }
-            }
-            block_sum<6>(cv, S.red, phase);
-            if (tid < 32) {
-                const float d = cnt - 1.f;
-                const Eig3 E = eig3_sym(cv[0] / d, cv[1] / d, cv[2] / d, cv[3] / d, cv[4] / d, cv[5] / d);
-                float ax = E.vec[0][0], ay = E.vec[1][0], az = E.vec[2][0];
-                if (az < 0.f) { ax = -ax; ay = -ay; az = -az; }
-                if (tid == 0) { bc[0] = ax; bc[1] = ay; bc[2] = az; }
-            }
-            __syncthreads();
-            nx = bc[0]; ny = bc[1]; nz = bc[2];
+            if (!have_cv) covariance_pass();
+            plane_normal<EXACT>(cv, cnt, bc, nx, ny, nz, A.timing);
             float rs[1] = {0.f};
-            for (uint32_t i = tid; i < n; i += kFitThreads) {
-                if (nv.mask(i)) {
-                    float x, y, z;
-                    nv.get(i, x, y, z);
-                    rs[0] += plane_dist(x, y, z, cx, cy, cz, nx, ny, nz);
-                }
-            }
-            block_sum<1>(rs, S.red, phase);
+            for_points<TT, SMEM, true>(nv, n, [&](uint32_t, float x, float y, float z, uint8_t m) {
+                rs[0] += m ? plane_dist(x, y, z, cx, cy, cz, nx, ny, nz) : 0.f;
+            });
+            block_sum<TT, 1>(rs, S.red, phase);
             residual = rs[0] / cnt;
         } else {
             cx = cy = cz = 0.f; nx = ny = 0.f; nz = 1.f; residual = FLT_MAX;  // :78-80
         }
     }
     const int n_in = (int)cnt;
+    tick(5);
+    tick.count(10, 1);
+    tick.count(11, (unsigned)iters);
 
     // ---- split decision (:231-235) -----------------------------------------------------------
     const float split_threshold = fp.th_dist * (1.0f + 1.5f * (float)depth);
     const uint32_t min_patch = (uint32_t)(50 + 10 * depth);
     if (!(residual > split_threshold && depth < fp.max_split_depth && n >= min_patch)) {
         // leaf: slot j labels input point sortedA[start + j].w (positional read-back, Q1)
-        for (uint32_t i = tid; i < n; i += kFitThreads)
-            A.labels[__float_as_uint(A.sortedA[nd.start + i].w)] = nv.mask(i);
+        {
+            const float4* rec = A.sortedA + nd.start;
+            uint32_t i = tid;
+            for (; i + 3 * TT < n; i += 4 * TT) {
+                uint32_t w[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) w[u] = __float_as_uint(__ldcg(&rec[i + u * TT].w));
+#pragma unroll
+                for (int u = 0; u < 4; ++u) A.labels[w[u]] = nv.mask(i + u * TT);
+            }
+            for (; i < n; i += TT) A.labels[__float_as_uint(__ldcg(&rec[i].w))] = nv.mask(i);
+        }
         if (tid == 0) dbg_record(A, nd, depth, RPW_NODE_FIT, iters, n_in, -1, cx, cy, cz, nx, ny, nz, residual, 0, mean_dist);
+        tick(6);
         return;
     }
 
     // ---- split (:238-283) --------------------------------------------------------------------
     float sxy[2] = {0.f, 0.f};
-    for (uint32_t i = tid; i < n; i += kFitThreads) {
+    for (uint32_t i = tid; i < n; i += TT) {
         float x, y, z;
         nv.get(i, x, y, z);
         sxy[0] += x; sxy[1] += y;
     }
-    block_sum<2>(sxy, S.red, phase);
+    block_sum<TT, 2>(sxy, S.red, phase);
     const float ccx = sxy[0] / (float)n, ccy = sxy[1] / (float)n;
     float var[2] = {0.f, 0.f};
-    for (uint32_t i = tid; i < n; i += kFitThreads) {
+    for (uint32_t i = tid; i < n; i += TT) {
         float x, y, z;
         nv.get(i, x, y, z);
         const float dx = x - ccx, dy = y - ccy;
         var[0] = fmaf(dx, dx, var[0]); var[1] = fmaf(dy, dy, var[1]);
     }
-    block_sum<2>(var, S.red, phase);
+    block_sum<TT, 2>(var, S.red, phase);
     const int axis = (var[0] / (float)n > var[1] / (float)n) ? 0 : 1;  // :250
-    const float median = radix_select<SMEM>(nv, n, axis, n / 2);       // upper median (Q7)
+    const float median = radix_select<TT, SMEM>(nv, n, axis, n / 2);       // upper median (Q7)
 
     // stable partition: thread t owns the contiguous run [t*per, (t+1)*per)
-    const uint32_t per = (n + kFitThreads - 1) / kFitThreads;
+    const uint32_t per = (n + TT - 1) / TT;
     const uint32_t lo = min(n, (uint32_t)tid * per), hi = min(n, lo + per);
     uint32_t nleft = 0;
     for (uint32_t i = lo; i < hi; ++i) nleft += nv.coord(i, axis) <= median;
@@ -625,7 +749,7 @@ __device__ void process_node(const FitArgs& A, const NodeRef nd, const int depth
     __syncthreads();
     uint32_t wbase = 0, total_left = 0;
 #pragma unroll
-    for (int w = 0; w < kFitWarps; ++w) {
+    for (int w = 0; w < (TT / 32); ++w) {
         const uint32_t v = wsum[w];
         if (w < warp) wbase += v;
         total_left += v;
@@ -646,11 +770,11 @@ __device__ void process_node(const FitArgs& A, const NodeRef nd, const int depth
     L.start = nd.start; L.n = total_left; L.root = nd.root; L.pad = 0;
     R.start = nd.start + total_left; R.n = n - total_left; R.root = nd.root; R.pad = 0;
     if (L.n < 3) {
-        label_const(A, L, 0);
+        label_const<TT>(A, L, 0);
         if (tid == 0) dbg_record(A, L, depth + 1, RPW_NODE_SMALL, 0, 0, -1, 0, 0, 0, 0, 0, 1, FLT_MAX, 0, 0);
     }
     if (R.n < 3) {
-        label_const(A, R, 0);
+        label_const<TT>(A, R, 0);
         if (tid == 0) dbg_record(A, R, depth + 1, RPW_NODE_SMALL, 0, 0, -1, 0, 0, 0, 0, 0, 1, FLT_MAX, 0, 0);
     }
     if (tid == 0) {
@@ -667,64 +791,91 @@ __device__ void process_node(const FitArgs& A, const NodeRef nd, const int depth
         }
         dbg_record(A, nd, depth, RPW_NODE_SPLIT, iters, n_in, axis, cx, cy, cz, nx, ny, nz, residual, median, mean_dist);
     }
+    tick(7);
 }
 
-__device__ __forceinline__ void run_node(const FitArgs& A, const NodeRef nd, int depth, FitSmem S) {
-    if (nd.n <= (uint32_t)A.smem_cap) process_node<true>(A, nd, depth, S);
-    else process_node<false>(A, nd, depth, S);
-}
-
-__global__ void __launch_bounds__(kFitThreads, 2) rpw_fit_kernel(FitArgs A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    cg::grid_group grid = cg::this_grid();
+__device__ __forceinline__ FitSmem carve_smem(unsigned char* raw, int cap, int warps) {
     FitSmem S;
-    S.x = reinterpret_cast<float*>(smem_raw);
-    S.y = S.x + A.smem_cap;
-    S.z = S.y + A.smem_cap;
-    S.red = S.z + A.smem_cap;
-    S.hist = reinterpret_cast<uint32_t*>(S.red + 2 * kFitWarps * kRedMax);
+    S.x = reinterpret_cast<float*>(raw);
+    S.y = S.x + cap;
+    S.z = S.y + cap;
+    S.red = S.z + cap;
+    S.hist = reinterpret_cast<uint32_t*>(S.red + 2 * warps * kRedMax);
     S.misc = S.hist + 256;
     S.m = reinterpret_cast<uint8_t*>(S.misc + 16);
-    __shared__ uint32_t s_fetch;
+    return S;
+}
 
-    // level 0: the ring/sector patches themselves
-    const uint32_t n_roots = (uint32_t)A.n_roots;
-    uint32_t n_done = 0;
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_fetch = atomicAdd(A.fetch_ctr + 0, 1u);
-        __syncthreads();
-        const uint32_t id = s_fetch;
-        if (id >= n_roots) break;
-        // largest patches first: id walks (patch rank, scan)
-        const uint32_t b = id % (uint32_t)A.n_scans, p = A.patch_order[id / (uint32_t)A.n_scans];
-        const uint32_t* ps = A.patch_start + (size_t)b * (A.P + 1) + p;
-        NodeRef nd;
-        nd.start = ps[0]; nd.n = ps[1] - ps[0]; nd.root = b * (uint32_t)A.P + p; nd.pad = 0;
-        if (nd.n == 0) continue;  // :380
-        run_node(A, nd, 0, S);
-        n_done++;
-    }
-    // deeper levels: level-synchronous, no host round trip
+// ---------------------------------------------------------------------------------------------
+// K3a: level 0 — the ring/sector patches themselves, one block per patch, no grid-wide barrier.
+// Patches come in very different sizes (a few points near the sensor, >10k in the far rings), so
+// the launch is split into size classes, each with its own block size and shared-memory carve-out:
+//   TT = 64,  <= 1024 points  (~15 KB)  : many resident blocks, their eigensolves overlap
+//   TT = 128, <= 4096 points  (~55 KB)
+//   TT = 256, everything larger: <= 8192 points shared-memory resident (~108 KB), beyond that streamed
+// The class kernels run concurrently on separate streams and the hardware block scheduler packs
+// whatever mix fits an SM.  blockIdx.x walks (patch rank, scan) largest patch first; a block whose
+// patch belongs to another class exits at once.
+// EXACT = true: plane normals from Eigen's QR sequence (bit-comparable with the CPU reference);
+// EXACT = false: closed-form FP64 smallest eigenvector (faster, ~1e-6 rad away from the reference's
+// float solver, which is enough to tip chaotic two-layer patches the other way).
+// ---------------------------------------------------------------------------------------------
+template <int TT, bool EXACT>
+__global__ void __launch_bounds__(TT) rpw_fit_roots_kernel(FitArgs A, uint32_t n_lo, uint32_t n_hi, int cap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t id = blockIdx.x;
+    const uint32_t b = id % (uint32_t)A.n_scans, p = A.patch_order[id / (uint32_t)A.n_scans];
+    const uint32_t* ps = A.patch_start + (size_t)b * (A.P + 1) + p;
+    NodeRef nd;
+    nd.start = ps[0]; nd.n = ps[1] - ps[0]; nd.root = b * (uint32_t)A.P + p; nd.pad = 0;
+    if (nd.n == 0 || nd.n <= n_lo || nd.n > n_hi) return;  // :380 empty patch, or another class's patch
+    FitSmem S = carve_smem(smem_raw, cap, TT / 32);
+    if (nd.n <= (uint32_t)cap) process_node<TT, true, EXACT>(A, nd, 0, S);
+    else if constexpr (TT == 256) process_node<TT, false, EXACT>(A, nd, 0, S);
+    if (threadIdx.x == 0) atomicAdd(A.stats + 1, 1u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3b: levels >= 1 — persistent cooperative kernel, level-synchronous device worklist with no
+// host round trip: every split at level l pushed its children to the queue of level l+1;
+// grid.sync() separates levels; the kernel ends when a level enqueued nothing.  Typical scans never
+// split and the kernel falls through after one barrier.
+// ---------------------------------------------------------------------------------------------
+template <bool EXACT>
+__global__ void __launch_bounds__(kFitThreads, 2) rpw_fit_levels_kernel(FitArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cg::grid_group grid = cg::this_grid();
+    constexpr int TT = kFitThreads;
+    FitSmem S = carve_smem(smem_raw, A.smem_cap, TT / 32);
+    __shared__ uint32_t s_fetch;
+    uint32_t n_done = 0, pre = 0;
+    Tick ktick(A.timing);
     int level = 0;
     for (;;) {
-        grid.sync();
         const uint32_t cnt = min(__ldcg(A.q_count + level + 1), A.q_cap);
         if (cnt == 0) break;
         level++;
         const NodeRef* q = A.queue[level & 1];
+        // the cursor of the NEXT node is fetched while the current one is processed
+        if (threadIdx.x == 0) pre = atomicAdd(A.fetch_ctr + level, 1u);
         for (;;) {
             __syncthreads();
-            if (threadIdx.x == 0) s_fetch = atomicAdd(A.fetch_ctr + level, 1u);
+            if (threadIdx.x == 0) s_fetch = pre;
             __syncthreads();
             const uint32_t id = s_fetch;
+            ktick(8);
             if (id >= cnt) break;
+            if (threadIdx.x == 0) pre = atomicAdd(A.fetch_ctr + level, 1u);
             NodeRef nd;
             const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(q + id));
             nd.start = raw.x; nd.n = raw.y; nd.root = raw.z; nd.pad = 0;
-            run_node(A, nd, level, S);
+            if (nd.n <= (uint32_t)A.smem_cap) process_node<TT, true, EXACT>(A, nd, level, S);
+            else process_node<TT, false, EXACT>(A, nd, level, S);
             n_done++;
+            if (A.timing && threadIdx.x == 0) ktick.last = clock64();
         }
+        grid.sync();
+        ktick(9);
     }
     // bookkeeping + self-cleaning: the last block to arrive publishes the totals and zeroes the
     // per-level counters, so the next call needs no memset
@@ -754,6 +905,33 @@ __global__ void rpw_eig3_kernel(const float* __restrict__ mats, size_t count, fl
         for (int c = 0; c < 3; ++c) evecs[i * 9 + r * 3 + c] = E.vec[r][c];
 }
 
+// One warp per scatter matrix (xx yx yy zx zy zz), the way the fit kernel calls the solvers; also
+// reports the cycles one call took (mode 0: closed-form FP64, mode 1: Eigen's QR sequence).
+__global__ void rpw_normal_kernel(const float* __restrict__ sc, size_t count, int mode, float* __restrict__ normals,
+                                  uint32_t* __restrict__ cycles) {
+    const size_t i = blockIdx.x;
+    if (i >= count) return;
+    const float* a = sc + i * 6;
+    const float s0 = a[0], s1 = a[1], s2 = a[2], s3 = a[3], s4 = a[4], s5 = a[5];
+    __syncwarp();
+    const long long t0 = clock64();
+    float nx, ny, nz;
+    if (mode == 1) {
+        const Eig3 E = eig3_sym(s0, s1, s2, s3, s4, s5);
+        nx = E.vec[0][0]; ny = E.vec[1][0]; nz = E.vec[2][0];
+    } else if (mode == 2) {  // the latency-restructured QR the fit kernel runs (must equal mode 1 bit for bit)
+        eig3_smallest_qr(s0, s1, s2, s3, s4, s5, nx, ny, nz);
+    } else {
+        smallest_eigvec_psd(s0, s1, s2, s3, s4, s5, nx, ny, nz);
+    }
+    if (nz < 0.f) { nx = -nx; ny = -ny; nz = -nz; }
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) {
+        normals[i * 3] = nx; normals[i * 3 + 1] = ny; normals[i * 3 + 2] = nz;
+        cycles[i] = (uint32_t)(t1 - t0);
+    }
+}
+
 __global__ void rpw_atan2_kernel(const float* __restrict__ y, const float* __restrict__ x, size_t count, float* __restrict__ out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) out[i] = atan2f_libm(y[i], x[i]);
@@ -762,8 +940,8 @@ __global__ void rpw_atan2_kernel(const float* __restrict__ y, const float* __res
 // =============================================================================================
 // host-side launchers
 // =============================================================================================
-size_t fit_smem_bytes(int smem_cap) {
-    return (size_t)smem_cap * 13 + (2 * kFitWarps * kRedMax + 256 + 16) * 4 + 16;
+size_t fit_smem_bytes(int smem_cap, int threads) {
+    return (size_t)smem_cap * 13 + (2 * (threads / 32) * kRedMax + 256 + 16) * 4 + 16;
 }
 
 cudaError_t launch_bin(cudaStream_t st, int stride_floats, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
@@ -792,22 +970,63 @@ cudaError_t launch_scatter(cudaStream_t st, int stride_floats, const float* pts,
     return cudaGetLastError();
 }
 
-cudaError_t fit_configure(int smem_cap, int* blocks_per_sm) {
-    const size_t smem = fit_smem_bytes(smem_cap);
-    cudaError_t e = cudaFuncSetAttribute(rpw_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, rpw_fit_kernel, kFitThreads, smem);
+template <typename KernelT>
+static cudaError_t set_smem(KernelT k, size_t bytes) {
+    return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-cudaError_t launch_fit(cudaStream_t st, const FitArgs& args, int grid_blocks) {
+cudaError_t fit_configure(int smem_cap, int* blocks_per_sm) {
+    cudaError_t e;
+    if ((e = set_smem(rpw_fit_roots_kernel<64, true>, fit_smem_bytes(kCapTiny, 64))) != cudaSuccess) return e;
+    if ((e = set_smem(rpw_fit_roots_kernel<64, false>, fit_smem_bytes(kCapTiny, 64))) != cudaSuccess) return e;
+    if ((e = set_smem(rpw_fit_roots_kernel<128, true>, fit_smem_bytes(kCapSmall, 128))) != cudaSuccess) return e;
+    if ((e = set_smem(rpw_fit_roots_kernel<128, false>, fit_smem_bytes(kCapSmall, 128))) != cudaSuccess) return e;
+    const size_t smem = fit_smem_bytes(smem_cap, kFitThreads);
+    if ((e = set_smem(rpw_fit_roots_kernel<256, true>, smem)) != cudaSuccess) return e;
+    if ((e = set_smem(rpw_fit_roots_kernel<256, false>, smem)) != cudaSuccess) return e;
+    if ((e = set_smem(rpw_fit_levels_kernel<true>, smem)) != cudaSuccess) return e;
+    if ((e = set_smem(rpw_fit_levels_kernel<false>, smem)) != cudaSuccess) return e;
+    int a = 0, b = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, rpw_fit_levels_kernel<true>, kFitThreads, smem)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, rpw_fit_levels_kernel<false>, kFitThreads, smem)) != cudaSuccess) return e;
+    *blocks_per_sm = a < b ? a : b;
+    return cudaSuccess;
+}
+
+// size class c: 0 tiny, 1 small, 2 large (see rpw_fit_roots_kernel)
+cudaError_t launch_fit_roots(cudaStream_t st, const FitArgs& args, int cls) {
+    const unsigned grid = (unsigned)args.n_roots;
+    const bool ex = args.fp.exact_eig != 0;
+    if (cls == 0) {
+        const size_t sm = fit_smem_bytes(kCapTiny, 64);
+        if (ex) rpw_fit_roots_kernel<64, true><<<grid, 64, sm, st>>>(args, 0u, (uint32_t)kCapTiny, kCapTiny);
+        else rpw_fit_roots_kernel<64, false><<<grid, 64, sm, st>>>(args, 0u, (uint32_t)kCapTiny, kCapTiny);
+    } else if (cls == 1) {
+        const size_t sm = fit_smem_bytes(kCapSmall, 128);
+        if (ex) rpw_fit_roots_kernel<128, true><<<grid, 128, sm, st>>>(args, (uint32_t)kCapTiny, (uint32_t)kCapSmall, kCapSmall);
+        else rpw_fit_roots_kernel<128, false><<<grid, 128, sm, st>>>(args, (uint32_t)kCapTiny, (uint32_t)kCapSmall, kCapSmall);
+    } else {
+        const size_t sm = fit_smem_bytes(args.smem_cap, 256);
+        if (ex) rpw_fit_roots_kernel<256, true><<<grid, 256, sm, st>>>(args, (uint32_t)kCapSmall, 0xFFFFFFFFu, args.smem_cap);
+        else rpw_fit_roots_kernel<256, false><<<grid, 256, sm, st>>>(args, (uint32_t)kCapSmall, 0xFFFFFFFFu, args.smem_cap);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fit_levels(cudaStream_t st, const FitArgs& args, int grid_blocks) {
     FitArgs a = args;
     void* params[] = {&a};
-    return cudaLaunchCooperativeKernel((void*)rpw_fit_kernel, dim3(grid_blocks), dim3(kFitThreads), params,
-                                       fit_smem_bytes(args.smem_cap), st);
+    void* fn = args.fp.exact_eig ? (void*)rpw_fit_levels_kernel<true> : (void*)rpw_fit_levels_kernel<false>;
+    return cudaLaunchCooperativeKernel(fn, dim3(grid_blocks), dim3(kFitThreads), params, fit_smem_bytes(args.smem_cap, kFitThreads), st);
 }
 
 cudaError_t launch_eig3(cudaStream_t st, const float* mats, size_t count, float* evals, float* evecs) {
     rpw_eig3_kernel<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(mats, count, evals, evecs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_normal(cudaStream_t st, const float* sc, size_t count, int mode, float* normals, uint32_t* cycles) {
+    rpw_normal_kernel<<<(unsigned)count, 32, 0, st>>>(sc, count, mode, normals, cycles);
     return cudaGetLastError();
 }
 

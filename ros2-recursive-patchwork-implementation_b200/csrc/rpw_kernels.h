@@ -31,6 +31,7 @@ struct FitArgs {
     uint32_t* fetch_ctr;       // [levels_cap] dynamic fetch cursor of level l
     uint32_t* stats;           // [0] levels run (out) [1] nodes processed (accumulator) [2] block arrival [3] nodes (out)
     uint32_t* overflow;        // set if a queue would overflow
+    unsigned long long* timing; // optional [16] cycle accounting (rpw_debug_fit_timing)
     rpw_node_rec* dbg_nodes;   // optional
     uint32_t* dbg_count;
     uint32_t dbg_cap;
@@ -43,7 +44,7 @@ struct FitArgs {
     FitParams fp;
 };
 
-size_t fit_smem_bytes(int smem_cap);
+size_t fit_smem_bytes(int smem_cap, int threads);
 cudaError_t fit_configure(int smem_cap, int* blocks_per_sm);
 
 cudaError_t launch_bin(cudaStream_t st, int stride_floats, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
@@ -54,8 +55,10 @@ cudaError_t launch_offsets(cudaStream_t st, const uint64_t* scan_off, const uint
 cudaError_t launch_scatter(cudaStream_t st, int stride_floats, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
                            const uint16_t* keys, const uint32_t* blk_hist, const uint32_t* patch_start, float4* sorted,
                            const uint32_t* patch_total, uint32_t* patch_order, int P, int max_chunks, int batch);
-cudaError_t launch_fit(cudaStream_t st, const FitArgs& args, int grid_blocks);
+cudaError_t launch_fit_roots(cudaStream_t st, const FitArgs& args, int size_class);
+cudaError_t launch_fit_levels(cudaStream_t st, const FitArgs& args, int grid_blocks);
 cudaError_t launch_eig3(cudaStream_t st, const float* mats, size_t count, float* evals, float* evecs);
+cudaError_t launch_normal(cudaStream_t st, const float* sc, size_t count, int mode, float* normals, uint32_t* cycles);
 cudaError_t launch_atan2(cudaStream_t st, const float* y, const float* x, size_t count, float* out);
 
 }  // namespace rpw

@@ -26,8 +26,8 @@ def compare_nodes(gpu_nodes, orc_nodes, scan=0):
             continue
         if a["n_inliers"] >= 3 and b["n_inliers"] >= 3 and a["outcome"] in (4, 5):
             na, nb = a["normal"].astype(np.float64), b["normal"].astype(np.float64)
-            c = abs(float(np.dot(na, nb))) / (np.linalg.norm(na) * np.linalg.norm(nb))
-            ang = float(np.arccos(min(1.0, c)))
+            # atan2(|a x b|, |a . b|): arccos of a dot product cannot resolve angles below ~3e-4 rad
+            ang = float(np.arctan2(np.linalg.norm(np.cross(na, nb)), abs(float(np.dot(na, nb)))))
             angles.append(ang)
             inlier_diff += int(a["n_inliers"] != b["n_inliers"])
             if worst is None or ang > worst[0]:

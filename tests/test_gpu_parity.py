@@ -140,3 +140,66 @@ def test_full_size_properties(rpw, h):
     lf = h.segment(flat)
     keys = h.debug_keys(len(flat))
     assert np.all(lf[keys < 0xFFFD] == 1)
+
+
+def test_restructured_qr_is_the_generic_qr(h):
+    """The latency-restructured solver the fit kernel runs must return the bits of the generic
+    Eigen-sequence solver (which test_device_eigensolver_bit_exact pins to the oracle)."""
+    rng = np.random.default_rng(11)
+    n = 20000
+    A = rng.normal(size=(n, 3, 3)).astype(np.float32)
+    A = A @ A.transpose(0, 2, 1)
+    A[: n // 2, 2, :] *= 1e-2
+    A[: n // 2, :, 2] *= 1e-2
+    A[0] = 0
+    A[1] = np.eye(3)
+    A[2] = np.diag([1.0, 1.0, 0.0])
+    A[3, :, :] = np.outer([1, 2, 3], [1, 2, 3])  # rank 1
+    sc = np.stack([A[:, 0, 0], A[:, 1, 0], A[:, 1, 1], A[:, 2, 0], A[:, 2, 1], A[:, 2, 2]], 1).astype(np.float32)
+    generic, _ = h.debug_normal(sc, 1)
+    fast, _ = h.debug_normal(sc, 2)
+    assert np.array_equal(generic.view(np.uint32), fast.view(np.uint32))
+
+
+def test_closed_form_solver_accuracy(h):
+    rng = np.random.default_rng(12)
+    mats = []
+    for i in range(3000):
+        n = int(rng.integers(3, 3000))
+        ext = rng.uniform(0.5, 30, 2)
+        p = rng.normal(size=(n, 3)) * np.array([ext[0], ext[1], rng.uniform(0.0, 0.2)])
+        a, b = rng.uniform(-0.3, 0.3, 2)
+        p[:, 2] += a * p[:, 0] + b * p[:, 1]
+        d = (p - p.mean(0)).astype(np.float32)
+        S = d.T @ d
+        mats.append([S[0, 0], S[1, 0], S[1, 1], S[2, 0], S[2, 1], S[2, 2]])
+    mats = np.array(mats, np.float32)
+    full = np.zeros((len(mats), 3, 3))
+    full[:, 0, 0] = mats[:, 0]; full[:, 1, 0] = full[:, 0, 1] = mats[:, 1]; full[:, 1, 1] = mats[:, 2]
+    full[:, 2, 0] = full[:, 0, 2] = mats[:, 3]; full[:, 2, 1] = full[:, 1, 2] = mats[:, 4]; full[:, 2, 2] = mats[:, 5]
+    w, v = np.linalg.eigh(full)
+    ref = v[:, :, 0]
+    nrm, _ = h.debug_normal(mats, 0)
+    nd = nrm.astype(np.float64)
+    ang = np.arctan2(np.linalg.norm(np.cross(nd, ref), axis=1), np.abs((nd * ref).sum(1)))
+    ok = (w[:, 1] - w[:, 0]) / np.abs(w).max(1) > 1e-4
+    assert ang[ok].max() < 1e-6
+    assert np.all(nrm[:, 2] >= 0) and np.allclose(np.linalg.norm(nrm, axis=1), 1, atol=1e-6)
+
+
+@pytest.mark.parametrize("case", ["C1_10000_splits", "C2_120k", "C4_300k", "C5_262k_deep"])
+def test_closed_form_solver_label_parity(case, rpw, gpu_handle_factory, oracle):
+    """The faster solver is not the reference's rounding, so the tree of fits may differ in chaotic
+    patches; on these scenes labels still clear the 99.9 % bar (C5 seed 3001, where the reference's
+    own -O2 and -ffast-math builds agree on only 99.69 %, is the documented exception)."""
+    hd = gpu_handle_factory(None, 1 << 19, 1)
+    hd.set_plane_solver(rpw.capi.SOLVER_CLOSED_FORM)
+    cfg, pts = CASES[case](rpw)
+    hd.set_config(cfg.to_c())
+    labels = hd.segment(pts)
+    keys = hd.debug_keys(len(pts))
+    o = oracle.run(cfg, pts)
+    rep = parity.compare_scan(labels, keys, o)
+    print(case, rep)
+    assert rep["key_mismatch"] == 0 and rep["n_flips_nonpatch"] == 0
+    assert rep["label_agreement"] >= LABEL_BAR
