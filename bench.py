@@ -117,7 +117,7 @@ def cpu_reference_throughput(scans, cfg, seconds_budget, threads):
     return n_jobs / dt, kind, f"{n_jobs} scans ({len(scans)} distinct, C2 seeds) on {threads} threads, {dt:.1f} s wall, libref_{'fast' if kind == 'reference' else 'oracle'}"
 
 
-def run_reference(args):
+def run_reference(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -146,7 +146,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     val = per_step * args.steps / dt
     sample = f"{per_step} scans per step ({len(scans)} distinct C2 scans) on {threads} host threads"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -154,10 +154,20 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "mpoints_per_sec": val * POINTS_PER_SCAN / 1e6,
-    }))
+    })
 
 
 def main():
+    # Libraries (NCCL's version banner, for one) print to stdout; the contract is ONE JSON line there.
+    # Everything but that line goes to stderr: fd 1 is pointed at fd 2 and the line is written to the
+    # saved descriptor at the end.
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(os.dup(1), "w", buffering=1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -171,7 +181,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, emit)
 
     import torch
     import torch.distributed as dist
@@ -318,7 +328,7 @@ def main():
         tf = ROOT / "profiles" / "fit_traffic.json"
         if tf.exists():
             try:
-                traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
+                traffic = json.loads(tf.read_text())["fit_phase_dram_bytes_per_point"] * pts_per_launch  # ncu, per launch
             except Exception:
                 traffic = None
         kernels = {}
@@ -335,7 +345,7 @@ def main():
                        "l2": f"batch is {total * 16 / 1e6:.0f} MB of float4 input per GPU > 126 MB L2 (no flush needed)"},
             "mpoints_per_sec": value * POINTS_PER_SCAN / 1e6,
             "hbm_fraction_whole_path": ALG_BYTES_PER_POINT * (value / world) * POINTS_PER_SCAN / 1e9 / peak,
-            "roofline": {"bound": "hbm", "kernel": "rpw_fit_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "fit phase = rpw_fit_roots_kernel<64|128|256> (three size classes, concurrent streams) + rpw_fit_levels_kernel, timed as one unit", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_point": ALG_BYTES_PER_POINT, "ms_per_launch": fit_ms},
             "kernels": kernels,
@@ -350,7 +360,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             v, kind, sample = cpu_reference_throughput(scans[:16], cfg, args.cpu_seconds, os.cpu_count() or 1)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": kind, "sample": sample}
-        print(json.dumps(out))
+        emit(out)
     h.close()
     if world > 1:
         dist.barrier()
