@@ -25,15 +25,29 @@ struct rpw_handle {
     int num_sms = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
-    cudaStream_t side[3] = {nullptr, nullptr, nullptr};  // the fit size classes run concurrently
-    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+    // Launch groups of one call alternate over two lanes so that the long-tail patches of one group
+    // overlap the bulk of the next.  A lane has its own streams and its own small worklist state; the
+    // big per-point buffers are shared (groups touch disjoint index ranges).
+    struct Lane {
+        cudaStream_t main = nullptr;                          // K1, K1b, K2, K3b
+        cudaStream_t side[3] = {nullptr, nullptr, nullptr};   // K3a size classes run concurrently
+        cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr}, ev_start = nullptr, ev_done = nullptr;
+        NodeRef* d_queue[2] = {nullptr, nullptr};
+        uint32_t* d_counters = nullptr;     // fetch_ctr[levels_cap] | q_count[levels_cap] | stats[8] | overflow
+        uint32_t* d_patch_total = nullptr;  // [P] points per patch over the launch group
+        uint32_t* d_patch_order = nullptr;  // [P] patches, largest first
+    };
+    static constexpr int kLanes = 2;
+    Lane lane[kLanes];
+    cudaEvent_t ev_call = nullptr;
+    uint32_t* d_dbg_count = nullptr;
+    int n_waves = 1;  // launch groups per call (1: within one call more groups only add tails)
     size_t cap_points = 0, cap_batch = 0;
     int P = 0;
     int levels_cap = 0;
     uint32_t q_cap = 0;
     int smem_cap = 0;
     int fit_blocks = 0;
-    int wave_scans = 0;  // scans per launch group (0 = whole batch)
     int solver = RPW_SOLVER_EIGEN_QR;
 
     // device buffers
@@ -47,10 +61,6 @@ struct rpw_handle {
     uint32_t* d_blk_hist = nullptr;
     uint32_t* d_patch_start = nullptr;
     float* d_root_mean = nullptr;
-    uint32_t* d_patch_total = nullptr;  // [P] batch-wide points per patch
-    uint32_t* d_patch_order = nullptr;  // [P] patches, largest first
-    NodeRef* d_queue[2] = {nullptr, nullptr};
-    uint32_t* d_counters = nullptr;  // fetch_ctr[levels_cap] | q_count[levels_cap] | stats[8] | overflow | dbg_count
     uint64_t* d_scan_off = nullptr;
     uint32_t* d_chunk_base = nullptr;
     rpw_node* d_dbg_nodes = nullptr;
@@ -153,8 +163,10 @@ static void free_patch_buffers(rpw_handle* h) {
     cudaFree(h->d_blk_hist); h->d_blk_hist = nullptr;
     cudaFree(h->d_patch_start); h->d_patch_start = nullptr;
     cudaFree(h->d_root_mean); h->d_root_mean = nullptr;
-    cudaFree(h->d_patch_total); h->d_patch_total = nullptr;
-    cudaFree(h->d_patch_order); h->d_patch_order = nullptr;
+    for (auto& L : h->lane) {
+        cudaFree(L.d_patch_total); L.d_patch_total = nullptr;
+        cudaFree(L.d_patch_order); L.d_patch_order = nullptr;
+    }
 }
 
 static int alloc_patch_buffers(rpw_handle* h) {
@@ -164,8 +176,10 @@ static int alloc_patch_buffers(rpw_handle* h) {
     RPW_CUDA(h, cudaMalloc(&h->d_blk_hist, rows * P * sizeof(uint32_t)));
     RPW_CUDA(h, cudaMalloc(&h->d_patch_start, h->cap_batch * (size_t)(P + 1) * sizeof(uint32_t)));
     RPW_CUDA(h, cudaMalloc(&h->d_root_mean, h->cap_batch * (size_t)P * sizeof(float)));
-    RPW_CUDA(h, cudaMalloc(&h->d_patch_total, (size_t)P * sizeof(uint32_t)));
-    RPW_CUDA(h, cudaMalloc(&h->d_patch_order, (size_t)P * sizeof(uint32_t)));
+    for (auto& L : h->lane) {
+        RPW_CUDA(h, cudaMalloc(&L.d_patch_total, (size_t)P * sizeof(uint32_t)));
+        RPW_CUDA(h, cudaMalloc(&L.d_patch_order, (size_t)P * sizeof(uint32_t)));
+    }
     return RPW_OK;
 }
 
@@ -174,11 +188,13 @@ static int alloc_level_buffers(rpw_handle* h) {
     if (h->cfg.max_split_depth >= 0 && h->cfg.max_split_depth < lv) lv = h->cfg.max_split_depth;
     if (lv < 0) lv = 0;
     h->levels_cap = (int)lv + 4;
-    cudaFree(h->d_counters);
-    h->d_counters = nullptr;
     const size_t words = (size_t)h->levels_cap * 2 + 16;
-    RPW_CUDA(h, cudaMalloc(&h->d_counters, words * sizeof(uint32_t)));
-    RPW_CUDA(h, cudaMemset(h->d_counters, 0, words * sizeof(uint32_t)));
+    for (auto& L : h->lane) {
+        cudaFree(L.d_counters);
+        L.d_counters = nullptr;
+        RPW_CUDA(h, cudaMalloc(&L.d_counters, words * sizeof(uint32_t)));
+        RPW_CUDA(h, cudaMemset(L.d_counters, 0, words * sizeof(uint32_t)));
+    }
     return RPW_OK;
 }
 
@@ -187,7 +203,7 @@ void rpw_destroy(rpw_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_in); cudaFree(h->d_keys); cudaFree(h->d_labels); cudaFree(h->d_sortedA); cudaFree(h->d_bufB);
-    cudaFree(h->d_bufC); cudaFree(h->d_gmask); cudaFree(h->d_queue[0]); cudaFree(h->d_queue[1]); cudaFree(h->d_counters);
+    cudaFree(h->d_bufC); cudaFree(h->d_gmask); cudaFree(h->d_dbg_count);
     cudaFree(h->d_scan_off); cudaFree(h->d_chunk_base); cudaFree(h->d_dbg_nodes); cudaFree(h->d_timing);
     free_patch_buffers(h);
     if (h->h_meta) cudaFreeHost(h->h_meta);
@@ -195,8 +211,15 @@ void rpw_destroy(rpw_handle* h) {
     if (h->h_stage_labels) cudaFreeHost(h->h_stage_labels);
     if (h->h_stats) cudaFreeHost(h->h_stats);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
-    for (int k = 0; k < 3; ++k) { if (h->side[k]) cudaStreamDestroy(h->side[k]); if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]); }
-    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    for (auto& L : h->lane) {
+        cudaFree(L.d_queue[0]); cudaFree(L.d_queue[1]); cudaFree(L.d_counters);
+        for (int k = 0; k < 3; ++k) { if (L.side[k]) cudaStreamDestroy(L.side[k]); if (L.ev_join[k]) cudaEventDestroy(L.ev_join[k]); }
+        if (L.ev_fork) cudaEventDestroy(L.ev_fork);
+        if (L.ev_start) cudaEventDestroy(L.ev_start);
+        if (L.ev_done) cudaEventDestroy(L.ev_done);
+        if (L.main) cudaStreamDestroy(L.main);
+    }
+    if (h->ev_call) cudaEventDestroy(h->ev_call);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -238,11 +261,19 @@ int rpw_create(const rpw_config* cfg, int device, size_t max_total_points, size_
     TRYC(cudaSetDevice(device));
     TRYC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
-    for (int k = 0; k < 3; ++k) {
-        TRYC(cudaStreamCreateWithFlags(&h->side[k], cudaStreamNonBlocking));
-        TRYC(cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming));
+    for (auto& L : h->lane) {
+        TRYC(cudaStreamCreateWithFlags(&L.main, cudaStreamNonBlocking));
+        for (int k = 0; k < 3; ++k) {
+            TRYC(cudaStreamCreateWithFlags(&L.side[k], cudaStreamNonBlocking));
+            TRYC(cudaEventCreateWithFlags(&L.ev_join[k], cudaEventDisableTiming));
+        }
+        TRYC(cudaEventCreateWithFlags(&L.ev_fork, cudaEventDisableTiming));
+        TRYC(cudaEventCreateWithFlags(&L.ev_start, cudaEventDisableTiming));
+        TRYC(cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
     }
-    TRYC(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    TRYC(cudaEventCreateWithFlags(&h->ev_call, cudaEventDisableTiming));
+    TRYC(cudaMalloc(&h->d_dbg_count, sizeof(uint32_t)));
+    TRYC(cudaMemset(h->d_dbg_count, 0, sizeof(uint32_t)));
     const size_t N = max_total_points;
     TRYC(cudaMalloc(&h->d_in, N * 16));
     TRYC(cudaMalloc(&h->d_keys, N * sizeof(uint16_t)));
@@ -252,23 +283,25 @@ int rpw_create(const rpw_config* cfg, int device, size_t max_total_points, size_
     TRYC(cudaMalloc(&h->d_bufC, N * sizeof(float4)));
     TRYC(cudaMalloc(&h->d_gmask, N));
     h->q_cap = (uint32_t)(N / 25 + 64);
-    TRYC(cudaMalloc(&h->d_queue[0], (size_t)h->q_cap * sizeof(NodeRef)));
-    TRYC(cudaMalloc(&h->d_queue[1], (size_t)h->q_cap * sizeof(NodeRef)));
+    for (auto& L : h->lane) {
+        TRYC(cudaMalloc(&L.d_queue[0], (size_t)h->q_cap * sizeof(NodeRef)));
+        TRYC(cudaMalloc(&L.d_queue[1], (size_t)h->q_cap * sizeof(NodeRef)));
+    }
     TRYC(cudaMalloc(&h->d_scan_off, (max_batch + 1) * sizeof(uint64_t)));
     TRYC(cudaMalloc(&h->d_chunk_base, (max_batch + 1) * sizeof(uint32_t)));
     TRYC(cudaMallocHost(&h->h_meta, (max_batch + 1) * (sizeof(uint64_t) + sizeof(uint32_t)) + 64));
-    TRYC(cudaMallocHost(&h->h_stats, 16 * sizeof(uint32_t)));
+    TRYC(cudaMallocHost(&h->h_stats, 16 * rpw_handle::kLanes * sizeof(uint32_t)));
     TRY(alloc_patch_buffers(h));
     TRY(alloc_level_buffers(h));
     // shared-memory budget of the fit kernel: points a block keeps resident
     int cap = 8192;
     if (const char* s = getenv("RPW_FIT_SMEM_CAP")) { const int v = atoi(s); if (v >= 256 && v <= 16384) cap = v; }
-    if (const char* s = getenv("RPW_WAVE_SCANS")) { const int v = atoi(s); if (v >= 0) h->wave_scans = v; }
+    if (const char* s = getenv("RPW_WAVES")) { const int v = atoi(s); if (v >= 0) h->n_waves = v; }
     h->smem_cap = cap;
     int bps = 0;
     TRYC(fit_configure(cap, &bps));
     if (bps < 1) { h->err = "fit kernel does not fit on an SM"; return fail(RPW_ERR_CUDA); }
-    h->fit_blocks = bps * h->num_sms;
+    h->fit_blocks = h->num_sms;  // the levels kernel: one persistent block per SM
 #undef TRY
 #undef TRYC
     *out = h;
@@ -395,74 +428,102 @@ static int upload_meta(rpw_handle* h, const uint64_t* off, size_t batch) {
     return RPW_OK;
 }
 
+// ProfScope records on h->stream; launch groups run on lane streams, so point it there for a while.
+struct StreamSwap {
+    rpw_handle* h; cudaStream_t saved;
+    StreamSwap(rpw_handle* h_, cudaStream_t s) : h(h_), saved(h_->stream) { h->stream = s; }
+    ~StreamSwap() { h->stream = saved; }
+};
+
+// One launch group: scans [b0, b0 + nb) of the call on lane `L`, stream `st`.
+static int run_group(rpw_handle* h, rpw_handle::Lane& L, cudaStream_t st, const float* d_pts, int stride_floats, uint8_t* d_labels,
+                     size_t b0, size_t nb) {
+    const uint64_t* so = h->last_off.data();
+    uint64_t max_n = 0;
+    for (size_t i = b0; i < b0 + nb; ++i) max_n = so[i + 1] - so[i] > max_n ? so[i + 1] - so[i] : max_n;
+    if (so[b0 + nb] == so[b0]) return RPW_OK;  // nothing but empty scans
+    const int max_chunks = (int)((max_n + kBinChunk - 1) / kBinChunk);
+    StreamSwap swap(h, st);
+    // The kernels index scans relative to the pointers they are given.
+    const uint64_t* d_so = h->d_scan_off + b0;
+    const uint32_t* d_cb = h->d_chunk_base + b0;
+    uint32_t* d_ps = h->d_patch_start + b0 * (size_t)(h->P + 1);
+    { ProfScope ps(h, 0);
+      RPW_CUDA(h, launch_bin(st, stride_floats, d_pts, d_so, d_cb, h->zm, h->d_keys, d_labels, h->d_blk_hist, L.d_patch_total, max_chunks, (int)nb)); }
+    { ProfScope ps(h, 1);
+      RPW_CUDA(h, launch_offsets(st, d_so, d_cb, h->d_blk_hist, d_ps, L.d_patch_total, h->P, (int)nb)); }
+    { ProfScope ps(h, 2);
+      RPW_CUDA(h, launch_scatter(st, stride_floats, d_pts, d_so, d_cb, h->d_keys, h->d_blk_hist, d_ps, h->d_sortedA, L.d_patch_total,
+                                 L.d_patch_order, h->P, max_chunks, (int)nb)); }
+    FitArgs A;
+    A.sortedA = h->d_sortedA; A.bufB = h->d_bufB; A.bufC = h->d_bufC; A.gmask = h->d_gmask;
+    A.labels = d_labels;
+    A.patch_start = d_ps;
+    A.patch_order = L.d_patch_order;
+    A.root_mean = h->d_root_mean + b0 * (size_t)h->P;
+    A.queue[0] = L.d_queue[0]; A.queue[1] = L.d_queue[1];
+    A.fetch_ctr = L.d_counters;
+    A.q_count = L.d_counters + h->levels_cap;
+    A.stats = L.d_counters + 2 * (size_t)h->levels_cap;
+    A.overflow = A.stats + 8;
+    A.timing = h->timing_enabled ? h->d_timing : nullptr;
+    A.dbg_nodes = h->dbg_enabled ? h->d_dbg_nodes : nullptr;
+    A.dbg_count = h->d_dbg_count;
+    A.dbg_cap = h->dbg_cap;
+    A.q_cap = h->q_cap;
+    A.n_roots = (int)(nb * (size_t)h->P);
+    A.n_scans = (int)nb;
+    A.P = h->P;
+    A.smem_cap = h->smem_cap;
+    A.scan_base = (uint32_t)b0;
+    A.fp = h->fp;
+    {
+        ProfScope ps(h, 3);
+        // level 0: three size classes on side streams (largest first), joined back before the
+        // persistent kernel that walks the deeper levels
+        static const char* dbg_mask = getenv("RPW_DBG_CLASS_MASK");  // profiling aid: bit k = run size class k only
+        const int mask = dbg_mask ? atoi(dbg_mask) : 7;
+        RPW_CUDA(h, cudaEventRecord(L.ev_fork, st));
+        for (int k = 0; k < 3; ++k) {
+            RPW_CUDA(h, cudaStreamWaitEvent(L.side[k], L.ev_fork, 0));
+            if (mask & (1 << (2 - k))) RPW_CUDA(h, launch_fit_roots(L.side[k], A, 2 - k));
+            RPW_CUDA(h, cudaEventRecord(L.ev_join[k], L.side[k]));
+        }
+        for (int k = 0; k < 3; ++k) RPW_CUDA(h, cudaStreamWaitEvent(st, L.ev_join[k], 0));
+        RPW_CUDA(h, launch_fit_levels(st, A, h->fit_blocks));
+    }
+    h->launches += 7;
+    h->launches_call += 7;
+    return RPW_OK;
+}
+
 // Enqueues K1..K3 for scans [0, batch) whose points are device resident at `d_pts`.
 static int run_pipeline(rpw_handle* h, const float* d_pts, int stride_floats, uint8_t* d_labels, size_t batch) {
-    const uint64_t* so = h->last_off.data();
-    const size_t wave = h->wave_scans > 0 ? (size_t)h->wave_scans : batch;
     h->launches_call = 0;
     // stats[0] (levels) and stats[3] (nodes) accumulate over the call's launch groups
-    RPW_CUDA(h, cudaMemsetAsync(h->d_counters + 2 * (size_t)h->levels_cap, 0, sizeof(uint32_t), h->stream));
-    RPW_CUDA(h, cudaMemsetAsync(h->d_counters + 2 * (size_t)h->levels_cap + 3, 0, sizeof(uint32_t), h->stream));
-    for (size_t b0 = 0; b0 < batch; b0 += wave) {
-        const size_t nb = (b0 + wave <= batch) ? wave : batch - b0;
-        uint64_t max_n = 0;
-        for (size_t i = b0; i < b0 + nb; ++i) max_n = so[i + 1] - so[i] > max_n ? so[i + 1] - so[i] : max_n;
-        if (so[b0 + nb] == so[b0]) continue;  // nothing but empty scans
-        const int max_chunks = (int)((max_n + kBinChunk - 1) / kBinChunk);
-        // The kernels index scans relative to the pointers they are given.
-        const uint64_t* d_so = h->d_scan_off + b0;
-        const uint32_t* d_cb = h->d_chunk_base + b0;
-        { ProfScope ps(h, 0);
-        RPW_CUDA(h, launch_bin(h->stream, stride_floats, d_pts, d_so, d_cb, h->zm, h->d_keys, d_labels, h->d_blk_hist, h->d_patch_total, max_chunks, (int)nb)); }
-        { ProfScope ps(h, 1);
-        RPW_CUDA(h, launch_offsets(h->stream, d_so, d_cb, h->d_blk_hist, h->d_patch_start + b0 * (size_t)(h->P + 1), h->d_patch_total, h->P, (int)nb)); }
-        { ProfScope ps(h, 2);
-        RPW_CUDA(h, launch_scatter(h->stream, stride_floats, d_pts, d_so, d_cb, h->d_keys, h->d_blk_hist,
-                                   h->d_patch_start + b0 * (size_t)(h->P + 1), h->d_sortedA, h->d_patch_total, h->d_patch_order, h->P, max_chunks, (int)nb)); }
-        FitArgs A;
-        A.sortedA = h->d_sortedA; A.bufB = h->d_bufB; A.bufC = h->d_bufC; A.gmask = h->d_gmask;
-        A.labels = d_labels;
-        A.patch_start = h->d_patch_start + b0 * (size_t)(h->P + 1);
-        A.root_mean = h->d_root_mean + b0 * (size_t)h->P;
-        A.queue[0] = h->d_queue[0]; A.queue[1] = h->d_queue[1];
-        A.fetch_ctr = h->d_counters;
-        A.q_count = h->d_counters + h->levels_cap;
-        A.stats = h->d_counters + 2 * (size_t)h->levels_cap;
-        A.overflow = A.stats + 8;
-        A.dbg_nodes = h->dbg_enabled ? h->d_dbg_nodes : nullptr;
-        A.dbg_count = A.stats + 9;
-        A.dbg_cap = h->dbg_cap;
-        A.timing = h->timing_enabled ? h->d_timing : nullptr;
-        A.q_cap = h->q_cap;
-        A.n_roots = (int)(nb * (size_t)h->P);
-        A.n_scans = (int)nb;
-        A.patch_order = h->d_patch_order;
-        A.P = h->P;
-        A.smem_cap = h->smem_cap;
-        A.fp = h->fp;
-        A.scan_base = (uint32_t)b0;
-        {
-            ProfScope ps(h, 3);
-            // level 0: three size classes on side streams (largest first), joined back before
-            // the cooperative kernel that walks the deeper levels
-            static const char* dbg_mask = getenv("RPW_DBG_CLASS_MASK");   // experiments: bit k = run class k
-            static const char* dbg_serial = getenv("RPW_DBG_SERIAL");
-            const int mask = dbg_mask ? atoi(dbg_mask) : 7;
-            if (dbg_serial) {
-                for (int k = 0; k < 3; ++k) if (mask & (1 << (2 - k))) RPW_CUDA(h, launch_fit_roots(h->stream, A, 2 - k));
-            } else {
-            RPW_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
-            for (int k = 0; k < 3; ++k) {
-                RPW_CUDA(h, cudaStreamWaitEvent(h->side[k], h->ev_fork, 0));
-                if (mask & (1 << (2 - k))) RPW_CUDA(h, launch_fit_roots(h->side[k], A, 2 - k));
-                RPW_CUDA(h, cudaEventRecord(h->ev_join[k], h->side[k]));
-            }
-            for (int k = 0; k < 3; ++k) RPW_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join[k], 0));
-            }
-            RPW_CUDA(h, launch_fit_levels(h->stream, A, h->fit_blocks));
-        }
-        h->launches += 7;
-        h->launches_call += 7;
+    for (auto& L : h->lane) {
+        uint32_t* st = L.d_counters + 2 * (size_t)h->levels_cap;
+        RPW_CUDA(h, cudaMemsetAsync(st, 0, sizeof(uint32_t), h->stream));
+        RPW_CUDA(h, cudaMemsetAsync(st + 3, 0, sizeof(uint32_t), h->stream));
+    }
+    int waves = h->n_waves > 0 ? h->n_waves : 1;
+    if ((size_t)waves > batch) waves = (int)batch;
+    if (h->dbg_enabled || h->timing_enabled) waves = 1;  // debug records are easier to read in one group
+    if (waves <= 1) return run_group(h, h->lane[0], h->stream, d_pts, stride_floats, d_labels, 0, batch);
+    // fork: both lanes wait for everything already enqueued on the handle's stream (inputs, meta)
+    RPW_CUDA(h, cudaEventRecord(h->ev_call, h->stream));
+    for (auto& L : h->lane) RPW_CUDA(h, cudaStreamWaitEvent(L.main, h->ev_call, 0));
+    for (int w = 0; w < waves; ++w) {
+        const size_t b0 = batch * (size_t)w / waves, b1 = batch * (size_t)(w + 1) / waves;
+        if (b1 <= b0) continue;
+        rpw_handle::Lane& L = h->lane[w % rpw_handle::kLanes];
+        int rc = run_group(h, L, L.main, d_pts, stride_floats, d_labels, b0, b1 - b0);
+        if (rc != RPW_OK) return rc;
+    }
+    // join
+    for (auto& L : h->lane) {
+        RPW_CUDA(h, cudaEventRecord(L.ev_done, L.main));
+        RPW_CUDA(h, cudaStreamWaitEvent(h->stream, L.ev_done, 0));
     }
     return RPW_OK;
 }
@@ -480,21 +541,25 @@ static int ensure_stage(rpw_handle* h) {
 }
 
 static int reset_dbg(rpw_handle* h) {
-    if (h->dbg_enabled) RPW_CUDA(h, cudaMemsetAsync(h->d_counters + 2 * (size_t)h->levels_cap + 9, 0, sizeof(uint32_t), h->stream));
+    if (h->dbg_enabled) RPW_CUDA(h, cudaMemsetAsync(h->d_dbg_count, 0, sizeof(uint32_t), h->stream));
     return RPW_OK;
 }
 
 static int fill_stats(rpw_handle* h, rpw_stats* st, uint8_t* const* labels, const size_t* n, size_t batch) {
     if (!st) return RPW_OK;
     memset(st, 0, sizeof(*st));
-    RPW_CUDA(h, cudaMemcpyAsync(h->h_stats, h->d_counters + 2 * (size_t)h->levels_cap, 10 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    for (int l = 0; l < rpw_handle::kLanes; ++l)
+        RPW_CUDA(h, cudaMemcpyAsync(h->h_stats + 16 * l, h->lane[l].d_counters + 2 * (size_t)h->levels_cap, 10 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     RPW_CUDA(h, cudaStreamSynchronize(h->stream));
-    st->n_levels = h->h_stats[0];
-    st->n_nodes = h->h_stats[3];
     st->kernel_launches = h->launches_call;
-    if (h->h_stats[8]) {
-        cudaMemsetAsync(h->d_counters + 2 * (size_t)h->levels_cap + 8, 0, sizeof(uint32_t), h->stream);
-        RPW_FAIL(h, RPW_ERR_CAPACITY, "device worklist overflowed (q_cap %u)", h->q_cap);
+    for (int l = 0; l < rpw_handle::kLanes; ++l) {
+        const uint32_t* s = h->h_stats + 16 * l;
+        st->n_levels = s[0] > st->n_levels ? s[0] : st->n_levels;
+        st->n_nodes += s[3];
+        if (s[8]) {
+            cudaMemsetAsync(h->lane[l].d_counters + 2 * (size_t)h->levels_cap + 8, 0, sizeof(uint32_t), h->stream);
+            RPW_FAIL(h, RPW_ERR_CAPACITY, "device worklist overflowed (q_cap %u)", h->q_cap);
+        }
     }
     uint64_t cnt[4] = {0, 0, 0, 0};
     for (size_t b = 0; b < batch; ++b) {
@@ -695,7 +760,7 @@ int rpw_debug_nodes(rpw_handle* h, rpw_node* out, size_t cap, size_t* count) {
     if (!h->dbg_enabled) RPW_FAIL(h, RPW_ERR_BAD_ARG, "node recording is not enabled");
     RPW_CUDA(h, cudaSetDevice(h->device));
     uint32_t c = 0;
-    RPW_CUDA(h, cudaMemcpyAsync(&c, h->d_counters + 2 * (size_t)h->levels_cap + 9, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    RPW_CUDA(h, cudaMemcpyAsync(&c, h->d_dbg_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     RPW_CUDA(h, cudaStreamSynchronize(h->stream));
     *count = c;
     size_t take = c < h->dbg_cap ? c : h->dbg_cap;

@@ -10,17 +10,14 @@
 //                           per node: early-outs, seeds, iterated PCA plane fit with a register
 //                           3x3 eigensolve, residual mask, split (variance axis, exact radix-select
 //                           median, stable partition), child enqueue, label scatter
-//   K3b rpw_fit_levels_kernel persistent cooperative kernel: level-synchronous device worklist over
-//                           the children of split nodes (depth >= 1), no host round trips
+//   K3b rpw_fit_levels_kernel persistent kernel (one block per SM, grid barrier in global memory):
+//                           level-synchronous device worklist over the children of split nodes
+//                           (depth >= 1), no host round trips
 //   dbg rpw_eig3_kernel / rpw_atan2_kernel   unit-test entry points for the device math
 //
 // All of it is HBM/L2/shared-memory bound integer-and-float SIMT work; there is no dense
 // contraction, so no tensor-core path.  Compiled with -fmad=false (see rpw_device.cuh).
 #include "rpw_kernels.h"
-
-#include <cooperative_groups.h>
-
-namespace cg = cooperative_groups;
 
 namespace rpw {
 
@@ -226,6 +223,7 @@ struct FitSmem {
 constexpr int kRedMax = 16;
 constexpr int kCapTiny = 1024;   // points a 64-thread block keeps in shared memory
 constexpr int kCapSmall = 4096;  // points a 128-thread block keeps in shared memory
+constexpr int kCapLarge = 8192;  // 512-thread block; larger patches stream from L2
 
 // Sum of K floats over the block; every thread receives the totals (bitwise identical in all
 // threads).  One __syncthreads per call; the scratch area alternates so that back-to-back calls do
@@ -810,9 +808,10 @@ __device__ __forceinline__ FitSmem carve_smem(unsigned char* raw, int cap, int w
 // K3a: level 0 — the ring/sector patches themselves, one block per patch, no grid-wide barrier.
 // Patches come in very different sizes (a few points near the sensor, >10k in the far rings), so
 // the launch is split into size classes, each with its own block size and shared-memory carve-out:
-//   TT = 64,  <= 1024 points  (~15 KB)  : many resident blocks, their eigensolves overlap
-//   TT = 128, <= 4096 points  (~55 KB)
-//   TT = 256, everything larger: <= 8192 points shared-memory resident (~108 KB), beyond that streamed
+//   TT = 64,   <= 1024 points  (~15 KB)  : many resident blocks, their eigensolves overlap
+//   TT = 128,  <= 4096 points  (~55 KB)
+//   TT = 512,  everything larger: <= 8192 points shared-memory resident (~108 KB), beyond that
+//              streamed from L2; the far-ring patches that iterate longest get the most threads
 // The class kernels run concurrently on separate streams and the hardware block scheduler packs
 // whatever mix fits an SM.  blockIdx.x walks (patch rank, scan) largest patch first; a block whose
 // patch belongs to another class exits at once.
@@ -821,7 +820,8 @@ __device__ __forceinline__ FitSmem carve_smem(unsigned char* raw, int cap, int w
 // float solver, which is enough to tip chaotic two-layer patches the other way).
 // ---------------------------------------------------------------------------------------------
 template <int TT, bool EXACT>
-__global__ void __launch_bounds__(TT) rpw_fit_roots_kernel(FitArgs A, uint32_t n_lo, uint32_t n_hi, int cap) {
+__global__ void __launch_bounds__(TT, (TT <= 64 ? 8 : TT <= 128 ? 4 : 2))
+rpw_fit_roots_kernel(FitArgs A, uint32_t n_lo, uint32_t n_hi, int cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t id = blockIdx.x;
     const uint32_t b = id % (uint32_t)A.n_scans, p = A.patch_order[id / (uint32_t)A.n_scans];
@@ -831,24 +831,41 @@ __global__ void __launch_bounds__(TT) rpw_fit_roots_kernel(FitArgs A, uint32_t n
     if (nd.n == 0 || nd.n <= n_lo || nd.n > n_hi) return;  // :380 empty patch, or another class's patch
     FitSmem S = carve_smem(smem_raw, cap, TT / 32);
     if (nd.n <= (uint32_t)cap) process_node<TT, true, EXACT>(A, nd, 0, S);
-    else if constexpr (TT == 256) process_node<TT, false, EXACT>(A, nd, 0, S);
+    else if constexpr (TT >= 512) process_node<TT, false, EXACT>(A, nd, 0, S);
     if (threadIdx.x == 0) atomicAdd(A.stats + 1, 1u);
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3b: levels >= 1 — persistent cooperative kernel, level-synchronous device worklist with no
-// host round trip: every split at level l pushed its children to the queue of level l+1;
-// grid.sync() separates levels; the kernel ends when a level enqueued nothing.  Typical scans never
-// split and the kernel falls through after one barrier.
+// K3b: levels >= 1 — persistent kernel, level-synchronous device worklist with no host round trip:
+// every split at level l pushed its children to the queue of level l+1; a grid-wide barrier
+// separates levels; the kernel ends when a level enqueued nothing.  Typical scans never split: every
+// block then reads an empty queue and leaves without touching the barrier.
+//
+// The grid is one block per SM and the barrier is a counter in global memory (arrive + spin), not a
+// cooperative launch: a cooperative kernel cannot start until the whole grid fits at once, which
+// would stall the other launch group that the host pipelines next to this one.  Blocks of this
+// kernel only ever wait for sibling blocks of the same launch, and those only wait for SM resources
+// held by independent kernels that run to completion, so the spin always ends.  All cross-block data
+// (children, queues, counters) is read with ld.global.cg, so no stale L1 lines are involved.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(uint32_t* ctr, uint32_t target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        while (*reinterpret_cast<volatile uint32_t*>(ctr) < target) __nanosleep(64);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
 template <bool EXACT>
-__global__ void __launch_bounds__(kFitThreads, 2) rpw_fit_levels_kernel(FitArgs A) {
+__global__ void __launch_bounds__(kFitThreads, 1) rpw_fit_levels_kernel(FitArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cg::grid_group grid = cg::this_grid();
     constexpr int TT = kFitThreads;
     FitSmem S = carve_smem(smem_raw, A.smem_cap, TT / 32);
     __shared__ uint32_t s_fetch;
-    uint32_t n_done = 0, pre = 0;
+    uint32_t n_done = 0, pre = 0, bar_target = 0;
     Tick ktick(A.timing);
     int level = 0;
     for (;;) {
@@ -874,7 +891,8 @@ __global__ void __launch_bounds__(kFitThreads, 2) rpw_fit_levels_kernel(FitArgs 
             n_done++;
             if (A.timing && threadIdx.x == 0) ktick.last = clock64();
         }
-        grid.sync();
+        bar_target += gridDim.x;
+        grid_barrier(A.stats + 4, bar_target);
         ktick(9);
     }
     // bookkeeping + self-cleaning: the last block to arrive publishes the totals and zeroes the
@@ -887,6 +905,7 @@ __global__ void __launch_bounds__(kFitThreads, 2) rpw_fit_levels_kernel(FitArgs 
             A.stats[0] = max(A.stats[0], (uint32_t)level + 1);
             A.stats[3] += atomicExch(A.stats + 1, 0u);
             A.stats[2] = 0;
+            A.stats[4] = 0;
             for (int l = 0; l <= level + 1; ++l) { A.fetch_ctr[l] = 0; A.q_count[l] = 0; }
         }
     }
@@ -981,9 +1000,9 @@ cudaError_t fit_configure(int smem_cap, int* blocks_per_sm) {
     if ((e = set_smem(rpw_fit_roots_kernel<64, false>, fit_smem_bytes(kCapTiny, 64))) != cudaSuccess) return e;
     if ((e = set_smem(rpw_fit_roots_kernel<128, true>, fit_smem_bytes(kCapSmall, 128))) != cudaSuccess) return e;
     if ((e = set_smem(rpw_fit_roots_kernel<128, false>, fit_smem_bytes(kCapSmall, 128))) != cudaSuccess) return e;
+    if ((e = set_smem(rpw_fit_roots_kernel<512, true>, fit_smem_bytes(kCapLarge, 512))) != cudaSuccess) return e;
+    if ((e = set_smem(rpw_fit_roots_kernel<512, false>, fit_smem_bytes(kCapLarge, 512))) != cudaSuccess) return e;
     const size_t smem = fit_smem_bytes(smem_cap, kFitThreads);
-    if ((e = set_smem(rpw_fit_roots_kernel<256, true>, smem)) != cudaSuccess) return e;
-    if ((e = set_smem(rpw_fit_roots_kernel<256, false>, smem)) != cudaSuccess) return e;
     if ((e = set_smem(rpw_fit_levels_kernel<true>, smem)) != cudaSuccess) return e;
     if ((e = set_smem(rpw_fit_levels_kernel<false>, smem)) != cudaSuccess) return e;
     int a = 0, b = 0;
@@ -993,7 +1012,7 @@ cudaError_t fit_configure(int smem_cap, int* blocks_per_sm) {
     return cudaSuccess;
 }
 
-// size class c: 0 tiny, 1 small, 2 large (see rpw_fit_roots_kernel)
+// size class: 0 tiny, 1 small, 2 large (see rpw_fit_roots_kernel)
 cudaError_t launch_fit_roots(cudaStream_t st, const FitArgs& args, int cls) {
     const unsigned grid = (unsigned)args.n_roots;
     const bool ex = args.fp.exact_eig != 0;
@@ -1006,18 +1025,18 @@ cudaError_t launch_fit_roots(cudaStream_t st, const FitArgs& args, int cls) {
         if (ex) rpw_fit_roots_kernel<128, true><<<grid, 128, sm, st>>>(args, (uint32_t)kCapTiny, (uint32_t)kCapSmall, kCapSmall);
         else rpw_fit_roots_kernel<128, false><<<grid, 128, sm, st>>>(args, (uint32_t)kCapTiny, (uint32_t)kCapSmall, kCapSmall);
     } else {
-        const size_t sm = fit_smem_bytes(args.smem_cap, 256);
-        if (ex) rpw_fit_roots_kernel<256, true><<<grid, 256, sm, st>>>(args, (uint32_t)kCapSmall, 0xFFFFFFFFu, args.smem_cap);
-        else rpw_fit_roots_kernel<256, false><<<grid, 256, sm, st>>>(args, (uint32_t)kCapSmall, 0xFFFFFFFFu, args.smem_cap);
+        const size_t sm = fit_smem_bytes(kCapLarge, 512);
+        if (ex) rpw_fit_roots_kernel<512, true><<<grid, 512, sm, st>>>(args, (uint32_t)kCapSmall, 0xFFFFFFFFu, kCapLarge);
+        else rpw_fit_roots_kernel<512, false><<<grid, 512, sm, st>>>(args, (uint32_t)kCapSmall, 0xFFFFFFFFu, kCapLarge);
     }
     return cudaGetLastError();
 }
 
 cudaError_t launch_fit_levels(cudaStream_t st, const FitArgs& args, int grid_blocks) {
-    FitArgs a = args;
-    void* params[] = {&a};
-    void* fn = args.fp.exact_eig ? (void*)rpw_fit_levels_kernel<true> : (void*)rpw_fit_levels_kernel<false>;
-    return cudaLaunchCooperativeKernel(fn, dim3(grid_blocks), dim3(kFitThreads), params, fit_smem_bytes(args.smem_cap, kFitThreads), st);
+    const size_t sm = fit_smem_bytes(args.smem_cap, kFitThreads);
+    if (args.fp.exact_eig) rpw_fit_levels_kernel<true><<<grid_blocks, kFitThreads, sm, st>>>(args);
+    else rpw_fit_levels_kernel<false><<<grid_blocks, kFitThreads, sm, st>>>(args);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_eig3(cudaStream_t st, const float* mats, size_t count, float* evals, float* evecs) {
