@@ -146,6 +146,7 @@ static int check_config(const rpw_config* c, std::string& why) {
 static void apply_config(rpw_handle* h, const rpw_config* c) {
     h->cfg = *c;
     rpw_zone_model(c, h->zm.ring_edges, &h->zm.sector_angle);
+    h->zm.inv_sector_angle = 1.0f / h->zm.sector_angle;
     h->zm.radius = c->filtering_radius;
     h->zm.num_sectors = c->num_sectors;
     h->zm.num_patches = RPW_NUM_RINGS * c->num_sectors;

@@ -203,3 +203,32 @@ def test_closed_form_solver_label_parity(case, rpw, gpu_handle_factory, oracle):
     print(case, rep)
     assert rep["key_mismatch"] == 0 and rep["n_flips_nonpatch"] == 0
     assert rep["label_agreement"] >= LABEL_BAR
+
+
+def test_sector_edges_take_the_exact_path(rpw, h, oracle):
+    """K1 decides sectors from a cheap angle estimate unless the point is within 5e-5 rad of a sector
+    edge; those fall back to the bit-exact libm sequence.  Put points ON the edges (and a few ulps
+    around them, all four quadrants, +-0 coordinates) and demand exact keys."""
+    import oracle_lib
+    for S, R in ((10, 80.0), (37, 60.0), (128, 150.0), (1, 50.0)):
+        cfg = rpw.PatchworkConfig(num_sectors=S, filtering_radius=R)
+        _, delta = oracle.zone_model(oracle_lib.to_cfg(cfg))
+        edges = (np.arange(S + 1, dtype=np.float32) * np.float32(delta)).astype(np.float32)
+        ang = []
+        for k in range(-6, 7):
+            a = edges.copy()
+            for _ in range(abs(k)):
+                a = np.nextafter(a, np.float32(np.inf if k > 0 else -np.inf)).astype(np.float32)
+            ang.append(a)
+        ang = np.concatenate(ang + [edges + np.float32(4e-5), edges - np.float32(4e-5), edges + np.float32(6e-5)])
+        rng = np.random.default_rng(S)
+        r = rng.uniform(1.5, R * 0.99, len(ang)).astype(np.float32)
+        pts = np.stack([r * np.cos(ang.astype(np.float64)), r * np.sin(ang.astype(np.float64)), np.zeros_like(r)], 1).astype(np.float32)
+        extra = np.array([[5, 0.0, 0], [5, -0.0, 0], [-5, 0.0, 0], [-5, -0.0, 0], [0.0, 5, 0], [-0.0, 5, 0], [0.0, -5, 0], [5, -1e-9, 0],
+                          [5, 1e-9, 0], [5, -1e-30, 0], [1.0, 0, 0], [R, 0, 0]], np.float32)
+        pts = np.concatenate([pts, extra])
+        h.set_config(cfg.to_c())
+        h.segment(pts)
+        keys = h.debug_keys(len(pts))
+        o = oracle.run(cfg, pts)
+        assert np.array_equal(keys, o["keys"]), (S, np.nonzero(keys != o["keys"])[0][:10])
