@@ -229,13 +229,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)  # samples from the first warm-up step to the end of the e2e arm (all under load)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_resident()
     barrier()
     h.profile_enable(True)
     launches0 = h.kernel_launches()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
@@ -244,7 +244,6 @@ def main():
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop()
     prof = h.profile_read()
     h.profile_enable(False)
     launches = h.kernel_launches() - launches0
@@ -317,6 +316,23 @@ def main():
     e2e_value = world * B * e2e_steps / float(t.item())
     for hc, _, _, _ in chunks:
         hc.close()
+    clocks = sampler.stop()
+
+    # ---- single-scan latency: the reference's own use (one scan per ROS2 callback), synchronous
+    # rpw_segment on pinned host buffers, H2D + 7 launches + D2H per call ----
+    lat_ms = None
+    if rank == 0:
+        h1 = rpw.Handle(cfg.to_c(), local_rank, POINTS_PER_SCAN + 4096, 1)
+        h1.set_plane_solver(solver_id)
+        lat = []
+        for i in range(min(B, 48)):
+            a = pin_in.array[int(offsets[i]):int(offsets[i + 1])]
+            o = pin_out.array[int(offsets[i]):int(offsets[i + 1])]
+            t0 = time.perf_counter()
+            h1.lib.rpw_segment(h1._h, a.ctypes.data, len(a), 12, o.ctypes.data, None)
+            lat.append(time.perf_counter() - t0)
+        lat_ms = {"median": 1e3 * float(np.median(lat[8:])), "p90": 1e3 * float(np.quantile(lat[8:], 0.9)), "scans": len(lat) - 8}
+        h1.close()
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -352,6 +368,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": total * 12, "d2h_bytes_per_step": total,
                     "api": f"rpw_segment_batch_async + rpw_wait (C-ABI) over {len(chunks)} handles, pinned host xyz stride 12 in, labels out",
                     "steps": e2e_steps},
+            "single_scan_latency_ms": lat_ms,
             "solver": args.solver,
             "other_solver": {"name": "closed_form" if solver_id == rpw.capi.SOLVER_EIGEN_QR else "eigen_qr", "value": other_value, "unit": UNIT},
             "gpu_launches": int(launches),

@@ -130,11 +130,11 @@ void rpw_synth_testsuite(uint32_t seed, size_t n, float* out) {
 // of the azimuth range and so exercises the beyond-radius path); `nan_per_million` of the
 // returns are replaced by NaN records to exercise the cleaning path.
 //   clutter = 0: planar ground (slightly tilted per seed) + 25-40 boxes (cars, poles, walls).
-//   clutter = 1: undulating ground (up to +-0.3 m, 40-90 m wavelengths) with a porous second layer
-//                0.8-1.0 m above it over 6-9 large regions (12-30 m radius) (kerbs / vegetation / vehicle
-//                bodies; half of the beams inside a region return from the layer), 60-90 boxes.
-//                Inside a region the first plane fit lands between the two layers, finds no
-//                inliers, collapses, and the patch splits until its bbox drops under 25 m^2.
+//   clutter = 1: gently undulating ground (40-90 m wavelengths) with a porous second layer 0.85-1.05 m
+//                above it in six of the ten 36-degree sectors (kerbs / vegetation / vehicle bodies; half
+//                of the beams there return from the layer), 15-25 boxes within 40 m, backdrop beyond R.  In a layered
+//                sector the first plane fit lands between the two sheets, finds no inliers, collapses,
+//                and the patch splits until its bbox drops under 25 m^2 (depth 4-6 in the outer rings).
 // Returns the number of records written (= beams * steps).
 size_t rpw_synth_spinning(uint32_t seed, int beams, int steps, int clutter, int nan_per_million, float* out) {
     Rng rng(seed * 2654435761u + 12345u);
@@ -147,7 +147,7 @@ size_t rpw_synth_spinning(uint32_t seed, int beams, int steps, int clutter, int 
     // undulation: a few random sinusoids (clutter only)
     double ua[4], ukx[4], uky[4], uph[4];
     for (int k = 0; k < 4; ++k) {
-        ua[k] = clutter ? rng.uni(0.04, 0.09) : 0.0;
+        ua[k] = clutter ? rng.uni(0.02, 0.045) : 0.0;
         const double wl = rng.uni(40.0, 90.0), th = rng.uni(0, 2 * kPi);
         ukx[k] = 2 * kPi / wl * std::cos(th); uky[k] = 2 * kPi / wl * std::sin(th);
         uph[k] = rng.uni(0, 2 * kPi);
@@ -157,20 +157,24 @@ size_t rpw_synth_spinning(uint32_t seed, int beams, int steps, int clutter, int 
         for (int k = 0; k < 4; ++k) z += ua[k] * std::sin(ukx[k] * x + uky[k] * y + uph[k]);
         return z;
     };
-    // second-layer coverage field (clutter only): blobs where a layer 0.6-1.0 m above ground exists
-    const int n_blobs = clutter ? rng.irange(6, 9) : 0;
-    std::vector<double> bx(n_blobs), by(n_blobs), br(n_blobs), bh(n_blobs);
-    for (int k = 0; k < n_blobs; ++k) {
-        const double r = rng.uni(8.0, 55.0), a = rng.uni(0, 2 * kPi);
-        bx[k] = r * std::cos(a); by[k] = r * std::sin(a);
-        br[k] = rng.uni(12.0, 30.0);
-        bh[k] = rng.uni(0.8, 1.0);
+    // second-layer coverage (clutter only): six of the ten 36-degree sectors of the default zone model
+    // (chosen per seed) carry a porous layer 0.85-1.05 m above the ground, all ranges, each with its
+    // own height; inside such a sector every ground return comes from the layer with probability one
+    // half.  Whole ring/sector patches are therefore two parallel sheets: the first plane fit lands
+    // exactly between them, finds no inliers, collapses, and the patch splits until its
+    // bounding box drops under 25 m^2 — depth 4-6 in the outer rings.
+    const int n_blobs = clutter ? 10 : 0;
+    std::vector<double> bh(n_blobs, 0.0);  // layer height per sector, 0 = no layer
+    if (clutter) {
+        int order[10];
+        for (int k = 0; k < 10; ++k) order[k] = k;
+        for (int k = 9; k > 0; --k) { const int j = rng.irange(0, k); std::swap(order[k], order[j]); }
+        for (int k = 0; k < 6; ++k) bh[order[k]] = rng.uni(0.85, 1.05);
     }
-
-    const int n_boxes = clutter ? rng.irange(60, 90) : rng.irange(25, 40);
+    const int n_boxes = clutter ? rng.irange(15, 25) : rng.irange(25, 40);
     std::vector<Box> boxes(n_boxes);
     for (auto& b : boxes) {
-        const double r = rng.uni(5.0, 60.0), a = rng.uni(0, 2 * kPi), yaw = rng.uni(0, kPi);
+        const double r = rng.uni(clutter ? 9.0 : 5.0, clutter ? 40.0 : 60.0), a = rng.uni(0, 2 * kPi), yaw = rng.uni(0, kPi);
         b.cx = r * std::cos(a); b.cy = r * std::sin(a);
         const double kind = rng.uni();
         double L, W, H;
@@ -186,7 +190,8 @@ size_t rpw_synth_spinning(uint32_t seed, int beams, int steps, int clutter, int 
     double ba[3], bp[3];
     for (int k = 0; k < 3; ++k) { ba[k] = rng.uni(4.0, 9.0); bp[k] = rng.uni(0, 2 * kPi); }
     auto backdrop_r = [&](double az) {
-        return 85.0 + ba[0] * std::sin(az + bp[0]) + ba[1] * std::sin(2 * az + bp[1]) + ba[2] * std::sin(5 * az + bp[2]);
+        // clutter scenes keep the backdrop beyond R = 80 m so that the outer rings stay two clean sheets
+        return (clutter ? 110.0 : 85.0) + ba[0] * std::sin(az + bp[0]) + ba[1] * std::sin(2 * az + bp[1]) + ba[2] * std::sin(5 * az + bp[2]);
     };
 
     const double o[3] = {0.0, 0.0, h};
@@ -224,13 +229,15 @@ size_t rpw_synth_spinning(uint32_t seed, int beams, int steps, int clutter, int 
             if (tbk < t) { t = tbk; what = 2; }
             double x = t * d[0], y = t * d[1], z = h + t * d[2];
             if (what == 0) {
-                // second layer: with probability 0.55 the return comes from the layer instead of the ground
+                // second layer: inside a layered sector half of the beams return from the layer
                 bool layered = false;
-                for (int k = 0; k < n_blobs && !layered; ++k) {
-                    const double dx = x - bx[k], dy = y - by[k];
-                    if (dx * dx + dy * dy < br[k] * br[k]) {
-                        // porous layer: about half of the beams are returned by it, the rest reach the ground
-                        if (rng.uni() < 0.5) z += bh[k] + 0.03 * rng.normal();
+                if (n_blobs) {
+                    double a = std::atan2(y, x);
+                    if (a < 0) a += 2 * kPi;
+                    int sec = (int)(a / (2 * kPi / 10.0));
+                    sec = sec < 0 ? 0 : (sec > 9 ? 9 : sec);
+                    if (bh[sec] > 0.0) {
+                        if (rng.uni() < 0.5) z += bh[sec] + 0.03 * rng.normal();
                         else z += 0.02 * rng.normal();
                         layered = true;
                     }
