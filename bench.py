@@ -320,7 +320,7 @@ def main():
 
     # ---- single-scan latency: the reference's own use (one scan per ROS2 callback), synchronous
     # rpw_segment on pinned host buffers, H2D + 7 launches + D2H per call ----
-    lat_ms = None
+    lat_ms, other_shapes = None, None
     if rank == 0:
         h1 = rpw.Handle(cfg.to_c(), local_rank, POINTS_PER_SCAN + 4096, 1)
         h1.set_plane_solver(solver_id)
@@ -333,6 +333,24 @@ def main():
             lat.append(time.perf_counter() - t0)
         lat_ms = {"median": 1e3 * float(np.median(lat[8:])), "p90": 1e3 * float(np.quantile(lat[8:], 0.9)), "scans": len(lat) - 8}
         h1.close()
+        # the other named shapes, one scan at a time (BASELINE configs[3] and [4]); parity for them is in tests/
+        other_shapes = {}
+        for name, pc, cloud in (("C4 3x solid-state merged ~300k pts, banked track, R=150", rpw.PatchworkConfig(), rpw.synth.solidstate_merged(2000)),
+                                ("C5 128-beam dense urban 262k pts, deep recursion, R=80", rpw.PatchworkConfig(filtering_radius=80.0), rpw.synth.dense_urban_scan(3000))):
+            hs = rpw.Handle(pc.to_c(), local_rank, len(cloud) + 4096, 1)
+            hs.set_plane_solver(solver_id)
+            pi = rpw.capi.PinnedArray((len(cloud), 3), np.float32)
+            pi.array[:] = cloud[:, :3]
+            po = rpw.capi.PinnedArray((len(cloud),), np.uint8)
+            ts = []
+            for _ in range(12):
+                t0 = time.perf_counter()
+                hs.lib.rpw_segment(hs._h, pi.ptr, len(cloud), 12, po.ptr, None)
+                ts.append(time.perf_counter() - t0)
+            med = float(np.median(ts[2:]))
+            other_shapes[name] = {"points": int(len(cloud)), "ms_per_scan": 1e3 * med, "scans_per_sec": 1.0 / med, "mpoints_per_sec": len(cloud) / med / 1e6,
+                                  "ground_points": int((po.array == 1).sum())}
+            hs.close()
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -369,6 +387,7 @@ def main():
                     "api": f"rpw_segment_batch_async + rpw_wait (C-ABI) over {len(chunks)} handles, pinned host xyz stride 12 in, labels out",
                     "steps": e2e_steps},
             "single_scan_latency_ms": lat_ms,
+            "other_shapes_single_scan": other_shapes,
             "solver": args.solver,
             "other_solver": {"name": "closed_form" if solver_id == rpw.capi.SOLVER_EIGEN_QR else "eigen_qr", "value": other_value, "unit": UNIT},
             "gpu_launches": int(launches),

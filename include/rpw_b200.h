@@ -155,7 +155,8 @@ const char* rpw_last_error(const rpw_handle* h);
 
 /* ---- the path, host buffers in / host labels out ---------------------------------------- */
 /* One scan.  xyz: n points, first three floats of every `stride_bytes` record (12 = the
- * reference's Point3D AoS, 16 = float4).  labels_out: n bytes.  stats may be NULL.
+ * reference's Point3D AoS, 16 = float4, any multiple of 4 up to 1024 = wider records with xyz in
+ * front, which is how RP/src/rosbag_loader.cpp:226-254 reads a PointCloud2).  labels_out: n bytes.  stats may be NULL.
  * Synchronous: returns after labels_out is filled. */
 int rpw_segment(rpw_handle* h, const float* xyz, size_t n, size_t stride_bytes, uint8_t* labels_out, rpw_stats* stats);
 
@@ -169,6 +170,14 @@ int rpw_segment_batch(rpw_handle* h, const float* const* clouds, const size_t* n
 int rpw_segment_batch_async(rpw_handle* h, const float* const* clouds, const size_t* n, size_t batch, size_t stride_bytes,
                             uint8_t* const* labels_out);
 int rpw_wait(rpw_handle* h, rpw_stats* stats);
+
+/* One scan straight from a sensor_msgs/PointCloud2 data buffer (little-endian float32 x, y, z
+ * fields at byte offsets off_x/off_y/off_z of every point_step-byte record): the device reads the
+ * records in place, so the host-side pcl::fromROSMsg + copy loop of the node
+ * (RP/src/recursive_patchwork_node.cpp:67-88) disappears.  The buffer is copied as it is
+ * (n_points * point_step bytes). */
+int rpw_segment_pc2(rpw_handle* h, const void* data, size_t n_points, size_t point_step, size_t off_x, size_t off_y, size_t off_z,
+                    uint8_t* labels_out, rpw_stats* stats);
 
 /* One scan, with the two clouds the reference returns, in the reference's order.
  * ground_xyz / nonground_xyz: caller buffers of 3*n floats each (either may be NULL). */

@@ -48,7 +48,7 @@ NODE_DTYPE = np.dtype([("scan", "<i4"), ("root", "<i4"), ("depth", "<i4"), ("sta
 # Every symbol include/rpw_b200.h declares (tests check that the library exports all of them).
 EXPORTS = ["rpw_default_config", "rpw_zone_model", "rpw_create", "rpw_destroy", "rpw_set_config", "rpw_get_config",
            "rpw_set_plane_solver", "rpw_set_stream", "rpw_last_error", "rpw_segment", "rpw_segment_batch", "rpw_segment_batch_async", "rpw_wait",
-           "rpw_segment_clouds", "rpw_segment_device", "rpw_debug_keys", "rpw_debug_enable_nodes", "rpw_debug_nodes",
+           "rpw_segment_pc2", "rpw_segment_clouds", "rpw_segment_device", "rpw_debug_keys", "rpw_debug_enable_nodes", "rpw_debug_nodes",
            "rpw_debug_eig3", "rpw_debug_normal", "rpw_debug_atan2", "rpw_debug_fit_timing", "rpw_profile_enable", "rpw_profile_read", "rpw_host_alloc", "rpw_host_free", "rpw_kernel_launches", "rpw_abi_version"]
 
 _lib = None
@@ -85,6 +85,7 @@ def load_library() -> C.CDLL:
     lib.rpw_segment_batch_async.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), sz, sz, C.POINTER(vp)]
     lib.rpw_segment_batch_async.restype = C.c_int
     lib.rpw_wait.argtypes = [vp, C.POINTER(RpwStats)]; lib.rpw_wait.restype = C.c_int
+    lib.rpw_segment_pc2.argtypes = [vp, vp, sz, sz, sz, sz, sz, vp, C.POINTER(RpwStats)]; lib.rpw_segment_pc2.restype = C.c_int
     lib.rpw_segment_clouds.argtypes = [vp, vp, sz, sz, vp, vp, C.POINTER(sz), vp, C.POINTER(sz)]
     lib.rpw_segment_clouds.restype = C.c_int
     lib.rpw_segment_device.argtypes = [vp, vp, C.POINTER(C.c_uint64), sz, vp]; lib.rpw_segment_device.restype = C.c_int
@@ -192,8 +193,8 @@ class Handle:
     @staticmethod
     def _as_points(points):
         a = np.ascontiguousarray(points, dtype=np.float32)
-        if a.ndim != 2 or a.shape[1] not in (3, 4):
-            raise ValueError("points must be (n, 3) or (n, 4) float32")
+        if a.ndim != 2 or a.shape[1] < 3:
+            raise ValueError("points must be (n, k >= 3) float32 with x, y, z first")
         return a
 
     def segment(self, points, want_stats=False):
@@ -227,6 +228,14 @@ class Handle:
 
     def wait(self):
         self._check(self.lib.rpw_wait(self._h, None))
+
+    def segment_pc2(self, data, n_points, point_step, off_x=0, off_y=4, off_z=8):
+        """data: bytes-like PointCloud2 payload (n_points * point_step bytes)."""
+        buf = np.frombuffer(data, dtype=np.uint8)
+        assert buf.size >= n_points * point_step
+        labels = np.empty(n_points, np.uint8)
+        self._check(self.lib.rpw_segment_pc2(self._h, buf.ctypes.data, n_points, point_step, off_x, off_y, off_z, labels.ctypes.data, None))
+        return labels
 
     def segment_clouds(self, points):
         a = self._as_points(points)

@@ -51,7 +51,10 @@ struct rpw_handle {
     int solver = RPW_SOLVER_EIGEN_QR;
 
     // device buffers
-    float* d_in = nullptr;       // staged input (12 or 16 bytes per point)
+    float* d_in = nullptr;       // staged input records of host-path calls
+    size_t d_in_bytes = 0;
+    size_t h_stage_in_bytes = 0;
+    size_t field_off[3] = {0, 4, 8};  // byte offsets of x, y, z inside a record for the next host-path call
     uint16_t* d_keys = nullptr;
     uint8_t* d_labels = nullptr;
     float4* d_sortedA = nullptr;
@@ -277,6 +280,7 @@ int rpw_create(const rpw_config* cfg, int device, size_t max_total_points, size_
     TRYC(cudaMemset(h->d_dbg_count, 0, sizeof(uint32_t)));
     const size_t N = max_total_points;
     TRYC(cudaMalloc(&h->d_in, N * 16));
+    h->d_in_bytes = N * 16;
     TRYC(cudaMalloc(&h->d_keys, N * sizeof(uint16_t)));
     TRYC(cudaMalloc(&h->d_labels, N));
     TRYC(cudaMalloc(&h->d_sortedA, N * sizeof(float4)));
@@ -437,7 +441,7 @@ struct StreamSwap {
 };
 
 // One launch group: scans [b0, b0 + nb) of the call on lane `L`, stream `st`.
-static int run_group(rpw_handle* h, rpw_handle::Lane& L, cudaStream_t st, const float* d_pts, int stride_floats, uint8_t* d_labels,
+static int run_group(rpw_handle* h, rpw_handle::Lane& L, cudaStream_t st, const float* d_pts, const PointLayout& lay, uint8_t* d_labels,
                      size_t b0, size_t nb) {
     const uint64_t* so = h->last_off.data();
     uint64_t max_n = 0;
@@ -450,11 +454,11 @@ static int run_group(rpw_handle* h, rpw_handle::Lane& L, cudaStream_t st, const 
     const uint32_t* d_cb = h->d_chunk_base + b0;
     uint32_t* d_ps = h->d_patch_start + b0 * (size_t)(h->P + 1);
     { ProfScope ps(h, 0);
-      RPW_CUDA(h, launch_bin(st, stride_floats, d_pts, d_so, d_cb, h->zm, h->d_keys, d_labels, h->d_blk_hist, L.d_patch_total, max_chunks, (int)nb)); }
+      RPW_CUDA(h, launch_bin(st, lay, d_pts, d_so, d_cb, h->zm, h->d_keys, d_labels, h->d_blk_hist, L.d_patch_total, max_chunks, (int)nb)); }
     { ProfScope ps(h, 1);
       RPW_CUDA(h, launch_offsets(st, d_so, d_cb, h->d_blk_hist, d_ps, L.d_patch_total, h->P, (int)nb)); }
     { ProfScope ps(h, 2);
-      RPW_CUDA(h, launch_scatter(st, stride_floats, d_pts, d_so, d_cb, h->d_keys, h->d_blk_hist, d_ps, h->d_sortedA, L.d_patch_total,
+      RPW_CUDA(h, launch_scatter(st, lay, d_pts, d_so, d_cb, h->d_keys, h->d_blk_hist, d_ps, h->d_sortedA, L.d_patch_total,
                                  L.d_patch_order, h->P, max_chunks, (int)nb)); }
     FitArgs A;
     A.sortedA = h->d_sortedA; A.bufB = h->d_bufB; A.bufC = h->d_bufC; A.gmask = h->d_gmask;
@@ -499,7 +503,7 @@ static int run_group(rpw_handle* h, rpw_handle::Lane& L, cudaStream_t st, const 
 }
 
 // Enqueues K1..K3 for scans [0, batch) whose points are device resident at `d_pts`.
-static int run_pipeline(rpw_handle* h, const float* d_pts, int stride_floats, uint8_t* d_labels, size_t batch) {
+static int run_pipeline(rpw_handle* h, const float* d_pts, const PointLayout& lay, uint8_t* d_labels, size_t batch) {
     h->launches_call = 0;
     // stats[0] (levels) and stats[3] (nodes) accumulate over the call's launch groups
     for (auto& L : h->lane) {
@@ -510,7 +514,7 @@ static int run_pipeline(rpw_handle* h, const float* d_pts, int stride_floats, ui
     int waves = h->n_waves > 0 ? h->n_waves : 1;
     if ((size_t)waves > batch) waves = (int)batch;
     if (h->dbg_enabled || h->timing_enabled) waves = 1;  // debug records are easier to read in one group
-    if (waves <= 1) return run_group(h, h->lane[0], h->stream, d_pts, stride_floats, d_labels, 0, batch);
+    if (waves <= 1) return run_group(h, h->lane[0], h->stream, d_pts, lay, d_labels, 0, batch);
     // fork: both lanes wait for everything already enqueued on the handle's stream (inputs, meta)
     RPW_CUDA(h, cudaEventRecord(h->ev_call, h->stream));
     for (auto& L : h->lane) RPW_CUDA(h, cudaStreamWaitEvent(L.main, h->ev_call, 0));
@@ -518,7 +522,7 @@ static int run_pipeline(rpw_handle* h, const float* d_pts, int stride_floats, ui
         const size_t b0 = batch * (size_t)w / waves, b1 = batch * (size_t)(w + 1) / waves;
         if (b1 <= b0) continue;
         rpw_handle::Lane& L = h->lane[w % rpw_handle::kLanes];
-        int rc = run_group(h, L, L.main, d_pts, stride_floats, d_labels, b0, b1 - b0);
+        int rc = run_group(h, L, L.main, d_pts, lay, d_labels, b0, b1 - b0);
         if (rc != RPW_OK) return rc;
     }
     // join
@@ -535,11 +539,31 @@ static bool is_pinned(const void* p) {
     return a.type == cudaMemoryTypeHost;
 }
 
-static int ensure_stage(rpw_handle* h) {
-    if (!h->h_stage_in) RPW_CUDA(h, cudaMallocHost(&h->h_stage_in, h->cap_points * 16));
+static int ensure_stage(rpw_handle* h, size_t in_bytes) {
+    if (in_bytes < h->cap_points * 16) in_bytes = h->cap_points * 16;
+    if (!h->h_stage_in || h->h_stage_in_bytes < in_bytes) {
+        if (h->h_stage_in) cudaFreeHost(h->h_stage_in);
+        h->h_stage_in = nullptr;
+        RPW_CUDA(h, cudaMallocHost(&h->h_stage_in, in_bytes));
+        h->h_stage_in_bytes = in_bytes;
+    }
     if (!h->h_stage_labels) RPW_CUDA(h, cudaMallocHost(&h->h_stage_labels, h->cap_points));
     return RPW_OK;
 }
+
+// Wide records (a PointCloud2 point_step above 16 bytes) need a larger device staging area.
+static int ensure_d_in(rpw_handle* h, size_t bytes) {
+    if (bytes <= h->d_in_bytes) return RPW_OK;
+    RPW_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_in);
+    h->d_in = nullptr;
+    h->d_in_bytes = 0;
+    RPW_CUDA(h, cudaMalloc(&h->d_in, bytes));
+    h->d_in_bytes = bytes;
+    return RPW_OK;
+}
+
+static bool stride_ok(size_t stride_bytes) { return stride_bytes >= 12 && stride_bytes <= 1024 && stride_bytes % 4 == 0; }
 
 static int reset_dbg(rpw_handle* h) {
     if (h->dbg_enabled) RPW_CUDA(h, cudaMemsetAsync(h->d_dbg_count, 0, sizeof(uint32_t), h->stream));
@@ -578,7 +602,7 @@ int rpw_segment_batch_async(rpw_handle* h, const float* const* clouds, const siz
                             uint8_t* const* labels_out) {
     if (!h) return RPW_ERR_BAD_ARG;
     if (!clouds || !n || !labels_out || batch == 0) RPW_FAIL(h, RPW_ERR_BAD_ARG, "NULL argument or empty batch");
-    if (stride_bytes != 12 && stride_bytes != 16) RPW_FAIL(h, RPW_ERR_BAD_ARG, "stride_bytes must be 12 (xyz) or 16 (xyzw), got %zu", stride_bytes);
+    if (!stride_ok(stride_bytes)) RPW_FAIL(h, RPW_ERR_BAD_ARG, "stride_bytes must be a multiple of 4 in [12, 1024], got %zu", stride_bytes);
     RPW_CUDA(h, cudaSetDevice(h->device));
     std::vector<uint64_t> off(batch + 1);
     off[0] = 0;
@@ -593,6 +617,8 @@ int rpw_segment_batch_async(rpw_handle* h, const float* const* clouds, const siz
     if (rc != RPW_OK) return rc;
     rc = reset_dbg(h);
     if (rc != RPW_OK) return rc;
+    rc = ensure_d_in(h, (size_t)off[batch] * stride_bytes);
+    if (rc != RPW_OK) return rc;
     // H2D: one copy per run of scans that are contiguous in host memory
     char* d_in = reinterpret_cast<char*>(h->d_in);
     for (size_t b = 0; b < batch;) {
@@ -603,7 +629,11 @@ int rpw_segment_batch_async(rpw_handle* h, const float* const* clouds, const siz
         if (bytes) RPW_CUDA(h, cudaMemcpyAsync(d_in + off[b] * stride_bytes, base, bytes, cudaMemcpyHostToDevice, h->stream));
         b = e;
     }
-    rc = run_pipeline(h, h->d_in, (int)(stride_bytes / 4), h->d_labels, batch);
+    PointLayout lay;
+    lay.stride = (int)(stride_bytes / 4);
+    lay.ox = (int)(h->field_off[0] / 4); lay.oy = (int)(h->field_off[1] / 4); lay.oz = (int)(h->field_off[2] / 4);
+    lay.vec4 = (stride_bytes == 16 && lay.ox == 0 && lay.oy == 1 && lay.oz == 2) ? 1 : 0;
+    rc = run_pipeline(h, h->d_in, lay, h->d_labels, batch);
     if (rc != RPW_OK) return rc;
     for (size_t b = 0; b < batch;) {
         size_t e = b + 1;
@@ -634,7 +664,7 @@ int rpw_segment_batch(rpw_handle* h, const float* const* clouds, const size_t* n
                       uint8_t* const* labels_out, rpw_stats* stats) {
     if (!h) return RPW_ERR_BAD_ARG;
     if (!clouds || !n || !labels_out || batch == 0) RPW_FAIL(h, RPW_ERR_BAD_ARG, "NULL argument or empty batch");
-    if (stride_bytes != 12 && stride_bytes != 16) RPW_FAIL(h, RPW_ERR_BAD_ARG, "stride_bytes must be 12 (xyz) or 16 (xyzw), got %zu", stride_bytes);
+    if (!stride_ok(stride_bytes)) RPW_FAIL(h, RPW_ERR_BAD_ARG, "stride_bytes must be a multiple of 4 in [12, 1024], got %zu", stride_bytes);
     RPW_CUDA(h, cudaSetDevice(h->device));
     size_t total = 0;
     for (size_t b = 0; b < batch; ++b) total += n[b];
@@ -655,7 +685,7 @@ int rpw_segment_batch(rpw_handle* h, const float* const* clouds, const size_t* n
         if (rc != RPW_OK) return rc;
         RPW_CUDA(h, cudaStreamSynchronize(h->stream));
     } else {
-        rc = ensure_stage(h);
+        rc = ensure_stage(h, total * stride_bytes);
         if (rc != RPW_OK) return rc;
         RPW_CUDA(h, cudaStreamSynchronize(h->stream));
         std::vector<const float*> src(batch);
@@ -687,6 +717,19 @@ int rpw_segment(rpw_handle* h, const float* xyz, size_t n, size_t stride_bytes, 
     const float* c[1] = {xyz};
     uint8_t* l[1] = {labels_out};
     return rpw_segment_batch(h, c, &n, 1, stride_bytes, l, stats);
+}
+
+int rpw_segment_pc2(rpw_handle* h, const void* data, size_t n_points, size_t point_step, size_t off_x, size_t off_y, size_t off_z,
+                    uint8_t* labels_out, rpw_stats* stats) {
+    if (!h) return RPW_ERR_BAD_ARG;
+    if (!stride_ok(point_step)) RPW_FAIL(h, RPW_ERR_BAD_ARG, "point_step must be a multiple of 4 in [12, 1024], got %zu", point_step);
+    const size_t offs[3] = {off_x, off_y, off_z};
+    for (size_t o : offs)
+        if (o % 4 != 0 || o + 4 > point_step) RPW_FAIL(h, RPW_ERR_BAD_ARG, "field offset %zu does not address a float32 inside a %zu-byte record", o, point_step);
+    h->field_off[0] = off_x; h->field_off[1] = off_y; h->field_off[2] = off_z;
+    const int rc = rpw_segment(h, reinterpret_cast<const float*>(data), n_points, point_step, labels_out, stats);
+    h->field_off[0] = 0; h->field_off[1] = 4; h->field_off[2] = 8;
+    return rc;
 }
 
 int rpw_segment_clouds(rpw_handle* h, const float* xyz, size_t n, size_t stride_bytes, uint8_t* labels_out,
@@ -731,7 +774,9 @@ int rpw_segment_device(rpw_handle* h, const void* d_points, const uint64_t* scan
     if (rc != RPW_OK) return rc;
     h->pend_labels.clear();
     const float* pts = reinterpret_cast<const float*>(d_points) + scan_offsets[0] * 4;
-    return run_pipeline(h, pts, 4, reinterpret_cast<uint8_t*>(d_labels) + scan_offsets[0], batch);
+    PointLayout lay;
+    lay.vec4 = 1; lay.stride = 4; lay.ox = 0; lay.oy = 1; lay.oz = 2;
+    return run_pipeline(h, pts, lay, reinterpret_cast<uint8_t*>(d_labels) + scan_offsets[0], batch);
 }
 
 int rpw_debug_keys(rpw_handle* h, uint16_t* keys_out, size_t n_total) {

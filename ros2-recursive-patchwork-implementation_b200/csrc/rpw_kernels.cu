@@ -24,19 +24,23 @@ namespace rpw {
 // =============================================================================================
 // K1: binning
 // =============================================================================================
-template <int STRIDE>
-__device__ __forceinline__ void load_xyz(const float* __restrict__ pts, uint64_t i, float& x, float& y, float& z) {
-    if (STRIDE == 4) {
+// Input records: VEC4 = packed float4 (x, y, z, ignored), one 16-byte load; otherwise any record of
+// `stride` 4-byte words with x, y, z at word offsets ox, oy, oz — the reference's 12-byte Point3D
+// (stride 3, offsets 0 1 2) and a PointCloud2 data buffer (point_step / 4, field offsets / 4;
+// RP/src/recursive_patchwork_node.cpp:67-88, RP/src/rosbag_loader.cpp:226-254) are both this case.
+template <bool VEC4>
+__device__ __forceinline__ void load_xyz(const float* __restrict__ pts, uint64_t i, const PointLayout& L, float& x, float& y, float& z) {
+    if (VEC4) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(pts) + i);
         x = v.x; y = v.y; z = v.z;
     } else {
-        const float* p = pts + i * 3;
-        x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
+        const float* p = pts + i * (uint64_t)L.stride;
+        x = __ldg(p + L.ox); y = __ldg(p + L.oy); z = __ldg(p + L.oz);
     }
 }
 
-template <int STRIDE>
-__global__ void __launch_bounds__(kBinThreads) rpw_bin_kernel(const float* __restrict__ pts, const uint64_t* __restrict__ scan_off,
+template <bool VEC4>
+__global__ void __launch_bounds__(kBinThreads) rpw_bin_kernel(const float* __restrict__ pts, PointLayout lay, const uint64_t* __restrict__ scan_off,
                                                              const uint32_t* __restrict__ chunk_base, ZoneModel zm,
                                                              uint16_t* __restrict__ keys, uint8_t* __restrict__ labels,
                                                              uint32_t* __restrict__ blk_hist, uint32_t* __restrict__ patch_total) {
@@ -61,7 +65,7 @@ __global__ void __launch_bounds__(kBinThreads) rpw_bin_kernel(const float* __res
         const bool valid = i < n;
         if (valid) {
             float x, y, z;
-            load_xyz<STRIDE>(pts, off + i, x, y, z);
+            load_xyz<VEC4>(pts, off + i, lay, x, y, z);
             key = bin_key(x, y, z, zm);
             keys[off + i] = key;
             // points that never enter a patch get their final label here; patch points are
@@ -134,8 +138,8 @@ __global__ void __launch_bounds__(256) rpw_offsets_kernel(const uint64_t* __rest
 // 32-group come from __match_any_sync.  No atomics claim slots, so the result is deterministic
 // and stable regardless of scheduling (SURVEY Q1 needs that).
 // =============================================================================================
-template <int STRIDE>
-__global__ void __launch_bounds__(kBinThreads) rpw_scatter_kernel(const float* __restrict__ pts, const uint64_t* __restrict__ scan_off,
+template <bool VEC4>
+__global__ void __launch_bounds__(kBinThreads) rpw_scatter_kernel(const float* __restrict__ pts, PointLayout lay, const uint64_t* __restrict__ scan_off,
                                                                  const uint32_t* __restrict__ chunk_base,
                                                                  const uint16_t* __restrict__ keys, const uint32_t* __restrict__ blk_hist,
                                                                  const uint32_t* __restrict__ patch_start, float4* __restrict__ sorted,
@@ -201,7 +205,7 @@ __global__ void __launch_bounds__(kBinThreads) rpw_scatter_kernel(const float* _
             const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
             const uint32_t pos = my[kk] + rank;
             float x, y, z;
-            load_xyz<STRIDE>(pts, off + i, x, y, z);
+            load_xyz<VEC4>(pts, off + i, lay, x, y, z);
             sorted[pos] = make_float4(x, y, z, __uint_as_float((uint32_t)(off + i)));
         }
         __syncwarp();
@@ -963,13 +967,13 @@ size_t fit_smem_bytes(int smem_cap, int threads) {
     return (size_t)smem_cap * 13 + (2 * (threads / 32) * kRedMax + 256 + 16) * 4 + 16;
 }
 
-cudaError_t launch_bin(cudaStream_t st, int stride_floats, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
+cudaError_t launch_bin(cudaStream_t st, const PointLayout& lay, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
                        const ZoneModel& zm, uint16_t* keys, uint8_t* labels, uint32_t* blk_hist, uint32_t* patch_total,
                        int max_chunks, int batch) {
     dim3 grid(max_chunks, batch);
     const size_t smem = (size_t)zm.num_patches * 4;
-    if (stride_floats == 4) rpw_bin_kernel<4><<<grid, kBinThreads, smem, st>>>(pts, scan_off, chunk_base, zm, keys, labels, blk_hist, patch_total);
-    else rpw_bin_kernel<3><<<grid, kBinThreads, smem, st>>>(pts, scan_off, chunk_base, zm, keys, labels, blk_hist, patch_total);
+    if (lay.vec4) rpw_bin_kernel<true><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, zm, keys, labels, blk_hist, patch_total);
+    else rpw_bin_kernel<false><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, zm, keys, labels, blk_hist, patch_total);
     return cudaGetLastError();
 }
 
@@ -979,13 +983,13 @@ cudaError_t launch_offsets(cudaStream_t st, const uint64_t* scan_off, const uint
     return cudaGetLastError();
 }
 
-cudaError_t launch_scatter(cudaStream_t st, int stride_floats, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
+cudaError_t launch_scatter(cudaStream_t st, const PointLayout& lay, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
                            const uint16_t* keys, const uint32_t* blk_hist, const uint32_t* patch_start, float4* sorted,
                            const uint32_t* patch_total, uint32_t* patch_order, int P, int max_chunks, int batch) {
     dim3 grid(max_chunks, batch);
     const size_t smem = (size_t)(kBinThreads / 32) * P * 4;
-    if (stride_floats == 4) rpw_scatter_kernel<4><<<grid, kBinThreads, smem, st>>>(pts, scan_off, chunk_base, keys, blk_hist, patch_start, sorted, patch_total, patch_order, P);
-    else rpw_scatter_kernel<3><<<grid, kBinThreads, smem, st>>>(pts, scan_off, chunk_base, keys, blk_hist, patch_start, sorted, patch_total, patch_order, P);
+    if (lay.vec4) rpw_scatter_kernel<true><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, keys, blk_hist, patch_start, sorted, patch_total, patch_order, P);
+    else rpw_scatter_kernel<false><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, keys, blk_hist, patch_start, sorted, patch_total, patch_order, P);
     return cudaGetLastError();
 }
 

@@ -123,3 +123,26 @@ def test_set_config_changes_sector_count(rpw, h, oracle):
         o = oracle.run(cfg, pts)
         assert np.array_equal(keys, o["keys"])
         assert (got == o["labels"]).mean() >= 0.999
+
+
+def test_pointcloud2_buffer_ingest(rpw, h, oracle):
+    """x, y, z read in place from a PointCloud2-style record buffer
+    (point_step 32, fields at 4 / 12 / 20 like an x-y-z-intensity-ring layout with padding)."""
+    cfg = rpw.PatchworkConfig(filtering_radius=80.0)
+    h.set_config(cfg.to_c())
+    pts = rpw.synth.spinning_scan(1300, 64, 400)
+    n = len(pts)
+    rec = np.zeros((n, 8), np.float32)
+    rec[:, 1] = pts[:, 0]; rec[:, 3] = pts[:, 1]; rec[:, 5] = pts[:, 2]
+    rec[:, 0] = 123.0; rec[:, 2] = np.nan; rec[:, 7] = -1.0   # junk in the other fields must not matter
+    got = h.segment_pc2(rec.tobytes(), n, 32, 4, 12, 20)
+    want = oracle.run(cfg, pts)["labels"]
+    assert np.array_equal(got, want)
+    # wide records with xyz in front through the plain entry point (the bag loader's convention)
+    wide = np.zeros((n, 6), np.float32)
+    wide[:, :3] = pts[:, :3]
+    assert np.array_equal(h.segment(wide), want)
+    with pytest.raises(rpw.RpwError):
+        h.segment_pc2(rec.tobytes(), n, 30, 4, 12, 20)
+    with pytest.raises(rpw.RpwError):
+        h.segment_pc2(rec.tobytes(), n, 32, 4, 12, 30)
