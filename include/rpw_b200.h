@@ -69,11 +69,13 @@ typedef struct rpw_config {
 #define RPW_LABEL_GROUND 1u
 #define RPW_LABEL_BEYOND 2u  /* finite, sqrt(x^2+y^2) > filtering_radius */
 #define RPW_LABEL_DROPPED 3u /* non-finite coordinate (cleanPoints)      */
+#define RPW_LABEL_EGO 4u     /* rpw_segment_fused only: inside the sensor's ego radius, never part of the merged cloud */
 
 /* Per-input-point binning key (debug / parity output). key = ring * num_sectors + sector. */
 #define RPW_KEY_DROPPED 0xFFFFu
 #define RPW_KEY_BEYOND 0xFFFEu
 #define RPW_KEY_UNBINNED 0xFFFDu /* in radius but in no ring/sector (d < 1 m, d == R, angle == 2*pi) */
+#define RPW_KEY_EGO 0xFFFCu      /* rpw_segment_fused only */
 
 #define RPW_NUM_RINGS 8 /* RP/src/recursive_patchwork.cpp:345 */
 
@@ -178,6 +180,22 @@ int rpw_wait(rpw_handle* h, rpw_stats* stats);
  * (n_points * point_step bytes). */
 int rpw_segment_pc2(rpw_handle* h, const void* data, size_t n_points, size_t point_step, size_t off_x, size_t off_y, size_t off_z,
                     uint8_t* labels_out, rpw_stats* stats);
+
+/* One merged multi-LiDAR frame with the fusion front end folded into the binning kernel (SURVEY
+ * section 8f row 1).  Replaces LidarFusion::fuseLidarPointClouds + filterGroundPoints
+ * (RP/src/lidar_fusion.cpp:42-126, RP/src/main.cpp:245-268): every sensor's cloud is rotated about z
+ * by rotation_deg when |rotation_deg| > 1e-6 (same float operations as applyRotation2D, :110-126),
+ * points with sqrt(x^2+y^2) <= ego_radius are removed (:148-159, :184-187; label RPW_LABEL_EGO), the
+ * rest is segmented as ONE cloud in sensor order — no host-side rotate / filter / concatenate passes.
+ * labels_out[s]: sensors[s].n bytes.  Up to 8 sensors. */
+typedef struct rpw_sensor_cloud {
+    const float* xyz;   /* host, stride_bytes records */
+    size_t n;
+    float rotation_deg; /* LidarConfig::rotation_angle, RP/include/recursive_patchwork.hpp:39-44 */
+    float ego_radius;   /* LidarConfig::ego_radius (2.5 default) */
+} rpw_sensor_cloud;
+int rpw_segment_fused(rpw_handle* h, const rpw_sensor_cloud* sensors, size_t n_sensors, size_t stride_bytes,
+                      uint8_t* const* labels_out, rpw_stats* stats);
 
 /* One scan, with the two clouds the reference returns, in the reference's order.
  * ground_xyz / nonground_xyz: caller buffers of 3*n floats each (either may be NULL). */

@@ -11,6 +11,7 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
 // load the resulting library.
 #include "recursive_patchwork.hpp"
+#include "lidar_fusion.hpp"
 
 #include <chrono>
 #include <cstdint>
@@ -152,6 +153,35 @@ int rpwref_filter_ground(const rpwref_config* c, const float* xyz, size_t n, siz
     if (!degenerate && (gi != g.size() || ni != zone_ng_end || ti != ng.size())) return -1;
     if (ambiguous) *ambiguous = amb;
     return 0;
+}
+
+// The reference's multi-LiDAR fusion front end: LidarFusion::fuseLidarPointClouds
+// (RP/include/lidar_fusion.hpp:21-22, RP/src/lidar_fusion.cpp:42-86) with one LidarConfig per sensor.
+// fused_xyz: caller buffer of 3 * (sum of n) floats.  Returns the number of fused points.
+struct rpwref_sensor {
+    const float* xyz;
+    size_t n;
+    float rotation_deg;
+    float ego_radius;
+};
+
+size_t rpwref_fuse(const rpwref_sensor* sensors, size_t n_sensors, size_t stride, float* fused_xyz) {
+    recursive_patchwork::LidarFusion fusion;
+    fusion.clearLidars();
+    std::vector<std::vector<Point3D>> clouds(n_sensors);
+    for (size_t s = 0; s < n_sensors; ++s) {
+        recursive_patchwork::LidarConfig lc{static_cast<int>(s + 1), "", sensors[s].rotation_deg, sensors[s].ego_radius};
+        fusion.addLidar(lc);
+        clouds[s].resize(sensors[s].n);
+        for (size_t i = 0; i < sensors[s].n; ++i) {
+            clouds[s][i].x = sensors[s].xyz[i * stride];
+            clouds[s][i].y = sensors[s].xyz[i * stride + 1];
+            clouds[s][i].z = sensors[s].xyz[i * stride + 2];
+        }
+    }
+    const std::vector<Point3D> fused = fusion.fuseLidarPointClouds(clouds);
+    for (size_t i = 0; i < fused.size(); ++i) { fused_xyz[3 * i] = fused[i].x; fused_xyz[3 * i + 1] = fused[i].y; fused_xyz[3 * i + 2] = fused[i].z; }
+    return fused.size();
 }
 
 // Times `reps` back-to-back calls of filterGroundPoints on one cloud (seconds per call,

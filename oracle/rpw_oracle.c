@@ -663,6 +663,39 @@ int rpwo_filter_ground(const rpwo_config* cfg, const float* xyz, size_t n, size_
     return C.oom ? -1 : 0;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Multi-LiDAR fusion front end: LidarFusion::fuseLidarPointClouds,
+ * RP/src/lidar_fusion.cpp:42-86; processSingleLidar :88-108; applyRotation2D :110-126;
+ * removeEgoVehicle :148-159; isPointInEgoRadius :184-187.
+ * fused_xyz: 3 floats per surviving point, sensor after sensor; src[k]: index of fused point k in the
+ * concatenation of all sensor inputs.  Returns the number of fused points.
+ * ---------------------------------------------------------------------------------------- */
+size_t rpwo_fuse(const rpwo_sensor* sensors, size_t n_sensors, size_t stride, float* fused_xyz, uint32_t* src) {
+    size_t w = 0, base = 0;
+    for (size_t s = 0; s < n_sensors; ++s) {
+        const rpwo_sensor* S = &sensors[s];
+        const int rotate = fabsf(S->rotation_deg) > 1e-6f;                         /* :99 */
+        const float angle_rad = (float)((double)S->rotation_deg * M_PI / (double)180.0f); /* :111 */
+        const float cos_a = cosf(angle_rad), sin_a = sinf(angle_rad);             /* :112-113 */
+        for (size_t i = 0; i < S->n; ++i) {
+            float x = S->xyz[i * stride], y = S->xyz[i * stride + 1];
+            const float z = S->xyz[i * stride + 2];
+            if (rotate) {
+                const float rx = x * cos_a - y * sin_a;                           /* :120 */
+                const float ry = x * sin_a + y * cos_a;                           /* :121 */
+                x = rx; y = ry;
+            }
+            const float d = sqrtf(x * x + y * y);                                 /* :185 */
+            if (d <= S->ego_radius) continue;                                     /* :186, :153 */
+            if (fused_xyz) { fused_xyz[3 * w] = x; fused_xyz[3 * w + 1] = y; fused_xyz[3 * w + 2] = z; }
+            if (src) src[w] = (uint32_t)(base + i);
+            ++w;
+        }
+        base += S->n;
+    }
+    return w;
+}
+
 double rpwo_time_scan(const rpwo_config* cfg, const float* xyz, size_t n, size_t stride, int reps) {
     uint8_t* labels = (uint8_t*)malloc(n ? n : 1);
     struct timespec t0, t1;

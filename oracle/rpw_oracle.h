@@ -101,6 +101,15 @@ int rpwo_eig3_f32(const float a[9], float evals[3], float evecs[9]);
 float rpwo_atan2f_restated(float y, float x);
 uint64_t rpwo_atan2f_selfcheck(uint64_t n, uint64_t seed, float range);
 
+/* Multi-LiDAR fusion front end (RP/src/lidar_fusion.cpp:42-126,148-159,184-187). */
+typedef struct rpwo_sensor {
+    const float* xyz;
+    size_t n;
+    float rotation_deg;
+    float ego_radius;
+} rpwo_sensor;
+size_t rpwo_fuse(const rpwo_sensor* sensors, size_t n_sensors, size_t stride, float* fused_xyz, uint32_t* src);
+
 /* seconds per call over `reps` calls (wall clock); labels only. */
 double rpwo_time_scan(const rpwo_config* cfg, const float* xyz, size_t n, size_t stride, int reps);
 

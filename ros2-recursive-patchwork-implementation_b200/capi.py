@@ -13,8 +13,8 @@ PKG = Path(__file__).resolve().parent
 LIB_PATH = PKG / "librpw_b200.so"
 
 RPW_OK, RPW_ERR_BAD_ARG, RPW_ERR_NO_DEVICE, RPW_ERR_CUDA, RPW_ERR_CAPACITY, RPW_ERR_ALLOC = range(6)
-LABEL_NONGROUND, LABEL_GROUND, LABEL_BEYOND, LABEL_DROPPED = 0, 1, 2, 3
-KEY_DROPPED, KEY_BEYOND, KEY_UNBINNED = 0xFFFF, 0xFFFE, 0xFFFD
+LABEL_NONGROUND, LABEL_GROUND, LABEL_BEYOND, LABEL_DROPPED, LABEL_EGO = 0, 1, 2, 3, 4
+KEY_DROPPED, KEY_BEYOND, KEY_UNBINNED, KEY_EGO = 0xFFFF, 0xFFFE, 0xFFFD, 0xFFFC
 SOLVER_EIGEN_QR, SOLVER_CLOSED_FORM = 0, 1
 NODE_SMALL, NODE_AREA, NODE_FLAT, NODE_FIT, NODE_SPLIT = 1, 2, 3, 4, 5
 
@@ -33,6 +33,10 @@ class RpwStats(C.Structure):
                 ("n_nodes", C.c_uint32), ("kernel_launches", C.c_uint64)]
 
 
+class RpwSensorCloud(C.Structure):
+    _fields_ = [("xyz", C.c_void_p), ("n", C.c_size_t), ("rotation_deg", C.c_float), ("ego_radius", C.c_float)]
+
+
 class RpwProfile(C.Structure):
     _fields_ = [("ms", C.c_double * 4), ("launches", C.c_uint64 * 4), ("fit_grid_blocks", C.c_uint32),
                 ("fit_smem_points", C.c_uint32)]
@@ -48,7 +52,7 @@ NODE_DTYPE = np.dtype([("scan", "<i4"), ("root", "<i4"), ("depth", "<i4"), ("sta
 # Every symbol include/rpw_b200.h declares (tests check that the library exports all of them).
 EXPORTS = ["rpw_default_config", "rpw_zone_model", "rpw_create", "rpw_destroy", "rpw_set_config", "rpw_get_config",
            "rpw_set_plane_solver", "rpw_set_stream", "rpw_last_error", "rpw_segment", "rpw_segment_batch", "rpw_segment_batch_async", "rpw_wait",
-           "rpw_segment_pc2", "rpw_segment_clouds", "rpw_segment_device", "rpw_debug_keys", "rpw_debug_enable_nodes", "rpw_debug_nodes",
+           "rpw_segment_pc2", "rpw_segment_fused", "rpw_segment_clouds", "rpw_segment_device", "rpw_debug_keys", "rpw_debug_enable_nodes", "rpw_debug_nodes",
            "rpw_debug_eig3", "rpw_debug_normal", "rpw_debug_atan2", "rpw_debug_fit_timing", "rpw_profile_enable", "rpw_profile_read", "rpw_host_alloc", "rpw_host_free", "rpw_kernel_launches", "rpw_abi_version"]
 
 _lib = None
@@ -86,6 +90,8 @@ def load_library() -> C.CDLL:
     lib.rpw_segment_batch_async.restype = C.c_int
     lib.rpw_wait.argtypes = [vp, C.POINTER(RpwStats)]; lib.rpw_wait.restype = C.c_int
     lib.rpw_segment_pc2.argtypes = [vp, vp, sz, sz, sz, sz, sz, vp, C.POINTER(RpwStats)]; lib.rpw_segment_pc2.restype = C.c_int
+    lib.rpw_segment_fused.argtypes = [vp, C.POINTER(RpwSensorCloud), sz, sz, C.POINTER(vp), C.POINTER(RpwStats)]
+    lib.rpw_segment_fused.restype = C.c_int
     lib.rpw_segment_clouds.argtypes = [vp, vp, sz, sz, vp, vp, C.POINTER(sz), vp, C.POINTER(sz)]
     lib.rpw_segment_clouds.restype = C.c_int
     lib.rpw_segment_device.argtypes = [vp, vp, C.POINTER(C.c_uint64), sz, vp]; lib.rpw_segment_device.restype = C.c_int
@@ -236,6 +242,21 @@ class Handle:
         labels = np.empty(n_points, np.uint8)
         self._check(self.lib.rpw_segment_pc2(self._h, buf.ctypes.data, n_points, point_step, off_x, off_y, off_z, labels.ctypes.data, None))
         return labels
+
+    def segment_fused(self, clouds, rotations_deg, ego_radii, want_stats=False):
+        """One merged multi-LiDAR frame: per-sensor clouds, yaw angles (degrees) and ego radii."""
+        arrs = [self._as_points(c) for c in clouds]
+        stride = arrs[0].shape[1]
+        k = len(arrs)
+        sens = (RpwSensorCloud * k)()
+        labels = [np.empty(len(a), np.uint8) for a in arrs]
+        for i, a in enumerate(arrs):
+            sens[i].xyz = a.ctypes.data; sens[i].n = len(a)
+            sens[i].rotation_deg = float(rotations_deg[i]); sens[i].ego_radius = float(ego_radii[i])
+        lp = (C.c_void_p * k)(*[l.ctypes.data for l in labels])
+        st = RpwStats()
+        self._check(self.lib.rpw_segment_fused(self._h, sens, k, stride * 4, lp, C.byref(st)))
+        return (labels, st) if want_stats else labels
 
     def segment_clouds(self, points):
         a = self._as_points(points)

@@ -66,6 +66,9 @@ struct rpw_handle {
     float* d_root_mean = nullptr;
     uint64_t* d_scan_off = nullptr;
     uint32_t* d_chunk_base = nullptr;
+    FusionTable* d_fusion = nullptr;    // device copy of the sensor table of a fused frame
+    const FusionTable* fusion_arg = nullptr;  // non-null while a fused frame is being enqueued
+    FusionTable* h_fusion = nullptr;    // pinned
     rpw_node* d_dbg_nodes = nullptr;
     unsigned long long* d_timing = nullptr;  // [16], allocated by rpw_debug_fit_timing
     bool timing_enabled = false;
@@ -208,7 +211,8 @@ void rpw_destroy(rpw_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_in); cudaFree(h->d_keys); cudaFree(h->d_labels); cudaFree(h->d_sortedA); cudaFree(h->d_bufB);
     cudaFree(h->d_bufC); cudaFree(h->d_gmask); cudaFree(h->d_dbg_count);
-    cudaFree(h->d_scan_off); cudaFree(h->d_chunk_base); cudaFree(h->d_dbg_nodes); cudaFree(h->d_timing);
+    cudaFree(h->d_scan_off); cudaFree(h->d_chunk_base); cudaFree(h->d_dbg_nodes); cudaFree(h->d_timing); cudaFree(h->d_fusion);
+    if (h->h_fusion) cudaFreeHost(h->h_fusion);
     free_patch_buffers(h);
     if (h->h_meta) cudaFreeHost(h->h_meta);
     if (h->h_stage_in) cudaFreeHost(h->h_stage_in);
@@ -295,6 +299,8 @@ int rpw_create(const rpw_config* cfg, int device, size_t max_total_points, size_
     TRYC(cudaMalloc(&h->d_scan_off, (max_batch + 1) * sizeof(uint64_t)));
     TRYC(cudaMalloc(&h->d_chunk_base, (max_batch + 1) * sizeof(uint32_t)));
     TRYC(cudaMallocHost(&h->h_meta, (max_batch + 1) * (sizeof(uint64_t) + sizeof(uint32_t)) + 64));
+    TRYC(cudaMalloc(&h->d_fusion, sizeof(FusionTable)));
+    TRYC(cudaMallocHost(&h->h_fusion, sizeof(FusionTable)));
     TRYC(cudaMallocHost(&h->h_stats, 16 * rpw_handle::kLanes * sizeof(uint32_t)));
     TRY(alloc_patch_buffers(h));
     TRY(alloc_level_buffers(h));
@@ -454,12 +460,12 @@ static int run_group(rpw_handle* h, rpw_handle::Lane& L, cudaStream_t st, const 
     const uint32_t* d_cb = h->d_chunk_base + b0;
     uint32_t* d_ps = h->d_patch_start + b0 * (size_t)(h->P + 1);
     { ProfScope ps(h, 0);
-      RPW_CUDA(h, launch_bin(st, lay, d_pts, d_so, d_cb, h->zm, h->d_keys, d_labels, h->d_blk_hist, L.d_patch_total, max_chunks, (int)nb)); }
+      RPW_CUDA(h, launch_bin(st, lay, d_pts, d_so, d_cb, h->zm, h->d_keys, d_labels, h->d_blk_hist, L.d_patch_total, h->fusion_arg, max_chunks, (int)nb)); }
     { ProfScope ps(h, 1);
       RPW_CUDA(h, launch_offsets(st, d_so, d_cb, h->d_blk_hist, d_ps, L.d_patch_total, h->P, (int)nb)); }
     { ProfScope ps(h, 2);
       RPW_CUDA(h, launch_scatter(st, lay, d_pts, d_so, d_cb, h->d_keys, h->d_blk_hist, d_ps, h->d_sortedA, L.d_patch_total,
-                                 L.d_patch_order, h->P, max_chunks, (int)nb)); }
+                                 L.d_patch_order, h->P, h->fusion_arg, max_chunks, (int)nb)); }
     FitArgs A;
     A.sortedA = h->d_sortedA; A.bufB = h->d_bufB; A.bufC = h->d_bufC; A.gmask = h->d_gmask;
     A.labels = d_labels;
@@ -589,7 +595,7 @@ static int fill_stats(rpw_handle* h, rpw_stats* st, uint8_t* const* labels, cons
     uint64_t cnt[4] = {0, 0, 0, 0};
     for (size_t b = 0; b < batch; ++b) {
         const uint8_t* l = labels[b];
-        for (size_t i = 0; i < n[b]; ++i) cnt[l[i] & 3]++;
+        for (size_t i = 0; i < n[b]; ++i) cnt[l[i] & 3]++;  // (label 4, ego, only occurs in fused frames; rpw_segment_fused recounts)
         st->n_points += n[b];
     }
     st->n_nonground = cnt[0]; st->n_ground = cnt[1]; st->n_beyond = cnt[2]; st->n_dropped = cnt[3];
@@ -730,6 +736,81 @@ int rpw_segment_pc2(rpw_handle* h, const void* data, size_t n_points, size_t poi
     const int rc = rpw_segment(h, reinterpret_cast<const float*>(data), n_points, point_step, labels_out, stats);
     h->field_off[0] = 0; h->field_off[1] = 4; h->field_off[2] = 8;
     return rc;
+}
+
+int rpw_segment_fused(rpw_handle* h, const rpw_sensor_cloud* sensors, size_t n_sensors, size_t stride_bytes,
+                      uint8_t* const* labels_out, rpw_stats* stats) {
+    if (!h) return RPW_ERR_BAD_ARG;
+    if (!sensors || !labels_out || n_sensors == 0 || n_sensors > (size_t)kMaxSensors)
+        RPW_FAIL(h, RPW_ERR_BAD_ARG, "need 1..%d sensors", kMaxSensors);
+    if (!stride_ok(stride_bytes)) RPW_FAIL(h, RPW_ERR_BAD_ARG, "stride_bytes must be a multiple of 4 in [12, 1024], got %zu", stride_bytes);
+    RPW_CUDA(h, cudaSetDevice(h->device));
+    size_t total = 0;
+    for (size_t s = 0; s < n_sensors; ++s) {
+        if (sensors[s].n && (!sensors[s].xyz || !labels_out[s])) RPW_FAIL(h, RPW_ERR_BAD_ARG, "sensor %zu has a NULL buffer", s);
+        total += sensors[s].n;
+    }
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (total == 0) return RPW_OK;
+    if (total > h->cap_points) RPW_FAIL(h, RPW_ERR_CAPACITY, "%zu points exceed the handle's capacity %zu", total, h->cap_points);
+    int rc = ensure_stage(h, total * stride_bytes);
+    if (rc != RPW_OK) return rc;
+    rc = ensure_d_in(h, total * stride_bytes);
+    if (rc != RPW_OK) return rc;
+    RPW_CUDA(h, cudaStreamSynchronize(h->stream));  // staging buffers and the sensor table are reused
+    // sensor table: angle in radians and its cosine / sine exactly as LidarFusion::applyRotation2D
+    // computes them on the host (lidar_fusion.cpp:111-113): float(deg * M_PI / 180.0f), cosf, sinf
+    FusionTable& ft = *h->h_fusion;
+    memset(&ft, 0, sizeof(ft));
+    ft.n = (int)n_sensors;
+    size_t o = 0;
+    char* stage = reinterpret_cast<char*>(h->h_stage_in);
+    for (size_t s = 0; s < n_sensors; ++s) {
+        ft.start[s] = (uint32_t)o;
+        const float deg = sensors[s].rotation_deg;
+        const float rad = (float)((double)deg * 3.14159265358979323846 / (double)180.0f);
+        ft.cos_a[s] = cosf(rad);
+        ft.sin_a[s] = sinf(rad);
+        ft.rotate[s] = fabsf(deg) > 1e-6f ? 1 : 0;
+        ft.ego[s] = sensors[s].ego_radius;
+        if (sensors[s].n) memcpy(stage + o * stride_bytes, sensors[s].xyz, sensors[s].n * stride_bytes);
+        o += sensors[s].n;
+    }
+    for (size_t s = n_sensors; s <= (size_t)kMaxSensors; ++s) ft.start[s] = (uint32_t)total;
+    RPW_CUDA(h, cudaMemcpyAsync(h->d_fusion, &ft, sizeof(ft), cudaMemcpyHostToDevice, h->stream));
+    const uint64_t off[2] = {0, (uint64_t)total};
+    rc = upload_meta(h, off, 1);
+    if (rc != RPW_OK) return rc;
+    rc = reset_dbg(h);
+    if (rc != RPW_OK) return rc;
+    RPW_CUDA(h, cudaMemcpyAsync(h->d_in, stage, total * stride_bytes, cudaMemcpyHostToDevice, h->stream));
+    PointLayout lay;
+    lay.stride = (int)(stride_bytes / 4); lay.ox = 0; lay.oy = 1; lay.oz = 2;
+    lay.vec4 = stride_bytes == 16 ? 1 : 0;
+    h->fusion_arg = h->d_fusion;
+    rc = run_pipeline(h, h->d_in, lay, h->d_labels, 1);
+    h->fusion_arg = nullptr;
+    if (rc != RPW_OK) return rc;
+    RPW_CUDA(h, cudaMemcpyAsync(h->h_stage_labels, h->d_labels, total, cudaMemcpyDeviceToHost, h->stream));
+    RPW_CUDA(h, cudaStreamSynchronize(h->stream));
+    o = 0;
+    for (size_t s = 0; s < n_sensors; ++s) {
+        if (sensors[s].n) memcpy(labels_out[s], h->h_stage_labels + o, sensors[s].n);
+        o += sensors[s].n;
+    }
+    h->pend_labels.clear();
+    if (stats) {
+        uint8_t* one[1] = {h->h_stage_labels};
+        const size_t nn[1] = {total};
+        rc = fill_stats(h, stats, one, nn, 1);
+        if (rc != RPW_OK) return rc;
+        // label 4 (ego) was folded into "dropped" by the 2-bit histogram; count it properly
+        uint64_t ego = 0, dropped = 0;
+        for (size_t i = 0; i < total; ++i) { ego += h->h_stage_labels[i] == RPW_LABEL_EGO; dropped += h->h_stage_labels[i] == RPW_LABEL_DROPPED; }
+        stats->n_dropped = dropped;
+        stats->n_nonground = total - stats->n_ground - stats->n_beyond - dropped - ego;
+    }
+    return RPW_OK;
 }
 
 int rpw_segment_clouds(rpw_handle* h, const float* xyz, size_t n, size_t stride_bytes, uint8_t* labels_out,

@@ -43,7 +43,8 @@ template <bool VEC4>
 __global__ void __launch_bounds__(kBinThreads) rpw_bin_kernel(const float* __restrict__ pts, PointLayout lay, const uint64_t* __restrict__ scan_off,
                                                              const uint32_t* __restrict__ chunk_base, ZoneModel zm,
                                                              uint16_t* __restrict__ keys, uint8_t* __restrict__ labels,
-                                                             uint32_t* __restrict__ blk_hist, uint32_t* __restrict__ patch_total) {
+                                                             uint32_t* __restrict__ blk_hist, uint32_t* __restrict__ patch_total,
+                                                             const FusionTable* __restrict__ fusion) {
     extern __shared__ uint32_t s_hist[];
     const int b = blockIdx.y, chunk = blockIdx.x;
     // batch-wide points-per-patch totals (scheduling order of the fit kernel) start from zero;
@@ -66,13 +67,14 @@ __global__ void __launch_bounds__(kBinThreads) rpw_bin_kernel(const float* __res
         if (valid) {
             float x, y, z;
             load_xyz<VEC4>(pts, off + i, lay, x, y, z);
-            key = bin_key(x, y, z, zm);
+            const bool ego = fusion != nullptr && fuse_point(*fusion, i, x, y);
+            key = ego ? kKeyEgo : bin_key(x, y, z, zm);
             keys[off + i] = key;
             // points that never enter a patch get their final label here; patch points are
             // labelled by the fit kernel when their leaf finishes.
-            if (key >= kKeyUnbinned) labels[off + i] = key == kKeyDropped ? 3 : (key == kKeyBeyond ? 2 : 0);
+            if (key >= kKeySpecialMin) labels[off + i] = key == kKeyDropped ? 3 : (key == kKeyBeyond ? 2 : (key == kKeyEgo ? 4 : 0));
         }
-        const uint32_t kk = (valid && key < kKeyUnbinned) ? key : 0xFFFFFFFFu;
+        const uint32_t kk = (valid && key < kKeySpecialMin) ? key : 0xFFFFFFFFu;
         const unsigned peers = __match_any_sync(0xffffffffu, kk);
         if (kk != 0xFFFFFFFFu && lane == __ffs(peers) - 1) atomicAdd(&s_hist[kk], __popc(peers));
     }
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(kBinThreads) rpw_scatter_kernel(const float* _
                                                                  const uint16_t* __restrict__ keys, const uint32_t* __restrict__ blk_hist,
                                                                  const uint32_t* __restrict__ patch_start, float4* __restrict__ sorted,
                                                                  const uint32_t* __restrict__ patch_total, uint32_t* __restrict__ patch_order,
-                                                                 int P) {
+                                                                 int P, const FusionTable* __restrict__ fusion) {
     extern __shared__ uint32_t s_off[];  // [warps][P]
     constexpr int kWarps = kBinThreads / 32;
     constexpr int kPerWarp = kBinChunk / kWarps;
@@ -176,7 +178,7 @@ __global__ void __launch_bounds__(kBinThreads) rpw_scatter_kernel(const float* _
     for (int r = 0; r < kPerWarp / 32; ++r) {
         const uint32_t i = wbase + r * 32 + lane;
         uint32_t kk = 0xFFFFFFFFu;
-        if (i < n) { const uint16_t key = keys[off + i]; if (key < kKeyUnbinned) kk = key; }
+        if (i < n) { const uint16_t key = keys[off + i]; if (key < kKeySpecialMin) kk = key; }
         const unsigned peers = __match_any_sync(0xffffffffu, kk);
         if (kk != 0xFFFFFFFFu && lane == __ffs(peers) - 1) my[kk] += __popc(peers);
         __syncwarp();
@@ -199,13 +201,14 @@ __global__ void __launch_bounds__(kBinThreads) rpw_scatter_kernel(const float* _
     for (int r = 0; r < kPerWarp / 32; ++r) {
         const uint32_t i = wbase + r * 32 + lane;
         uint32_t kk = 0xFFFFFFFFu;
-        if (i < n) { const uint16_t key = keys[off + i]; if (key < kKeyUnbinned) kk = key; }
+        if (i < n) { const uint16_t key = keys[off + i]; if (key < kKeySpecialMin) kk = key; }
         const unsigned peers = __match_any_sync(0xffffffffu, kk);
         if (kk != 0xFFFFFFFFu) {
             const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
             const uint32_t pos = my[kk] + rank;
             float x, y, z;
             load_xyz<VEC4>(pts, off + i, lay, x, y, z);
+            if (fusion != nullptr) fuse_point(*fusion, i, x, y);  // the patches hold vehicle-frame coordinates
             sorted[pos] = make_float4(x, y, z, __uint_as_float((uint32_t)(off + i)));
         }
         __syncwarp();
@@ -969,11 +972,11 @@ size_t fit_smem_bytes(int smem_cap, int threads) {
 
 cudaError_t launch_bin(cudaStream_t st, const PointLayout& lay, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
                        const ZoneModel& zm, uint16_t* keys, uint8_t* labels, uint32_t* blk_hist, uint32_t* patch_total,
-                       int max_chunks, int batch) {
+                       const FusionTable* fusion, int max_chunks, int batch) {
     dim3 grid(max_chunks, batch);
     const size_t smem = (size_t)zm.num_patches * 4;
-    if (lay.vec4) rpw_bin_kernel<true><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, zm, keys, labels, blk_hist, patch_total);
-    else rpw_bin_kernel<false><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, zm, keys, labels, blk_hist, patch_total);
+    if (lay.vec4) rpw_bin_kernel<true><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, zm, keys, labels, blk_hist, patch_total, fusion);
+    else rpw_bin_kernel<false><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, zm, keys, labels, blk_hist, patch_total, fusion);
     return cudaGetLastError();
 }
 
@@ -985,11 +988,11 @@ cudaError_t launch_offsets(cudaStream_t st, const uint64_t* scan_off, const uint
 
 cudaError_t launch_scatter(cudaStream_t st, const PointLayout& lay, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
                            const uint16_t* keys, const uint32_t* blk_hist, const uint32_t* patch_start, float4* sorted,
-                           const uint32_t* patch_total, uint32_t* patch_order, int P, int max_chunks, int batch) {
+                           const uint32_t* patch_total, uint32_t* patch_order, int P, const FusionTable* fusion, int max_chunks, int batch) {
     dim3 grid(max_chunks, batch);
     const size_t smem = (size_t)(kBinThreads / 32) * P * 4;
-    if (lay.vec4) rpw_scatter_kernel<true><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, keys, blk_hist, patch_start, sorted, patch_total, patch_order, P);
-    else rpw_scatter_kernel<false><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, keys, blk_hist, patch_start, sorted, patch_total, patch_order, P);
+    if (lay.vec4) rpw_scatter_kernel<true><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, keys, blk_hist, patch_start, sorted, patch_total, patch_order, P, fusion);
+    else rpw_scatter_kernel<false><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, keys, blk_hist, patch_start, sorted, patch_total, patch_order, P, fusion);
     return cudaGetLastError();
 }
 

@@ -49,12 +49,12 @@ cudaError_t fit_configure(int smem_cap, int* blocks_per_sm);
 
 cudaError_t launch_bin(cudaStream_t st, const PointLayout& lay, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
                        const ZoneModel& zm, uint16_t* keys, uint8_t* labels, uint32_t* blk_hist, uint32_t* patch_total,
-                       int max_chunks, int batch);
+                       const FusionTable* fusion, int max_chunks, int batch);
 cudaError_t launch_offsets(cudaStream_t st, const uint64_t* scan_off, const uint32_t* chunk_base, uint32_t* blk_hist,
                            uint32_t* patch_start, uint32_t* patch_total, int P, int batch);
 cudaError_t launch_scatter(cudaStream_t st, const PointLayout& lay, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
                            const uint16_t* keys, const uint32_t* blk_hist, const uint32_t* patch_start, float4* sorted,
-                           const uint32_t* patch_total, uint32_t* patch_order, int P, int max_chunks, int batch);
+                           const uint32_t* patch_total, uint32_t* patch_order, int P, const FusionTable* fusion, int max_chunks, int batch);
 cudaError_t launch_fit_roots(cudaStream_t st, const FitArgs& args, int size_class);
 cudaError_t launch_fit_levels(cudaStream_t st, const FitArgs& args, int grid_blocks);
 cudaError_t launch_eig3(cudaStream_t st, const float* mats, size_t count, float* evals, float* evecs);

@@ -111,6 +111,53 @@ public:
         return out;
     }
 
+    // Multi-LiDAR frame with the fusion front end on the device (what main.cpp:245-268 does with
+    // LidarFusion::fuseLidarPointClouds followed by filterGroundPoints): clouds[i] is sensor i's cloud in
+    // its own frame, configs[i] its LidarConfig (rotation_angle in degrees, ego_radius).  Returns the
+    // ground / non-ground clouds of the MERGED frame in vehicle coordinates, in the reference's order;
+    // labels (optional) receives one vector per sensor (RPW_LABEL_*; RPW_LABEL_EGO = removed).
+    std::pair<std::vector<Point3D>, std::vector<Point3D>> filterGroundPointsFused(
+        const std::vector<std::vector<Point3D>>& clouds, const std::vector<LidarConfig>& configs,
+        std::vector<std::vector<std::uint8_t>>* labels = nullptr) {
+        std::pair<std::vector<Point3D>, std::vector<Point3D>> out;
+        const std::size_t k = std::min(clouds.size(), configs.size());
+        std::vector<std::vector<std::uint8_t>> local(k);
+        std::vector<rpw_sensor_cloud> sens(k);
+        std::vector<std::uint8_t*> lp(k);
+        std::size_t total = 0;
+        for (std::size_t i = 0; i < k; ++i) {
+            local[i].assign(clouds[i].size(), RPW_LABEL_DROPPED);
+            sens[i].xyz = clouds[i].empty() ? nullptr : &clouds[i][0].x;
+            sens[i].n = clouds[i].size();
+            sens[i].rotation_deg = configs[i].rotation_angle;
+            sens[i].ego_radius = configs[i].ego_radius;
+            lp[i] = local[i].data();
+            total += clouds[i].size();
+        }
+        if (total) {
+            ensure(total);
+            check(rpw_segment_fused(handle_, sens.data(), k, sizeof(Point3D), lp.data(), nullptr));
+        }
+        // vehicle-frame coordinates with the operations LidarFusion::applyRotation2D uses
+        auto emit = [&](std::uint8_t want, std::vector<Point3D>& dst) {
+            for (std::size_t i = 0; i < k; ++i) {
+                const bool rot = std::abs(configs[i].rotation_angle) > 1e-6f;
+                const float a = configs[i].rotation_angle * M_PI / 180.0f;
+                const float c = std::cos(a), s = std::sin(a);
+                for (std::size_t j = 0; j < clouds[i].size(); ++j) {
+                    if (local[i][j] != want) continue;
+                    const Point3D& p = clouds[i][j];
+                    dst.push_back(rot ? Point3D(p.x * c - p.y * s, p.x * s + p.y * c, p.z) : p);
+                }
+            }
+        };
+        emit(RPW_LABEL_GROUND, out.first);
+        emit(RPW_LABEL_NONGROUND, out.second);
+        emit(RPW_LABEL_BEYOND, out.second);
+        if (labels) *labels = std::move(local);
+        return out;
+    }
+
     // Labels only (no cloud assembly): the cheapest call for a caller that indexes its own data.
     std::vector<std::uint8_t> segmentLabels(const std::vector<Point3D>& points) {
         std::vector<std::uint8_t> labels(points.size());

@@ -82,6 +82,18 @@ int main(int argc, char** argv) {
         auto again = patchwork.filterGroundPoints(points);
         REQUIRE(again.first.size() + again.second.size() == points.size());
     }
+    {   // fused multi-LiDAR frame: three sensors, default 0 / +120 / -120 degree yaws, ego radius 2.5
+        std::vector<std::vector<Point3D>> clouds = {synthetic_cloud(4000, 7), synthetic_cloud(3000, 8), synthetic_cloud(3000, 9)};
+        std::vector<LidarConfig> cfgs = {{1, "/lidar_front", 0.0f, 2.5f}, {2, "/lidar_left", 120.0f, 2.5f}, {3, "/lidar_right", -120.0f, 2.5f}};
+        RecursivePatchwork patchwork{PatchworkConfig{}};
+        std::vector<std::vector<std::uint8_t>> labels;
+        auto fused = patchwork.filterGroundPointsFused(clouds, cfgs, &labels);
+        size_t ego = 0, total = 0;
+        for (auto& l : labels) { total += l.size(); for (auto v : l) ego += v == RPW_LABEL_EGO; }
+        REQUIRE(total == 10000 && fused.first.size() > 0 && fused.second.size() > 0);
+        REQUIRE(fused.first.size() + fused.second.size() + ego == total);
+        std::printf("fused: ground=%zu non_ground=%zu ego_removed=%zu\n", fused.first.size(), fused.second.size(), ego);
+    }
     if (argc >= 3) {  // exact clouds from a cloud file + expected labels (written by the python test from the oracle)
         std::ifstream fc(argv[1], std::ios::binary), fl(argv[2], std::ios::binary);
         std::vector<char> cb((std::istreambuf_iterator<char>(fc)), std::istreambuf_iterator<char>());

@@ -29,6 +29,19 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class Sensor(C.Structure):
+    _fields_ = [("xyz", C.c_void_p), ("n", C.c_size_t), ("rotation_deg", C.c_float), ("ego_radius", C.c_float)]
+
+
+def _sensor_array(clouds, rotations_deg, ego_radii):
+    arrs = [_pts(c) for c in clouds]
+    sens = (Sensor * len(arrs))()
+    for i, a in enumerate(arrs):
+        sens[i].xyz = a.ctypes.data; sens[i].n = len(a)
+        sens[i].rotation_deg = float(rotations_deg[i]); sens[i].ego_radius = float(ego_radii[i])
+    return arrs, sens
+
+
 NODE_DTYPE = np.dtype([("root", "<i4"), ("depth", "<i4"), ("start", "<i4"), ("n", "<i4"), ("outcome", "<i4"),
                        ("iters", "<i4"), ("n_inliers", "<i4"), ("split_axis", "<i4"), ("centroid", "<f4", 3),
                        ("normal", "<f4", 3), ("residual", "<f4"), ("median", "<f4")])
@@ -118,6 +131,16 @@ class Oracle:
         f = np.frompyfunc(lambda a, b: self.lib.rpwo_atan2f_restated(float(a), float(b)), 2, 1)
         return f(np.asarray(y, np.float32), np.asarray(x, np.float32)).astype(np.float32)
 
+    def fuse(self, clouds, rotations_deg, ego_radii):
+        """Fusion front end restated: returns (fused (k,3) float32, src indices into the concatenated input)."""
+        arrs, sens = _sensor_array(clouds, rotations_deg, ego_radii)
+        total = sum(len(a) for a in arrs)
+        fused = np.zeros((max(total, 1), 3), np.float32)
+        src = np.zeros(max(total, 1), np.uint32)
+        self.lib.rpwo_fuse.restype = C.c_size_t
+        k = self.lib.rpwo_fuse(sens, C.c_size_t(len(arrs)), C.c_size_t(arrs[0].shape[1]), C.c_void_p(fused.ctypes.data), C.c_void_p(src.ctypes.data))
+        return fused[:k], src[:k]
+
     def time_scan(self, cfg, points, reps=1) -> float:
         cfg = cfg if isinstance(cfg, Cfg) else to_cfg(cfg)
         a = _pts(points)
@@ -151,6 +174,14 @@ class Reference:
         if rc != 0:
             raise RuntimeError("reference label reconstruction failed")
         return dict(ground=g[:n_g.value], non_ground=ng[:n_ng.value], labels=lab, ambiguous=amb.value)
+
+    def fuse(self, clouds, rotations_deg, ego_radii):
+        arrs, sens = _sensor_array(clouds, rotations_deg, ego_radii)
+        total = sum(len(a) for a in arrs)
+        fused = np.zeros((max(total, 1), 3), np.float32)
+        self.lib.rpwref_fuse.restype = C.c_size_t
+        k = self.lib.rpwref_fuse(sens, C.c_size_t(len(arrs)), C.c_size_t(arrs[0].shape[1]), C.c_void_p(fused.ctypes.data))
+        return fused[:k]
 
     def time_scan(self, cfg, points, reps=1) -> float:
         cfg = cfg if isinstance(cfg, Cfg) else to_cfg(cfg)

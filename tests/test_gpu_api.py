@@ -146,3 +146,26 @@ def test_pointcloud2_buffer_ingest(rpw, h, oracle):
         h.segment_pc2(rec.tobytes(), n, 30, 4, 12, 20)
     with pytest.raises(rpw.RpwError):
         h.segment_pc2(rec.tobytes(), n, 32, 4, 12, 30)
+
+
+def test_fused_multi_lidar_frame(rpw, h, oracle):
+    """rotation + ego removal + concatenation folded into the binning kernel.
+    Expected labels: oracle fusion -> oracle segmentation of the merged cloud, mapped back to the
+    sensors' own points; ego-removed points carry label 4."""
+    from test_oracle import sensor_frames
+    clouds, yaws, ego = sensor_frames(rpw, seed=9)
+    cfg = rpw.PatchworkConfig()
+    h.set_config(cfg.to_c())
+    labels, st = h.segment_fused(clouds, yaws, ego, want_stats=True)
+    fused, src = oracle.fuse(clouds, yaws, ego)
+    want = np.full(sum(map(len, clouds)), 4, np.uint8)
+    want[src] = oracle.run(cfg, fused)["labels"]
+    got = np.concatenate(labels)
+    assert np.array_equal(got == 4, want == 4), "ego removal differs"
+    assert np.array_equal(np.isin(got, (2, 3)), np.isin(want, (2, 3)))
+    assert (got == want).mean() >= 0.999
+    assert st.n_points == len(want) and st.n_ground == int((got == 1).sum())
+    # one sensor, no rotation, zero ego radius == the plain entry point
+    plain = h.segment(clouds[0])
+    one = h.segment_fused(clouds[:1], [0.0], [-1.0])[0]
+    assert np.array_equal(plain, one)

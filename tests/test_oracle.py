@@ -124,3 +124,39 @@ def test_zone_model_matches_host_library(rpw, oracle):
         import oracle_lib
         e2, a2 = oracle.zone_model(oracle_lib.to_cfg(cfg))
         assert np.array_equal(e1.view(np.uint32), e2.view(np.uint32)) and np.float32(a1) == np.float32(a2)
+
+
+def sensor_frames(rpw, seed=5):
+    """Three solid-state sensors in their OWN frames (so the fusion has something to rotate), a few
+    returns near the car so the ego filter bites, one NaN per sensor."""
+    merged = rpw.synth.solidstate_merged(2100 + seed, 150, 100)[:, :3]
+    rng = np.random.default_rng(seed)
+    parts = np.array_split(merged, 3)
+    yaws = [0.0, 120.0, -120.0]
+    out = []
+    for p, yaw in zip(parts, yaws):
+        a = np.deg2rad(-yaw)
+        q = p.copy()
+        q[:, 0] = (p[:, 0] * np.cos(a) - p[:, 1] * np.sin(a)).astype(np.float32)
+        q[:, 1] = (p[:, 0] * np.sin(a) + p[:, 1] * np.cos(a)).astype(np.float32)
+        near = rng.uniform(-2.4, 2.4, (40, 3)).astype(np.float32)
+        q = np.concatenate([q[: len(q) // 2], near, q[len(q) // 2:]])
+        q[7, 2] = np.nan
+        out.append(np.ascontiguousarray(q, np.float32))
+    return out, yaws, [2.5, 2.5, 2.5]
+
+
+def test_fusion_restatement_is_the_reference(rpw, oracle, ref):
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    clouds, yaws, ego = sensor_frames(rpw)
+    fused_ref = ref.fuse(clouds, yaws, ego)
+    fused, src = oracle.fuse(clouds, yaws, ego)
+    assert fused.shape == fused_ref.shape
+    assert np.array_equal(fused.view(np.uint32), fused_ref.view(np.uint32))
+    assert len(fused) < sum(map(len, clouds)) and np.all(np.diff(src.astype(np.int64)) > 0)
+    # a zero angle must not rotate at all, an angle just above the 1e-6 threshold must
+    f0, _ = oracle.fuse(clouds[:1], [0.0], [0.0])
+    f1 = ref.fuse(clouds[:1], [2e-6], [0.0])
+    f2, _ = oracle.fuse(clouds[:1], [2e-6], [0.0])
+    assert np.array_equal(f1.view(np.uint32), f2.view(np.uint32)) and len(f0) == len(f2)
