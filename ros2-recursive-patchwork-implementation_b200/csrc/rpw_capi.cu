@@ -30,8 +30,8 @@ struct rpw_handle {
     // big per-point buffers are shared (groups touch disjoint index ranges).
     struct Lane {
         cudaStream_t main = nullptr;                          // K1, K1b, K2, K3b
-        cudaStream_t side[3] = {nullptr, nullptr, nullptr};   // K3a size classes run concurrently
-        cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr}, ev_start = nullptr, ev_done = nullptr;
+        cudaStream_t side[kNumFitClasses] = {};   // K3a size classes run concurrently
+        cudaEvent_t ev_fork = nullptr, ev_join[kNumFitClasses] = {}, ev_start = nullptr, ev_done = nullptr;
         NodeRef* d_queue[2] = {nullptr, nullptr};
         uint32_t* d_counters = nullptr;     // fetch_ctr[levels_cap] | q_count[levels_cap] | stats[8] | overflow
         uint32_t* d_patch_total = nullptr;  // [P] points per patch over the launch group
@@ -221,7 +221,7 @@ void rpw_destroy(rpw_handle* h) {
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     for (auto& L : h->lane) {
         cudaFree(L.d_queue[0]); cudaFree(L.d_queue[1]); cudaFree(L.d_counters);
-        for (int k = 0; k < 3; ++k) { if (L.side[k]) cudaStreamDestroy(L.side[k]); if (L.ev_join[k]) cudaEventDestroy(L.ev_join[k]); }
+        for (int k = 0; k < kNumFitClasses; ++k) { if (L.side[k]) cudaStreamDestroy(L.side[k]); if (L.ev_join[k]) cudaEventDestroy(L.ev_join[k]); }
         if (L.ev_fork) cudaEventDestroy(L.ev_fork);
         if (L.ev_start) cudaEventDestroy(L.ev_start);
         if (L.ev_done) cudaEventDestroy(L.ev_done);
@@ -271,7 +271,7 @@ int rpw_create(const rpw_config* cfg, int device, size_t max_total_points, size_
     h->stream = h->own_stream;
     for (auto& L : h->lane) {
         TRYC(cudaStreamCreateWithFlags(&L.main, cudaStreamNonBlocking));
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < kNumFitClasses; ++k) {
             TRYC(cudaStreamCreateWithFlags(&L.side[k], cudaStreamNonBlocking));
             TRYC(cudaEventCreateWithFlags(&L.ev_join[k], cudaEventDisableTiming));
         }
@@ -490,21 +490,22 @@ static int run_group(rpw_handle* h, rpw_handle::Lane& L, cudaStream_t st, const 
     A.fp = h->fp;
     {
         ProfScope ps(h, 3);
-        // level 0: three size classes on side streams (largest first), joined back before the
+        // level 0: the size classes on side streams (largest first), joined back before the
         // persistent kernel that walks the deeper levels
         static const char* dbg_mask = getenv("RPW_DBG_CLASS_MASK");  // profiling aid: bit k = run size class k only
-        const int mask = dbg_mask ? atoi(dbg_mask) : 7;
+        const int mask = dbg_mask ? atoi(dbg_mask) : (1 << kNumFitClasses) - 1;
         RPW_CUDA(h, cudaEventRecord(L.ev_fork, st));
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < kNumFitClasses; ++k) {
+            const int cls = kNumFitClasses - 1 - k;
             RPW_CUDA(h, cudaStreamWaitEvent(L.side[k], L.ev_fork, 0));
-            if (mask & (1 << (2 - k))) RPW_CUDA(h, launch_fit_roots(L.side[k], A, 2 - k));
+            if (mask & (1 << cls)) RPW_CUDA(h, launch_fit_roots(L.side[k], A, cls));
             RPW_CUDA(h, cudaEventRecord(L.ev_join[k], L.side[k]));
         }
-        for (int k = 0; k < 3; ++k) RPW_CUDA(h, cudaStreamWaitEvent(st, L.ev_join[k], 0));
+        for (int k = 0; k < kNumFitClasses; ++k) RPW_CUDA(h, cudaStreamWaitEvent(st, L.ev_join[k], 0));
         RPW_CUDA(h, launch_fit_levels(st, A, h->fit_blocks));
     }
-    h->launches += 7;
-    h->launches_call += 7;
+    h->launches += 4 + kNumFitClasses;
+    h->launches_call += 4 + kNumFitClasses;
     return RPW_OK;
 }
 

@@ -815,10 +815,11 @@ __device__ __forceinline__ FitSmem carve_smem(unsigned char* raw, int cap, int w
 // K3a: level 0 — the ring/sector patches themselves, one block per patch, no grid-wide barrier.
 // Patches come in very different sizes (a few points near the sensor, >10k in the far rings), so
 // the launch is split into size classes, each with its own block size and shared-memory carve-out:
-//   TT = 64,   <= 1024 points  (~15 KB)  : many resident blocks, their eigensolves overlap
-//   TT = 128,  <= 4096 points  (~55 KB)
-//   TT = 512,  everything larger: <= 8192 points shared-memory resident (~108 KB), beyond that
-//              streamed from L2; the far-ring patches that iterate longest get the most threads
+//   64 threads: <= 1024 points (15 KB) and <= 2048 (28 KB) : many resident blocks, their eigensolves overlap
+//   128 threads: <= 3072 (41 KB) and <= 4096 (55 KB)
+//   256 threads: <= 5632 (74 KB, three per SM)
+//   512 threads: everything larger: <= 8192 points shared-memory resident (108 KB), beyond that
+//                streamed from L2; the far-ring patches that iterate longest get the most threads
 // The class kernels run concurrently on separate streams and the hardware block scheduler packs
 // whatever mix fits an SM.  blockIdx.x walks (patch rank, scan) largest patch first; a block whose
 // patch belongs to another class exits at once.
@@ -827,7 +828,7 @@ __device__ __forceinline__ FitSmem carve_smem(unsigned char* raw, int cap, int w
 // float solver, which is enough to tip chaotic two-layer patches the other way).
 // ---------------------------------------------------------------------------------------------
 template <int TT, bool EXACT>
-__global__ void __launch_bounds__(TT, (TT <= 64 ? 8 : TT <= 128 ? 4 : 2))
+__global__ void __launch_bounds__(TT, (TT <= 64 ? 8 : TT <= 128 ? 4 : TT <= 256 ? 3 : 2))
 rpw_fit_roots_kernel(FitArgs A, uint32_t n_lo, uint32_t n_hi, int cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t id = blockIdx.x;
@@ -1001,14 +1002,29 @@ static cudaError_t set_smem(KernelT k, size_t bytes) {
     return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+// Size classes of the level-0 kernel: (threads, largest patch, shared-memory capacity in points).
+// Finer steps waste less shared memory per resident patch (a 2100-point patch in a 4096-point slot
+// blocks twice the memory it needs for its whole 40 us life), which is what bounds the fit phase.
+struct FitClass { int threads; uint32_t hi; int cap; };
+static const FitClass kFitClasses[kNumFitClasses] = {
+    {64, 1024, 1024}, {64, 2048, 2048}, {128, 3072, 3072}, {128, 4096, 4096}, {256, 5632, 5632}, {512, 0xFFFFFFFFu, kCapLarge},
+};
+
+template <int TT>
+static cudaError_t configure_roots() {
+    size_t need = 0;
+    for (const FitClass& c : kFitClasses) if (c.threads == TT) need = fit_smem_bytes(c.cap, TT) > need ? fit_smem_bytes(c.cap, TT) : need;
+    cudaError_t e = set_smem(rpw_fit_roots_kernel<TT, true>, need);
+    if (e != cudaSuccess) return e;
+    return set_smem(rpw_fit_roots_kernel<TT, false>, need);
+}
+
 cudaError_t fit_configure(int smem_cap, int* blocks_per_sm) {
     cudaError_t e;
-    if ((e = set_smem(rpw_fit_roots_kernel<64, true>, fit_smem_bytes(kCapTiny, 64))) != cudaSuccess) return e;
-    if ((e = set_smem(rpw_fit_roots_kernel<64, false>, fit_smem_bytes(kCapTiny, 64))) != cudaSuccess) return e;
-    if ((e = set_smem(rpw_fit_roots_kernel<128, true>, fit_smem_bytes(kCapSmall, 128))) != cudaSuccess) return e;
-    if ((e = set_smem(rpw_fit_roots_kernel<128, false>, fit_smem_bytes(kCapSmall, 128))) != cudaSuccess) return e;
-    if ((e = set_smem(rpw_fit_roots_kernel<512, true>, fit_smem_bytes(kCapLarge, 512))) != cudaSuccess) return e;
-    if ((e = set_smem(rpw_fit_roots_kernel<512, false>, fit_smem_bytes(kCapLarge, 512))) != cudaSuccess) return e;
+    if ((e = configure_roots<64>()) != cudaSuccess) return e;
+    if ((e = configure_roots<128>()) != cudaSuccess) return e;
+    if ((e = configure_roots<256>()) != cudaSuccess) return e;
+    if ((e = configure_roots<512>()) != cudaSuccess) return e;
     const size_t smem = fit_smem_bytes(smem_cap, kFitThreads);
     if ((e = set_smem(rpw_fit_levels_kernel<true>, smem)) != cudaSuccess) return e;
     if ((e = set_smem(rpw_fit_levels_kernel<false>, smem)) != cudaSuccess) return e;
@@ -1019,22 +1035,23 @@ cudaError_t fit_configure(int smem_cap, int* blocks_per_sm) {
     return cudaSuccess;
 }
 
-// size class: 0 tiny, 1 small, 2 large (see rpw_fit_roots_kernel)
-cudaError_t launch_fit_roots(cudaStream_t st, const FitArgs& args, int cls) {
+template <int TT>
+static void launch_roots_tt(cudaStream_t st, const FitArgs& args, uint32_t lo, uint32_t hi, int cap) {
     const unsigned grid = (unsigned)args.n_roots;
-    const bool ex = args.fp.exact_eig != 0;
-    if (cls == 0) {
-        const size_t sm = fit_smem_bytes(kCapTiny, 64);
-        if (ex) rpw_fit_roots_kernel<64, true><<<grid, 64, sm, st>>>(args, 0u, (uint32_t)kCapTiny, kCapTiny);
-        else rpw_fit_roots_kernel<64, false><<<grid, 64, sm, st>>>(args, 0u, (uint32_t)kCapTiny, kCapTiny);
-    } else if (cls == 1) {
-        const size_t sm = fit_smem_bytes(kCapSmall, 128);
-        if (ex) rpw_fit_roots_kernel<128, true><<<grid, 128, sm, st>>>(args, (uint32_t)kCapTiny, (uint32_t)kCapSmall, kCapSmall);
-        else rpw_fit_roots_kernel<128, false><<<grid, 128, sm, st>>>(args, (uint32_t)kCapTiny, (uint32_t)kCapSmall, kCapSmall);
-    } else {
-        const size_t sm = fit_smem_bytes(kCapLarge, 512);
-        if (ex) rpw_fit_roots_kernel<512, true><<<grid, 512, sm, st>>>(args, (uint32_t)kCapSmall, 0xFFFFFFFFu, kCapLarge);
-        else rpw_fit_roots_kernel<512, false><<<grid, 512, sm, st>>>(args, (uint32_t)kCapSmall, 0xFFFFFFFFu, kCapLarge);
+    const size_t sm = fit_smem_bytes(cap, TT);
+    if (args.fp.exact_eig) rpw_fit_roots_kernel<TT, true><<<grid, TT, sm, st>>>(args, lo, hi, cap);
+    else rpw_fit_roots_kernel<TT, false><<<grid, TT, sm, st>>>(args, lo, hi, cap);
+}
+
+// size class cls in [0, kNumFitClasses): patches with kFitClasses[cls-1].hi < n <= kFitClasses[cls].hi
+cudaError_t launch_fit_roots(cudaStream_t st, const FitArgs& args, int cls) {
+    const FitClass& c = kFitClasses[cls];
+    const uint32_t lo = cls == 0 ? 0u : kFitClasses[cls - 1].hi;
+    switch (c.threads) {
+        case 64: launch_roots_tt<64>(st, args, lo, c.hi, c.cap); break;
+        case 128: launch_roots_tt<128>(st, args, lo, c.hi, c.cap); break;
+        case 256: launch_roots_tt<256>(st, args, lo, c.hi, c.cap); break;
+        default: launch_roots_tt<512>(st, args, lo, c.hi, c.cap); break;
     }
     return cudaGetLastError();
 }

@@ -44,6 +44,7 @@ struct FitArgs {
     FitParams fp;
 };
 
+constexpr int kNumFitClasses = 6;  // size classes of the level-0 fit kernel (rpw_kernels.cu: kFitClasses)
 size_t fit_smem_bytes(int smem_cap, int threads);
 cudaError_t fit_configure(int smem_cap, int* blocks_per_sm);
 
