@@ -10,7 +10,7 @@
 //                           per node: early-outs, seeds, iterated PCA plane fit with a register
 //                           3x3 eigensolve, residual mask, split (variance axis, exact radix-select
 //                           median, stable partition), child enqueue, label scatter
-//   K3b rpw_fit_levels_kernel persistent kernel (one block per SM, grid barrier in global memory):
+//   K3b rpw_fit_levels_kernel persistent cooperative kernel (one block per SM, grid barrier in global memory):
 //                           level-synchronous device worklist over the children of split nodes
 //                           (depth >= 1), no host round trips
 //   dbg rpw_eig3_kernel / rpw_atan2_kernel   unit-test entry points for the device math
@@ -849,12 +849,10 @@ rpw_fit_roots_kernel(FitArgs A, uint32_t n_lo, uint32_t n_hi, int cap) {
 // separates levels; the kernel ends when a level enqueued nothing.  Typical scans never split: every
 // block then reads an empty queue and leaves without touching the barrier.
 //
-// The grid is one block per SM and the barrier is a counter in global memory (arrive + spin), not a
-// cooperative launch: a cooperative kernel cannot start until the whole grid fits at once, which
-// would stall the other launch group that the host pipelines next to this one.  Blocks of this
-// kernel only ever wait for sibling blocks of the same launch, and those only wait for SM resources
-// held by independent kernels that run to completion, so the spin always ends.  All cross-block data
-// (children, queues, counters) is read with ld.global.cg, so no stale L1 lines are involved.
+// The grid is one block per SM, launched cooperatively (all blocks resident, so the barrier cannot
+// deadlock), and the barrier itself is a counter in global memory (arrive + spin with nanosleep).
+// All cross-block data (children, queues, counters) is read with ld.global.cg, so no stale L1 lines
+// are involved.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void grid_barrier(uint32_t* ctr, uint32_t target) {
     __syncthreads();
@@ -1056,11 +1054,15 @@ cudaError_t launch_fit_roots(cudaStream_t st, const FitArgs& args, int cls) {
     return cudaGetLastError();
 }
 
+// Launched with cudaLaunchCooperativeKernel: the driver only starts the grid when every block can be
+// resident, which is what makes the spin barrier safe however many handles share the device (two
+// plain launches from different handles could otherwise each hold half of the SMs and wait for the
+// other half forever).
 cudaError_t launch_fit_levels(cudaStream_t st, const FitArgs& args, int grid_blocks) {
-    const size_t sm = fit_smem_bytes(args.smem_cap, kFitThreads);
-    if (args.fp.exact_eig) rpw_fit_levels_kernel<true><<<grid_blocks, kFitThreads, sm, st>>>(args);
-    else rpw_fit_levels_kernel<false><<<grid_blocks, kFitThreads, sm, st>>>(args);
-    return cudaGetLastError();
+    FitArgs a = args;
+    void* params[] = {&a};
+    void* fn = args.fp.exact_eig ? (void*)rpw_fit_levels_kernel<true> : (void*)rpw_fit_levels_kernel<false>;
+    return cudaLaunchCooperativeKernel(fn, dim3(grid_blocks), dim3(kFitThreads), params, fit_smem_bytes(args.smem_cap, kFitThreads), st);
 }
 
 cudaError_t launch_eig3(cudaStream_t st, const float* mats, size_t count, float* evals, float* evecs) {
