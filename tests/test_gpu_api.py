@@ -169,3 +169,33 @@ def test_fused_multi_lidar_frame(rpw, h, oracle):
     plain = h.segment(clouds[0])
     one = h.segment_fused(clouds[:1], [0.0], [-1.0])[0]
     assert np.array_equal(plain, one)
+
+
+def test_concurrent_handles_with_recursion(rpw, oracle):
+    """Several handles on one device, each from its own thread and stream, on a scene that recurses
+    (so every handle's level kernel really runs its grid barrier): no deadlock, same labels."""
+    import threading
+    cfg = rpw.PatchworkConfig(filtering_radius=80.0)
+    pts = rpw.synth.spinning_scan(3000, 128, 1024, 1)
+    want = oracle.run(cfg, pts)["labels"]
+    assert oracle.run(cfg, pts, want_nodes=True)["stats"]["n_splits"] > 5
+    results, errors = {}, []
+
+    def work(k):
+        try:
+            hk = rpw.Handle(cfg.to_c(), 0, len(pts) + 16, 1)
+            for _ in range(15):
+                results[k] = hk.segment(pts)
+            hk.close()
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+        assert not t.is_alive(), "a handle is stuck"
+    assert not errors
+    for k in range(4):
+        assert (results[k] == want).mean() >= 0.999
