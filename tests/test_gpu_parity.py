@@ -235,3 +235,59 @@ def test_sector_edges_take_the_exact_path(rpw, h, oracle):
         keys = h.debug_keys(len(pts))
         o = oracle.run(cfg, pts)
         assert np.array_equal(keys, o["keys"]), (S, np.nonzero(keys != o["keys"])[0][:10])
+
+
+def _one_patch_cloud(n, seed, two_layers):
+    """Everything inside one ring/sector patch of the default zone model (ring 6, sector 0)."""
+    rng = np.random.default_rng(seed)
+    r = rng.uniform(45.0, 75.0, n)
+    a = rng.uniform(0.02, 0.60, n)
+    z = rng.normal(0.0, 0.03, n)
+    if two_layers:
+        z = z + (rng.uniform(size=n) < 0.5) * 0.95
+    return np.stack([r * np.cos(a), r * np.sin(a), z], 1).astype(np.float32)
+
+
+def _dup_xy(rpw):
+    p = rpw.synth.testsuite_cloud(54, 40000)[:, :3].copy()
+    p[:, :2] = np.round(p[:, :2] * np.float32(2)) / np.float32(2)  # x, y on a 0.5 m grid; z stays continuous
+    return p
+
+
+EDGE_CASES = {
+    # a 300k-point patch: streamed from L2 at depth 0, collapses and splits many levels deep, so the
+    # radix select, the stable partition and the level kernel all run in streaming mode first
+    "one_huge_patch_two_layers": lambda rpw: (rpw.PatchworkConfig(), _one_patch_cloud(300000, 1, True)),
+    "one_huge_patch_flat": lambda rpw: (rpw.PatchworkConfig(), _one_patch_cloud(200000, 2, False)),
+    # ring edges collapse when R <= 1: every in-zone point is unbinned (reference loop finds no ring)
+    "radius_below_one": lambda rpw: (rpw.PatchworkConfig(filtering_radius=0.9), rpw.synth.testsuite_cloud(51, 4000) * np.float32(0.02)),
+    "one_sector": lambda rpw: (rpw.PatchworkConfig(num_sectors=1, filtering_radius=60.0), rpw.synth.testsuite_cloud(52, 30000)),
+    "128_sectors": lambda rpw: (rpw.PatchworkConfig(num_sectors=128, filtering_radius=60.0), rpw.synth.testsuite_cloud(53, 60000)),
+    "no_splits_allowed": lambda rpw: (rpw.PatchworkConfig(filtering_radius=80.0, max_split_depth=0), rpw.synth.spinning_scan(3000, 128, 1024, 1)),
+    # a tiny distance threshold makes almost every fit collapse: recursion limited only by
+    # n >= 50 + 10 * depth and the 25 m^2 rule
+    "tiny_th_dist": lambda rpw: (rpw.PatchworkConfig(filtering_radius=80.0, th_dist=0.004), rpw.synth.spinning_scan(1000, 64, 900)),
+    # heavy coordinate duplication: medians with many ties, empty right children (SURVEY Q7)
+    "duplicated_coordinates": lambda rpw: (rpw.PatchworkConfig(filtering_radius=60.0, th_dist=0.01), _dup_xy(rpw)),
+    "million_points": lambda rpw: (rpw.PatchworkConfig(), rpw.synth.testsuite_cloud(55, 1000000)),
+    "sensor_height_negative": lambda rpw: (rpw.PatchworkConfig(sensor_height=-5.0), rpw.synth.testsuite_cloud(56, 20000)),  # < 3 seeds everywhere: lowest-3 fallback
+}
+
+
+@pytest.mark.parametrize("case", sorted(EDGE_CASES))
+def test_edge_cases_against_oracle(case, rpw, gpu_handle_factory, oracle):
+    cfg, pts = EDGE_CASES[case](rpw)
+    pts = np.ascontiguousarray(pts[:, :3], np.float32)
+    hd = gpu_handle_factory(cfg, len(pts) + 1024, 1)
+    hd.enable_nodes(True)
+    labels, st = hd.segment(pts, want_stats=True)
+    keys = hd.debug_keys(len(pts))
+    nodes = hd.debug_nodes()
+    o = oracle.run(cfg, pts, want_nodes=True)
+    rep = parity.compare_scan(labels, keys, o)
+    nrep = parity.compare_nodes(nodes, o["nodes"])
+    print(case, rep, {k: nrep[k] for k in ("n_gpu", "n_oracle", "n_shared", "outcome_mismatch", "max_angle")}, "levels", st.n_levels)
+    assert rep["key_mismatch"] == 0 and rep["n_flips_nonpatch"] == 0
+    assert rep["label_agreement"] >= LABEL_BAR
+    assert nrep["n_shared"] >= 0.98 * nrep["n_oracle"]
+    hd.close()
