@@ -583,8 +583,9 @@ __device__ void process_node(const FitArgs& A, const NodeRef nd, const int depth
     });
     block_sum<TT, 4>(acc, S.red, phase);
     if (acc[0] < 3.f) {
-        // the three lowest-z points, lowest index first among equal z (std::partial_sort at
-        // :175-176 leaves ties unspecified)
+        // the three lowest-z points (std::partial_sort over indices, :173-181).  Parallel pick by
+        // (z, index); if z ties reach across the cut the SET libstdc++'s heap-select keeps depends on
+        // its heap history, so in that (rare) case one thread replays the heap exactly.
         uint32_t chosen[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
         for (int r = 0; r < 3; ++r) {
             unsigned long long best = ~0ull;
@@ -595,6 +596,37 @@ __device__ void process_node(const FitArgs& A, const NodeRef nd, const int depth
             }
             best = block_min_u64<TT>(best, S.red, phase);
             chosen[r] = (uint32_t)(best & 0xFFFFFFFFu);
+        }
+        {
+            const float v3 = nv.coord(chosen[2], 2);
+            float ties[1] = {0.f};
+            for (uint32_t i = tid; i < n; i += TT) ties[0] += (nv.coord(i, 2) <= v3) ? 1.f : 0.f;
+            block_sum<TT, 1>(ties, S.red, phase);
+            if (ties[0] > 3.f) {
+                // replay of std::__heap_select(first, first + 3, last, z[a] < z[b]) on a 3-element heap
+                // (make_heap with one __adjust_heap, then __pop_heap for every later element that is
+                // strictly below the root); same code as oracle/rpw_oracle.c:lowest3
+                if (tid == 0) {
+                    uint32_t hp[3] = {0, 1, 2};
+                    auto zz = [&](uint32_t i) { return nv.coord(i, 2); };
+                    auto adjust = [&](uint32_t value) {
+                        uint32_t hole = 0;
+                        uint32_t second = 2;
+                        if (zz(hp[2]) < zz(hp[1])) second = 1;
+                        hp[0] = hp[second];
+                        hole = second;
+                        if (zz(hp[0]) < zz(value)) { hp[hole] = hp[0]; hole = 0; }  // __push_heap: parent is the root
+                        hp[hole] = value;
+                    };
+                    adjust(hp[0]);
+                    for (uint32_t i = 3; i < n; ++i)
+                        if (zz(i) < zz(hp[0])) adjust(i);
+                    S.misc[2] = hp[0]; S.misc[3] = hp[1]; S.misc[4] = hp[2];
+                }
+                __syncthreads();
+                chosen[0] = S.misc[2]; chosen[1] = S.misc[3]; chosen[2] = S.misc[4];
+                __syncthreads();
+            }
         }
         // ascending index so that the 3-term sums follow the reference's order
         if (chosen[0] > chosen[1]) { const uint32_t t = chosen[0]; chosen[0] = chosen[1]; chosen[1] = t; }

@@ -254,6 +254,12 @@ def _dup_xy(rpw):
     return p
 
 
+def _quantised_z(rpw):
+    p = rpw.synth.testsuite_cloud(57, 30000)[:, :3].copy()
+    p[:, 2] = np.round(p[:, 2] * np.float32(8)) / np.float32(8)
+    return p
+
+
 EDGE_CASES = {
     # a 300k-point patch: streamed from L2 at depth 0, collapses and splits many levels deep, so the
     # radix select, the stable partition and the level kernel all run in streaming mode first
@@ -270,6 +276,9 @@ EDGE_CASES = {
     # heavy coordinate duplication: medians with many ties, empty right children
     "duplicated_coordinates": lambda rpw: (rpw.PatchworkConfig(filtering_radius=60.0, th_dist=0.01), _dup_xy(rpw)),
     "million_points": lambda rpw: (rpw.PatchworkConfig(), rpw.synth.testsuite_cloud(55, 1000000)),
+    # no seed below the threshold anywhere AND z on a coarse grid: the lowest-3 fallback meets exact ties,
+    # which the device resolves by replaying libstdc++'s heap-select (std::partial_sort, :175-176)
+    "lowest3_with_ties": lambda rpw: (rpw.PatchworkConfig(sensor_height=-5.0), _quantised_z(rpw)),
     "sensor_height_negative": lambda rpw: (rpw.PatchworkConfig(sensor_height=-5.0), rpw.synth.testsuite_cloud(56, 20000)),  # < 3 seeds everywhere: lowest-3 fallback
 }
 
