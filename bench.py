@@ -347,7 +347,7 @@ def main():
     clocks = sampler.stop()
 
     # ---- single-scan latency: the reference's own use (one scan per ROS2 callback), synchronous
-    # rpw_segment on pinned host buffers, H2D + 7 launches + D2H per call ----
+    # rpw_segment on pinned host buffers, H2D + 10 launches + D2H per call ----
     lat_ms, other_shapes = None, None
     if rank == 0:
         h1 = rpw.Handle(cfg.to_c(), local_rank, POINTS_PER_SCAN + 4096, 1)

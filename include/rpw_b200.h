@@ -220,9 +220,11 @@ int rpw_debug_nodes(rpw_handle* h, rpw_node* out, size_t cap, size_t* count);
 int rpw_debug_eig3(rpw_handle* h, const float* mats, size_t count, float* evals, float* evecs);
 /* Runs the plane-normal solver the fit kernel uses on `count` scatter matrices (6 floats each:
  * xx yx yy zx zy zz; one warp per matrix): mode 0 = closed-form FP64 smallest eigenvector, mode 1 = Eigen's QR sequence
- * (generic form, the one rpw_debug_eig3 runs), mode 2 = the same sequence restructured for latency (what the
- * fit kernel runs by default; bit-identical to mode 1).  normals3: unit normals with z >= 0; cycles: SM cycles
- * one call took. */
+ * (generic form, the one rpw_debug_eig3 runs), mode 2 = the same sequence restructured for latency on the
+ * compiler's IEEE division / square root / reciprocal, mode 3 = mode 2 on branch-free copies of those operations'
+ * fast paths with an IEEE fallback (what the fit kernel runs by default; modes 1, 2, 3 are bit-identical),
+ * mode 4 = mode 3 without the fallback (normal (0, 0, 2) marks a solve whose operands left the fast range).
+ * normals3: unit normals with z >= 0; cycles: SM cycles one call took. */
 int rpw_debug_normal(rpw_handle* h, const float* scatter6, size_t count, int mode, float* normals3, uint32_t* cycles);
 /* Runs the device restatement of libm atan2f on `count` (y, x) pairs. */
 int rpw_debug_atan2(rpw_handle* h, const float* y, const float* x, size_t count, float* out);
@@ -232,6 +234,20 @@ int rpw_debug_atan2(rpw_handle* h, const float* y, const float* x, size_t count,
  * 1 seeds, 2 covariance pass, 3 eigensolve, 4 distance/mask pass, 5 final fit, 6 leaf label write,
  * 7 split, 8 fetch, 9 grid barrier, 10 nodes, 11 plane-fit iterations. */
 int rpw_debug_fit_timing(rpw_handle* h, int enable, uint64_t* cycles16);
+
+/* Per-node timeline of the fit kernels (scheduling analysis: which SM ran which node when).
+ * out == NULL: (re)arms the trace with room for `cap` records (0 switches it off).  Otherwise copies
+ * up to `cap` records of the calls since arming into `out`, stores how many nodes were seen in
+ * *count (may exceed cap: the rest was dropped) and clears the trace.  Tracing slows the kernels a
+ * little (one global timer read and one 32-byte store per node). */
+typedef struct rpw_trace_rec {
+    uint64_t t_start_ns, t_end_ns; /* %globaltimer */
+    uint32_t sm;                   /* %smid */
+    uint32_t n;                    /* points of the node */
+    uint16_t depth, size_class;    /* size_class: level-0 class index, 0xFFFF for deeper levels */
+    uint32_t iters;                /* plane-fit iterations */
+} rpw_trace_rec;
+int rpw_debug_fit_trace(rpw_handle* h, rpw_trace_rec* out, size_t cap, size_t* count);
 
 /* ---- measurement -------------------------------------------------------------------------- */
 /* Device time per kernel, measured with CUDA events recorded on the handle's stream around every

@@ -5,12 +5,13 @@ sm_100 device is present, everything here raises — there is no CPU fallback.""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "librpw_b200.so"
+LIB_PATH = Path(os.environ["RPW_B200_LIB"]) if os.environ.get("RPW_B200_LIB") else PKG / "librpw_b200.so"  # (override: kernel experiments)
 
 RPW_OK, RPW_ERR_BAD_ARG, RPW_ERR_NO_DEVICE, RPW_ERR_CUDA, RPW_ERR_CAPACITY, RPW_ERR_ALLOC = range(6)
 LABEL_NONGROUND, LABEL_GROUND, LABEL_BEYOND, LABEL_DROPPED, LABEL_EGO = 0, 1, 2, 3, 4
@@ -53,7 +54,7 @@ NODE_DTYPE = np.dtype([("scan", "<i4"), ("root", "<i4"), ("depth", "<i4"), ("sta
 EXPORTS = ["rpw_default_config", "rpw_zone_model", "rpw_create", "rpw_destroy", "rpw_set_config", "rpw_get_config",
            "rpw_set_plane_solver", "rpw_set_stream", "rpw_last_error", "rpw_segment", "rpw_segment_batch", "rpw_segment_batch_async", "rpw_wait",
            "rpw_segment_pc2", "rpw_segment_fused", "rpw_segment_clouds", "rpw_segment_device", "rpw_debug_keys", "rpw_debug_enable_nodes", "rpw_debug_nodes",
-           "rpw_debug_eig3", "rpw_debug_normal", "rpw_debug_atan2", "rpw_debug_fit_timing", "rpw_profile_enable", "rpw_profile_read", "rpw_host_alloc", "rpw_host_free", "rpw_kernel_launches", "rpw_abi_version"]
+           "rpw_debug_eig3", "rpw_debug_normal", "rpw_debug_atan2", "rpw_debug_fit_timing", "rpw_debug_fit_trace", "rpw_profile_enable", "rpw_profile_read", "rpw_host_alloc", "rpw_host_free", "rpw_kernel_launches", "rpw_abi_version"]
 
 _lib = None
 
@@ -102,6 +103,7 @@ def load_library() -> C.CDLL:
     lib.rpw_debug_normal.argtypes = [vp, vp, sz, C.c_int, vp, vp]; lib.rpw_debug_normal.restype = C.c_int
     lib.rpw_debug_atan2.argtypes = [vp, vp, vp, sz, vp]; lib.rpw_debug_atan2.restype = C.c_int
     lib.rpw_debug_fit_timing.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64)]; lib.rpw_debug_fit_timing.restype = C.c_int
+    lib.rpw_debug_fit_trace.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]; lib.rpw_debug_fit_trace.restype = C.c_int
     lib.rpw_profile_enable.argtypes = [vp, C.c_int]; lib.rpw_profile_enable.restype = C.c_int
     lib.rpw_profile_read.argtypes = [vp, C.POINTER(RpwProfile)]; lib.rpw_profile_read.restype = C.c_int
     lib.rpw_host_alloc.argtypes = [sz]; lib.rpw_host_alloc.restype = vp
@@ -318,6 +320,20 @@ class Handle:
         self._check(self.lib.rpw_debug_fit_timing(self._h, 1 if enable else 0, out))
         names = ["load", "seeds", "cov", "eig", "dist", "final", "label", "split", "fetch", "gridsync", "nodes", "iters", "cov_reduce", "dist_reduce", "qr_only"]
         return {k: int(out[i]) for i, k in enumerate(names)}
+
+    TRACE_DTYPE = np.dtype([("t_start_ns", "<u8"), ("t_end_ns", "<u8"), ("sm", "<u4"), ("n", "<u4"), ("depth", "<u2"),
+                            ("size_class", "<u2"), ("iters", "<u4")])
+
+    def fit_trace_arm(self, cap=1 << 20):
+        """Arms (cap > 0) or switches off (cap = 0) the per-node timeline of the fit kernels."""
+        self._check(self.lib.rpw_debug_fit_trace(self._h, None, int(cap), None))
+
+    def fit_trace_read(self, cap=1 << 20):
+        """Records since arming (structured array, TRACE_DTYPE) and the number of nodes seen; clears the trace."""
+        out = np.zeros(int(cap), self.TRACE_DTYPE)
+        seen = C.c_size_t(0)
+        self._check(self.lib.rpw_debug_fit_trace(self._h, out.ctypes.data, int(cap), C.byref(seen)))
+        return out[:min(int(seen.value), int(cap))], int(seen.value)
 
     def profile_enable(self, on=True):
         self._check(self.lib.rpw_profile_enable(self._h, 1 if on else 0))

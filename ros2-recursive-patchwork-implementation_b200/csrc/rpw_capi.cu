@@ -34,16 +34,20 @@ struct rpw_handle {
         cudaEvent_t ev_fork = nullptr, ev_join[kNumFitClasses] = {}, ev_start = nullptr, ev_done = nullptr;
         NodeRef* d_queue[2] = {nullptr, nullptr};
         uint32_t* d_counters = nullptr;     // fetch_ctr[levels_cap] | q_count[levels_cap] | stats[8] | overflow
-        uint32_t* d_patch_total = nullptr;  // [P] points per patch over the launch group
-        uint32_t* d_patch_order = nullptr;  // [P] patches, largest first
+        uint32_t* d_cls_count = nullptr;    // [8] root patches per size class over the launch group
+        uint4* d_cls_list = nullptr;        // [kNumFitClasses][cls_cap] the classes' work lists
+        uint32_t* h_counts = nullptr;       // mapped host copy of the last finished group's class counts ([kClsWords-1]: its scan count)
+        uint32_t* d_counts_map = nullptr;   // device address of h_counts
     };
     static constexpr int kLanes = 2;
     Lane lane[kLanes];
     cudaEvent_t ev_call = nullptr;
     uint32_t* d_dbg_count = nullptr;
+    uint32_t* d_sm_ticket = nullptr;
     int n_waves = 1;  // launch groups per call (1: within one call more groups only add tails)
     size_t cap_points = 0, cap_batch = 0;
     int P = 0;
+    uint32_t cls_cap = 0;
     int levels_cap = 0;
     uint32_t q_cap = 0;
     int smem_cap = 0;
@@ -71,6 +75,9 @@ struct rpw_handle {
     FusionTable* h_fusion = nullptr;    // pinned
     rpw_node* d_dbg_nodes = nullptr;
     unsigned long long* d_timing = nullptr;  // [16], allocated by rpw_debug_fit_timing
+    rpw_trace_rec* d_trace = nullptr;        // rpw_debug_fit_trace
+    uint32_t* d_trace_count = nullptr;
+    uint32_t trace_cap = 0;
     bool timing_enabled = false;
     uint32_t dbg_cap = 0;
     bool dbg_enabled = false;
@@ -171,8 +178,8 @@ static void free_patch_buffers(rpw_handle* h) {
     cudaFree(h->d_patch_start); h->d_patch_start = nullptr;
     cudaFree(h->d_root_mean); h->d_root_mean = nullptr;
     for (auto& L : h->lane) {
-        cudaFree(L.d_patch_total); L.d_patch_total = nullptr;
-        cudaFree(L.d_patch_order); L.d_patch_order = nullptr;
+        cudaFree(L.d_cls_count); L.d_cls_count = nullptr;
+        cudaFree(L.d_cls_list); L.d_cls_list = nullptr;
     }
 }
 
@@ -183,9 +190,17 @@ static int alloc_patch_buffers(rpw_handle* h) {
     RPW_CUDA(h, cudaMalloc(&h->d_blk_hist, rows * P * sizeof(uint32_t)));
     RPW_CUDA(h, cudaMalloc(&h->d_patch_start, h->cap_batch * (size_t)(P + 1) * sizeof(uint32_t)));
     RPW_CUDA(h, cudaMalloc(&h->d_root_mean, h->cap_batch * (size_t)P * sizeof(float)));
+    const size_t pairs = h->cap_batch * (size_t)P;  // a listed patch holds at least one point
+    h->cls_cap = (uint32_t)(pairs < h->cap_points ? pairs : h->cap_points);
     for (auto& L : h->lane) {
-        RPW_CUDA(h, cudaMalloc(&L.d_patch_total, (size_t)P * sizeof(uint32_t)));
-        RPW_CUDA(h, cudaMalloc(&L.d_patch_order, (size_t)P * sizeof(uint32_t)));
+        RPW_CUDA(h, cudaMalloc(&L.d_cls_count, kClsWords * sizeof(uint32_t)));
+        RPW_CUDA(h, cudaMemset(L.d_cls_count, 0, kClsWords * sizeof(uint32_t)));
+        RPW_CUDA(h, cudaMalloc(&L.d_cls_list, (size_t)kNumFitClasses * h->cls_cap * sizeof(uint4)));
+        if (!L.h_counts) {
+            RPW_CUDA(h, cudaHostAlloc(&L.h_counts, kClsWords * sizeof(uint32_t), cudaHostAllocMapped));
+            RPW_CUDA(h, cudaHostGetDevicePointer(&L.d_counts_map, L.h_counts, 0));
+        }
+        memset(L.h_counts, 0, kClsWords * sizeof(uint32_t));
     }
     return RPW_OK;
 }
@@ -210,7 +225,7 @@ void rpw_destroy(rpw_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_in); cudaFree(h->d_keys); cudaFree(h->d_labels); cudaFree(h->d_sortedA); cudaFree(h->d_bufB);
-    cudaFree(h->d_bufC); cudaFree(h->d_gmask); cudaFree(h->d_dbg_count);
+    cudaFree(h->d_bufC); cudaFree(h->d_gmask); cudaFree(h->d_dbg_count); cudaFree(h->d_sm_ticket); cudaFree(h->d_trace); cudaFree(h->d_trace_count);
     cudaFree(h->d_scan_off); cudaFree(h->d_chunk_base); cudaFree(h->d_dbg_nodes); cudaFree(h->d_timing); cudaFree(h->d_fusion);
     if (h->h_fusion) cudaFreeHost(h->h_fusion);
     free_patch_buffers(h);
@@ -218,6 +233,7 @@ void rpw_destroy(rpw_handle* h) {
     if (h->h_stage_in) cudaFreeHost(h->h_stage_in);
     if (h->h_stage_labels) cudaFreeHost(h->h_stage_labels);
     if (h->h_stats) cudaFreeHost(h->h_stats);
+    for (auto& L : h->lane) if (L.h_counts) { cudaFreeHost(L.h_counts); L.h_counts = nullptr; }
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     for (auto& L : h->lane) {
         cudaFree(L.d_queue[0]); cudaFree(L.d_queue[1]); cudaFree(L.d_counters);
@@ -269,10 +285,19 @@ int rpw_create(const rpw_config* cfg, int device, size_t max_total_points, size_
     TRYC(cudaSetDevice(device));
     TRYC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
+    // The size classes of the level-0 fit run on side streams whose priority falls with the patch
+    // size (side[0] is the largest class): the block scheduler then starts the big, long-iterating
+    // patches first and back-fills the shared memory they leave with the small ones, instead of
+    // draining the kernels in whatever order their stream dependencies happen to resolve.
+    int prio_least = 0, prio_greatest = 0;
+    TRYC(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    const int prio_levels = prio_least - prio_greatest + 1;
     for (auto& L : h->lane) {
         TRYC(cudaStreamCreateWithFlags(&L.main, cudaStreamNonBlocking));
         for (int k = 0; k < kNumFitClasses; ++k) {
-            TRYC(cudaStreamCreateWithFlags(&L.side[k], cudaStreamNonBlocking));
+            int lev = k * prio_levels / kNumFitClasses;
+            if (lev > prio_levels - 1) lev = prio_levels - 1;
+            TRYC(cudaStreamCreateWithPriority(&L.side[k], cudaStreamNonBlocking, prio_greatest + lev));
             TRYC(cudaEventCreateWithFlags(&L.ev_join[k], cudaEventDisableTiming));
         }
         TRYC(cudaEventCreateWithFlags(&L.ev_fork, cudaEventDisableTiming));
@@ -282,6 +307,8 @@ int rpw_create(const rpw_config* cfg, int device, size_t max_total_points, size_
     TRYC(cudaEventCreateWithFlags(&h->ev_call, cudaEventDisableTiming));
     TRYC(cudaMalloc(&h->d_dbg_count, sizeof(uint32_t)));
     TRYC(cudaMemset(h->d_dbg_count, 0, sizeof(uint32_t)));
+    TRYC(cudaMalloc(&h->d_sm_ticket, 1024 * sizeof(uint32_t)));
+    TRYC(cudaMemset(h->d_sm_ticket, 0, 1024 * sizeof(uint32_t)));
     const size_t N = max_total_points;
     TRYC(cudaMalloc(&h->d_in, N * 16));
     h->d_in_bytes = N * 16;
@@ -460,24 +487,31 @@ static int run_group(rpw_handle* h, rpw_handle::Lane& L, cudaStream_t st, const 
     const uint32_t* d_cb = h->d_chunk_base + b0;
     uint32_t* d_ps = h->d_patch_start + b0 * (size_t)(h->P + 1);
     { ProfScope ps(h, 0);
-      RPW_CUDA(h, launch_bin(st, lay, d_pts, d_so, d_cb, h->zm, h->d_keys, d_labels, h->d_blk_hist, L.d_patch_total, h->fusion_arg, max_chunks, (int)nb)); }
+      RPW_CUDA(h, launch_bin(st, lay, d_pts, d_so, d_cb, h->zm, h->d_keys, d_labels, h->d_blk_hist, L.d_cls_count, h->fusion_arg, max_chunks, (int)nb)); }
     { ProfScope ps(h, 1);
-      RPW_CUDA(h, launch_offsets(st, d_so, d_cb, h->d_blk_hist, d_ps, L.d_patch_total, h->P, (int)nb)); }
+      RPW_CUDA(h, launch_offsets(st, d_so, d_cb, h->d_blk_hist, d_ps, L.d_cls_count, L.d_cls_list, h->cls_cap, h->P, (int)nb)); }
     { ProfScope ps(h, 2);
-      RPW_CUDA(h, launch_scatter(st, lay, d_pts, d_so, d_cb, h->d_keys, h->d_blk_hist, d_ps, h->d_sortedA, L.d_patch_total,
-                                 L.d_patch_order, h->P, h->fusion_arg, max_chunks, (int)nb)); }
+      RPW_CUDA(h, launch_scatter(st, lay, d_pts, d_so, d_cb, h->d_keys, h->d_blk_hist, d_ps, h->d_sortedA,
+                                 h->P, h->fusion_arg, max_chunks, (int)nb)); }
     FitArgs A;
     A.sortedA = h->d_sortedA; A.bufB = h->d_bufB; A.bufC = h->d_bufC; A.gmask = h->d_gmask;
     A.labels = d_labels;
     A.patch_start = d_ps;
-    A.patch_order = L.d_patch_order;
+    A.cls_count = L.d_cls_count;
+    A.cls_list = L.d_cls_list;
+    A.cls_cap = h->cls_cap;
+    A.host_counts = L.d_counts_map;
     A.root_mean = h->d_root_mean + b0 * (size_t)h->P;
     A.queue[0] = L.d_queue[0]; A.queue[1] = L.d_queue[1];
     A.fetch_ctr = L.d_counters;
     A.q_count = L.d_counters + h->levels_cap;
     A.stats = L.d_counters + 2 * (size_t)h->levels_cap;
     A.overflow = A.stats + 8;
+    A.sm_ticket = h->d_sm_ticket;
     A.timing = h->timing_enabled ? h->d_timing : nullptr;
+    A.trace = h->trace_cap ? h->d_trace : nullptr;
+    A.trace_count = h->d_trace_count;
+    A.trace_cap = h->trace_cap;
     A.dbg_nodes = h->dbg_enabled ? h->d_dbg_nodes : nullptr;
     A.dbg_count = h->d_dbg_count;
     A.dbg_cap = h->dbg_cap;
@@ -494,11 +528,33 @@ static int run_group(rpw_handle* h, rpw_handle::Lane& L, cudaStream_t st, const 
         // persistent kernel that walks the deeper levels
         static const char* dbg_mask = getenv("RPW_DBG_CLASS_MASK");  // profiling aid: bit k = run size class k only
         const int mask = dbg_mask ? atoi(dbg_mask) : (1 << kNumFitClasses) - 1;
+        // Grid of class c: the class's patch count in the last finished launch group of this lane
+        // (scaled to this group's scan count, plus slack), capped by what the class can hold at all.
+        // Too small only makes some blocks take a second patch, too large starts blocks that leave
+        // after one load: the estimate never affects results.
+        static const char* no_est = getenv("RPW_NO_GRID_ESTIMATE");
+        const ClassBounds cb = fit_class_bounds();
+        const uint64_t group_pts = so[b0 + nb] - so[b0];
+        unsigned grids[kNumFitClasses];
+        const uint32_t est_scans = L.h_counts[kClsWords - 1];
+        for (int c = 0; c < kNumFitClasses; ++c) {
+            const uint64_t lo = c == 0 ? 0 : cb.hi[c - 1];
+            uint64_t bound = group_pts / (lo + 1);
+            if (bound > (uint64_t)nb * (uint64_t)h->P) bound = (uint64_t)nb * (uint64_t)h->P;
+            if (bound > h->cls_cap) bound = h->cls_cap;
+            uint64_t g = bound;
+            if (est_scans && !no_est) {
+                const uint64_t est = ((uint64_t)L.h_counts[c] * nb + est_scans - 1) / est_scans;
+                g = est + est / 32 + 2;
+                if (g > bound) g = bound;
+            }
+            grids[c] = (unsigned)(g ? g : 1);
+        }
         RPW_CUDA(h, cudaEventRecord(L.ev_fork, st));
         for (int k = 0; k < kNumFitClasses; ++k) {
             const int cls = kNumFitClasses - 1 - k;
             RPW_CUDA(h, cudaStreamWaitEvent(L.side[k], L.ev_fork, 0));
-            if (mask & (1 << cls)) RPW_CUDA(h, launch_fit_roots(L.side[k], A, cls));
+            if (mask & (1 << cls)) RPW_CUDA(h, launch_fit_roots(L.side[k], A, cls, grids[cls]));
             RPW_CUDA(h, cudaEventRecord(L.ev_join[k], L.side[k]));
         }
         for (int k = 0; k < kNumFitClasses; ++k) RPW_CUDA(h, cudaStreamWaitEvent(st, L.ev_join[k], 0));
@@ -966,6 +1022,37 @@ int rpw_debug_fit_timing(rpw_handle* h, int enable, uint64_t* cycles16) {
     if (cycles16) RPW_CUDA(h, cudaMemcpy(cycles16, h->d_timing, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     RPW_CUDA(h, cudaMemset(h->d_timing, 0, 16 * sizeof(unsigned long long)));
     h->timing_enabled = enable != 0;
+    return RPW_OK;
+}
+
+int rpw_debug_fit_trace(rpw_handle* h, rpw_trace_rec* out, size_t cap, size_t* count) {
+    if (!h) return RPW_ERR_BAD_ARG;
+    RPW_CUDA(h, cudaSetDevice(h->device));
+    RPW_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (!h->d_trace_count) {
+        RPW_CUDA(h, cudaMalloc(&h->d_trace_count, sizeof(uint32_t)));
+        RPW_CUDA(h, cudaMemset(h->d_trace_count, 0, sizeof(uint32_t)));
+    }
+    if (!out) {  // (re)arm
+        if (cap > 0xFFFFFFFFull) RPW_FAIL(h, RPW_ERR_BAD_ARG, "trace capacity %zu too large", cap);
+        if (cap > h->trace_cap) {
+            cudaFree(h->d_trace);
+            h->d_trace = nullptr;
+            h->trace_cap = 0;
+            RPW_CUDA(h, cudaMalloc(&h->d_trace, cap * sizeof(rpw_trace_rec)));
+        }
+        h->trace_cap = (uint32_t)cap;
+        RPW_CUDA(h, cudaMemset(h->d_trace_count, 0, sizeof(uint32_t)));
+        if (count) *count = 0;
+        return RPW_OK;
+    }
+    uint32_t seen = 0;
+    RPW_CUDA(h, cudaMemcpy(&seen, h->d_trace_count, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    size_t take = seen < h->trace_cap ? seen : h->trace_cap;
+    if (take > cap) take = cap;
+    if (take) RPW_CUDA(h, cudaMemcpy(out, h->d_trace, take * sizeof(rpw_trace_rec), cudaMemcpyDeviceToHost));
+    RPW_CUDA(h, cudaMemset(h->d_trace_count, 0, sizeof(uint32_t)));
+    if (count) *count = seen;
     return RPW_OK;
 }
 

@@ -43,14 +43,13 @@ template <bool VEC4>
 __global__ void __launch_bounds__(kBinThreads) rpw_bin_kernel(const float* __restrict__ pts, PointLayout lay, const uint64_t* __restrict__ scan_off,
                                                              const uint32_t* __restrict__ chunk_base, ZoneModel zm,
                                                              uint16_t* __restrict__ keys, uint8_t* __restrict__ labels,
-                                                             uint32_t* __restrict__ blk_hist, uint32_t* __restrict__ patch_total,
+                                                             uint32_t* __restrict__ blk_hist, uint32_t* __restrict__ cls_count,
                                                              const FusionTable* __restrict__ fusion) {
     extern __shared__ uint32_t s_hist[];
     const int b = blockIdx.y, chunk = blockIdx.x;
-    // batch-wide points-per-patch totals (scheduling order of the fit kernel) start from zero;
-    // the offsets kernel, which runs after this one, accumulates them
-    if (b == 0 && chunk == 0)
-        for (int p = threadIdx.x; p < zm.num_patches; p += kBinThreads) patch_total[p] = 0;
+    // the fit kernel's per-class work lists start empty; the offsets kernel, which runs after this
+    // one, fills them
+    if (b == 0 && chunk == 0 && threadIdx.x < kClsWords) cls_count[threadIdx.x] = 0;
     const uint64_t off = scan_off[b];
     const uint32_t n = (uint32_t)(scan_off[b + 1] - off);
     const uint32_t base = (uint32_t)chunk * kBinChunk;
@@ -89,13 +88,17 @@ __global__ void __launch_bounds__(kBinThreads) rpw_bin_kernel(const float* __res
 // =============================================================================================
 __global__ void __launch_bounds__(256) rpw_offsets_kernel(const uint64_t* __restrict__ scan_off, const uint32_t* __restrict__ chunk_base,
                                                          uint32_t* __restrict__ blk_hist, uint32_t* __restrict__ patch_start,
-                                                         uint32_t* __restrict__ patch_total, int P) {
-    extern __shared__ uint32_t s_cnt[];  // P + 1
+                                                         uint32_t* __restrict__ cls_count, uint4* __restrict__ cls_list, uint32_t cls_cap,
+                                                         ClassBounds cb, int P) {
+    extern __shared__ uint32_t s_cnt[];  // [P] sizes, then [P] starts
+    uint32_t* s_start = s_cnt + P;
+    __shared__ uint32_t s_cls[kNumFitClasses], s_base[kNumFitClasses];
     const int b = blockIdx.x;
     const uint64_t off = scan_off[b];
     const uint32_t n = (uint32_t)(scan_off[b + 1] - off);
     const int chunks = (int)((n + kBinChunk - 1) / kBinChunk);
     uint32_t* h = blk_hist + (size_t)chunk_base[b] * P;
+    if (threadIdx.x < kNumFitClasses) s_cls[threadIdx.x] = 0;
     for (int p = threadIdx.x; p < P; p += blockDim.x) {
         uint32_t run = 0;
         int c = 0;
@@ -113,7 +116,6 @@ __global__ void __launch_bounds__(256) rpw_offsets_kernel(const uint64_t* __rest
             run += v;
         }
         s_cnt[p] = run;
-        if (run) atomicAdd(&patch_total[p], run);
     }
     __syncthreads();
     if (threadIdx.x < 32) {
@@ -127,10 +129,42 @@ __global__ void __launch_bounds__(256) rpw_offsets_kernel(const uint64_t* __rest
                 const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
                 if ((int)threadIdx.x >= d) inc += t;
             }
-            if (p < P) patch_start[(size_t)b * (P + 1) + p] = carry + inc - v;
+            if (p < P) {
+                patch_start[(size_t)b * (P + 1) + p] = carry + inc - v;
+                s_start[p] = carry + inc - v;
+            }
             carry += __shfl_sync(0xffffffffu, inc, 31);
         }
         if (threadIdx.x == 0) patch_start[(size_t)b * (P + 1) + P] = carry;
+    }
+    __syncthreads();
+    // Work lists of the level-0 fit: every non-empty patch goes to the list of its size class (one
+    // shared-memory counter per class and block, one global atomic per class and block).  The order
+    // inside a list is arrival order; patches are independent, so it only affects scheduling.
+    constexpr int kPer = (8 * kMaxSectors + 255) / 256;
+    uint32_t rank[kPer];
+    int cls[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        const int p = threadIdx.x + k * 256;
+        cls[k] = -1;
+        if (p < P && s_cnt[p] > 0) {
+            int c = 0;
+            while (c < kNumFitClasses - 1 && s_cnt[p] > cb.hi[c]) ++c;
+            cls[k] = c;
+            rank[k] = atomicAdd(&s_cls[c], 1u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < kNumFitClasses) s_base[threadIdx.x] = s_cls[threadIdx.x] ? atomicAdd(&cls_count[threadIdx.x], s_cls[threadIdx.x]) : 0u;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        const int p = threadIdx.x + k * 256;
+        if (cls[k] >= 0) {
+            const uint32_t slot = s_base[cls[k]] + rank[k];
+            if (slot < cls_cap) cls_list[(size_t)cls[k] * cls_cap + slot] = make_uint4(s_start[p], s_cnt[p], (uint32_t)b * (uint32_t)P + (uint32_t)p, 0u);
+        }
     }
 }
 
@@ -145,26 +179,11 @@ __global__ void __launch_bounds__(kBinThreads) rpw_scatter_kernel(const float* _
                                                                  const uint32_t* __restrict__ chunk_base,
                                                                  const uint16_t* __restrict__ keys, const uint32_t* __restrict__ blk_hist,
                                                                  const uint32_t* __restrict__ patch_start, float4* __restrict__ sorted,
-                                                                 const uint32_t* __restrict__ patch_total, uint32_t* __restrict__ patch_order,
                                                                  int P, const FusionTable* __restrict__ fusion) {
     extern __shared__ uint32_t s_off[];  // [warps][P]
     constexpr int kWarps = kBinThreads / 32;
     constexpr int kPerWarp = kBinChunk / kWarps;
     const int b = blockIdx.y, chunk = blockIdx.x;
-    if (b == 0 && chunk == 0) {
-        // Longest-processing-time-first order for the fit kernel's worklist: patches ranked by
-        // their batch-wide point totals, largest first (ties by patch index).  Big far-ring
-        // patches are also the ones whose plane fit iterates longest, so they must start early.
-        for (int p = threadIdx.x; p < P; p += kBinThreads) s_off[p] = patch_total[p];
-        __syncthreads();
-        for (int p = threadIdx.x; p < P; p += kBinThreads) {
-            const uint32_t t = s_off[p];
-            uint32_t rank = 0;
-            for (int q = 0; q < P; ++q) { const uint32_t u = s_off[q]; rank += (u > t) || (u == t && q < p); }
-            patch_order[rank] = (uint32_t)p;
-        }
-        __syncthreads();
-    }
     const uint64_t off = scan_off[b];
     const uint32_t n = (uint32_t)(scan_off[b + 1] - off);
     const uint32_t base = (uint32_t)chunk * kBinChunk;
@@ -228,6 +247,9 @@ struct FitSmem {
 };
 
 constexpr int kRedMax = 16;
+// FitSmem::misc, in words: [0, 1] radix select, [2..4] heap-select replay, [5] eigensolve sub-partition,
+// [8..10] plane normal
+constexpr int kMiscWords = 16;
 constexpr int kCapTiny = 1024;   // points a 64-thread block keeps in shared memory
 constexpr int kCapSmall = 4096;  // points a 128-thread block keeps in shared memory
 constexpr int kCapLarge = 8192;  // 512-thread block; larger patches stream from L2
@@ -442,7 +464,10 @@ __device__ __forceinline__ void label_const(const FitArgs& A, const NodeRef& nd,
 
 // Strided loop over a node's points, four rows per trip: the loads of a trip are issued together
 // before any of its arithmetic (memory-level parallelism instead of one dependent chain per row).
-// body(i, x, y, z, m) sees point i with its current mask byte.
+// body(i, x, y, z, m) sees point i with its current mask byte.  (A layout where a thread owns four
+// CONSECUTIVE points and loads them with three LDS.128 needs a quarter of the load instructions but
+// measured 6 % slower end to end: the passes are bound by the dependent latency of a thread's own
+// instruction stream at the low occupancy shared memory allows, not by issue slots.)
 constexpr int kUnroll = 4;
 template <int TT, bool SMEM, bool WITH_MASK, typename F>
 __device__ __forceinline__ void for_points(const NodeView<SMEM>& nv, uint32_t n, F body) {
@@ -480,31 +505,53 @@ struct Tick {
 };
 
 // Plane normal from the scatter sums of the current inliers (fitPlanePCA, :86-95): smallest-
-// eigenvalue eigenvector, flipped to z >= 0.  Computed by warp 0, broadcast through shared memory.
+// eigenvalue eigenvector, flipped to z >= 0.  Computed by ONE warp, broadcast through shared memory.
+// The eigensolve is a long dependent chain of FP32 instructions that keeps an SM sub-partition's FMA
+// pipe about half busy; which warp runs it is chosen per node (qr_warp) so that the solves of the
+// blocks sharing an SM land on different sub-partitions instead of all on warp 0's.
 template <bool EXACT>
 __device__ __forceinline__ void plane_normal(const float (&cv)[6], float cnt, float* bc, float& nx, float& ny, float& nz,
-                                             unsigned long long* timing = nullptr) {
-    if (threadIdx.x < 32) {
+                                             int qr_warp, unsigned long long* timing = nullptr) {
+    if ((int)(threadIdx.x >> 5) == qr_warp) {
         float ax, ay, az;
         if (EXACT) {
-            const float d = cnt - 1.f;  // computeCovariance divides by n-1 (point_cloud_processor.cpp:84)
-            const float c0 = cv[0] / d, c1 = cv[1] / d, c2 = cv[2] / d, c3 = cv[3] / d, c4 = cv[4] / d, c5 = cv[5] / d;
             long long t0 = 0;
-            if (timing && threadIdx.x == 0) t0 = clock64();
-            eig3_smallest_qr(c0, c1, c2, c3, c4, c5, ax, ay, az);
-            if (timing && threadIdx.x == 0) atomicAdd(timing + 14, (unsigned long long)(clock64() - t0));
+            if (timing && (threadIdx.x & 31) == 0) t0 = clock64();
+            plane_normal_exact(cv, cnt - 1.f, ax, ay, az);  // computeCovariance divides by n-1 (point_cloud_processor.cpp:84)
+            if (timing && (threadIdx.x & 31) == 0) atomicAdd(timing + 14, (unsigned long long)(clock64() - t0));
         } else {
             smallest_eigvec_psd(cv[0], cv[1], cv[2], cv[3], cv[4], cv[5], ax, ay, az);
         }
         if (az < 0.f) { ax = -ax; ay = -ay; az = -az; }  // :93-95
-        if (threadIdx.x == 0) { bc[0] = ax; bc[1] = ay; bc[2] = az; }
+        if ((threadIdx.x & 31) == 0) { bc[0] = ax; bc[1] = ay; bc[2] = az; }
     }
     __syncthreads();
     nx = bc[0]; ny = bc[1]; nz = bc[2];
 }
 
+// Timeline record of one node (thread 0; debugging aid, off unless rpw_debug_fit_trace armed it).
+struct TraceScope {
+    const FitArgs& A; uint64_t t0; uint32_t n; uint16_t depth, cls;
+    __device__ __forceinline__ static uint64_t now() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+    __device__ __forceinline__ TraceScope(const FitArgs& a, uint32_t n_, int depth_, int cls_) : A(a), t0(0), n(n_), depth((uint16_t)depth_), cls((uint16_t)cls_) {
+        if (A.trace && threadIdx.x == 0) t0 = now();
+    }
+    __device__ __forceinline__ void done(int iters) {
+        if (A.trace && threadIdx.x == 0) {
+            const uint32_t slot = atomicAdd(A.trace_count, 1u);
+            if (slot < A.trace_cap) {
+                uint32_t smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                rpw_trace_rec r;
+                r.t_start_ns = t0; r.t_end_ns = now(); r.sm = smid; r.n = n; r.depth = depth; r.size_class = cls; r.iters = (uint32_t)iters;
+                A.trace[slot] = r;
+            }
+        }
+    }
+};
+
 template <int TT, bool SMEM, bool EXACT>
-__device__ void process_node(const FitArgs& A, const NodeRef nd, const int depth, FitSmem S) {
+__device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth, FitSmem S) {
     const FitParams& fp = A.fp;
     const uint32_t n = nd.n;
     const int tid = threadIdx.x;
@@ -514,7 +561,15 @@ __device__ void process_node(const FitArgs& A, const NodeRef nd, const int depth
     if (n < 3 || depth > fp.max_split_depth) {  // :111-113
         label_const<TT>(A, nd, 0);
         if (tid == 0) dbg_record(A, nd, depth, RPW_NODE_SMALL, 0, 0, -1, 0, 0, 0, 0, 0, 1, FLT_MAX, 0, 0);
-        return;
+        return 0;
+    }
+    // round-robin ticket of this SM: which sub-partition the node's eigensolves should run on
+    // (issued now, consumed after the load pass)
+    uint32_t ticket = 0;
+    if (tid == 0) {
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        ticket = atomicAdd(A.sm_ticket + (smid & 1023u), 1u);
     }
     NodeView<SMEM> nv;
     nv.s = S;
@@ -531,11 +586,21 @@ __device__ void process_node(const FitArgs& A, const NodeRef nd, const int depth
             mm[3] = fminf(mm[3], -v.x); mm[4] = fminf(mm[4], -v.y); mm[5] = fminf(mm[5], -v.z);
             if (depth == 0) sd[0] += range2d(v.x, v.y);
         };
+        // eight independent 16-byte loads in flight per thread: the pass is DRAM/L2-latency bound
         uint32_t i = tid;
+        for (; i + 7 * TT < n; i += 8 * TT) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(nv.src + i + u * TT);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) take(i + u * TT, v[u]);
+        }
         for (; i + 3 * TT < n; i += 4 * TT) {
-            const float4 v0 = __ldcg(nv.src + i), v1 = __ldcg(nv.src + i + TT);
-            const float4 v2 = __ldcg(nv.src + i + 2 * TT), v3 = __ldcg(nv.src + i + 3 * TT);
-            take(i, v0); take(i + TT, v1); take(i + 2 * TT, v2); take(i + 3 * TT, v3);
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = __ldcg(nv.src + i + u * TT);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) take(i + u * TT, v[u]);
         }
         for (; i < n; i += TT) take(i, __ldcg(nv.src + i));
     }
@@ -554,12 +619,12 @@ __device__ void process_node(const FitArgs& A, const NodeRef nd, const int depth
     if (area < 25.0f && depth > 0) {  // :126-129
         label_const<TT>(A, nd, 1);
         if (tid == 0) dbg_record(A, nd, depth, RPW_NODE_AREA, 0, 0, -1, 0, 0, 0, 0, 0, 1, FLT_MAX, 0, mean_dist);
-        return;
+        return 0;
     }
     if ((z_max - z_min) < 0.05f && n > 10) {  // :138-140
         label_const<TT>(A, nd, 1);
         if (tid == 0) dbg_record(A, nd, depth, RPW_NODE_FLAT, 0, 0, -1, 0, 0, 0, 0, 0, 1, FLT_MAX, 0, mean_dist);
-        return;
+        return 0;
     }
     // (the barrier inside block_min already made every thread's shared-memory stores visible)
 
@@ -581,7 +646,14 @@ __device__ void process_node(const FitArgs& A, const NodeRef nd, const int depth
         nv.set_mask(i, m ? 1 : 0);
         acc[0] += m ? 1.f : 0.f; acc[1] += m ? x : 0.f; acc[2] += m ? y : 0.f; acc[3] += m ? z : 0.f;
     });
+    if (tid == 0) {
+        uint32_t wid;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+        // warps of a block sit on consecutive hardware warp slots, slot % 4 is the sub-partition
+        S.misc[5] = ((ticket & 3u) - (wid & 3u)) & 3u;
+    }
     block_sum<TT, 4>(acc, S.red, phase);
+    const int qr_warp = (int)(S.misc[5] % (uint32_t)(TT / 32));
     if (acc[0] < 3.f) {
         // the three lowest-z points (std::partial_sort over indices, :173-181).  Parallel pick by
         // (z, index); if z ties reach across the cut the SET libstdc++'s heap-select keeps depends on
@@ -671,7 +743,7 @@ __device__ void process_node(const FitArgs& A, const NodeRef nd, const int depth
         if (cnt < 3.f) break;  // :196 — collapsed mask is kept (Q3)
         if (!have_cv) covariance_pass();
         tick(2);
-        plane_normal<EXACT>(cv, cnt, bc, nx, ny, nz, A.timing);
+        plane_normal<EXACT>(cv, cnt, bc, nx, ny, nz, qr_warp, A.timing);
         iters++;
         tick(3);
         // distances, new mask, convergence, residual of the fit just made, moments of the new mask
@@ -709,7 +781,7 @@ __device__ void process_node(const FitArgs& A, const NodeRef nd, const int depth
     if (!have_final) {
         if (cnt >= 3.f) {
             if (!have_cv) covariance_pass();
-            plane_normal<EXACT>(cv, cnt, bc, nx, ny, nz, A.timing);
+            plane_normal<EXACT>(cv, cnt, bc, nx, ny, nz, qr_warp, A.timing);
             float rs[1] = {0.f};
             for_points<TT, SMEM, true>(nv, n, [&](uint32_t, float x, float y, float z, uint8_t m) {
                 rs[0] += m ? plane_dist(x, y, z, cx, cy, cz, nx, ny, nz) : 0.f;
@@ -733,6 +805,13 @@ __device__ void process_node(const FitArgs& A, const NodeRef nd, const int depth
         {
             const float4* rec = A.sortedA + nd.start;
             uint32_t i = tid;
+            for (; i + 7 * TT < n; i += 8 * TT) {
+                uint32_t w[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) w[u] = __float_as_uint(__ldcg(&rec[i + u * TT].w));
+#pragma unroll
+                for (int u = 0; u < 8; ++u) A.labels[w[u]] = nv.mask(i + u * TT);
+            }
             for (; i + 3 * TT < n; i += 4 * TT) {
                 uint32_t w[4];
 #pragma unroll
@@ -744,7 +823,7 @@ __device__ void process_node(const FitArgs& A, const NodeRef nd, const int depth
         }
         if (tid == 0) dbg_record(A, nd, depth, RPW_NODE_FIT, iters, n_in, -1, cx, cy, cz, nx, ny, nz, residual, 0, mean_dist);
         tick(6);
-        return;
+        return iters;
     }
 
     // ---- split (:238-283) --------------------------------------------------------------------
@@ -829,6 +908,7 @@ __device__ void process_node(const FitArgs& A, const NodeRef nd, const int depth
         dbg_record(A, nd, depth, RPW_NODE_SPLIT, iters, n_in, axis, cx, cy, cz, nx, ny, nz, residual, median, mean_dist);
     }
     tick(7);
+    return iters;
 }
 
 __device__ __forceinline__ FitSmem carve_smem(unsigned char* raw, int cap, int warps) {
@@ -839,7 +919,7 @@ __device__ __forceinline__ FitSmem carve_smem(unsigned char* raw, int cap, int w
     S.red = S.z + cap;
     S.hist = reinterpret_cast<uint32_t*>(S.red + 2 * warps * kRedMax);
     S.misc = S.hist + 256;
-    S.m = reinterpret_cast<uint8_t*>(S.misc + 16);
+    S.m = reinterpret_cast<uint8_t*>(S.misc + kMiscWords);
     return S;
 }
 
@@ -861,18 +941,32 @@ __device__ __forceinline__ FitSmem carve_smem(unsigned char* raw, int cap, int w
 // ---------------------------------------------------------------------------------------------
 template <int TT, bool EXACT>
 __global__ void __launch_bounds__(TT, (TT <= 64 ? 8 : TT <= 128 ? 4 : TT <= 256 ? 3 : 2))
-rpw_fit_roots_kernel(FitArgs A, uint32_t n_lo, uint32_t n_hi, int cap) {
+rpw_fit_roots_kernel(FitArgs A, int cls, int cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const uint32_t id = blockIdx.x;
-    const uint32_t b = id % (uint32_t)A.n_scans, p = A.patch_order[id / (uint32_t)A.n_scans];
-    const uint32_t* ps = A.patch_start + (size_t)b * (A.P + 1) + p;
-    NodeRef nd;
-    nd.start = ps[0]; nd.n = ps[1] - ps[0]; nd.root = b * (uint32_t)A.P + p; nd.pad = 0;
-    if (nd.n == 0 || nd.n <= n_lo || nd.n > n_hi) return;  // :380 empty patch, or another class's patch
+    // The class's work list and its length are read together (independent addresses, one latency).
+    // The host sizes the grid from the previous launch group's counts; a block whose index is past
+    // the list leaves at once, and a grid shorter than the list strides over it.
+    const uint4* list = A.cls_list + (size_t)cls * A.cls_cap;
+    uint32_t i = blockIdx.x;
+    uint4 item = __ldcg(list + (i < A.cls_cap ? i : 0));
+    const uint32_t count = min(__ldcg(A.cls_count + cls), A.cls_cap);
+    if (i >= count) return;
     FitSmem S = carve_smem(smem_raw, cap, TT / 32);
-    if (nd.n <= (uint32_t)cap) process_node<TT, true, EXACT>(A, nd, 0, S);
-    else if constexpr (TT >= 512) process_node<TT, false, EXACT>(A, nd, 0, S);
-    if (threadIdx.x == 0) atomicAdd(A.stats + 1, 1u);
+    for (;;) {
+        NodeRef nd;
+        nd.start = item.x; nd.n = item.y; nd.root = item.z; nd.pad = 0;
+        const uint32_t next = i + gridDim.x;
+        if (next < count) item = __ldcg(list + next);  // in flight while this node is processed
+        TraceScope trace(A, nd.n, 0, cls);
+        int iters = 0;
+        if (nd.n <= (uint32_t)cap) iters = process_node<TT, true, EXACT>(A, nd, 0, S);
+        else if constexpr (TT >= 512) iters = process_node<TT, false, EXACT>(A, nd, 0, S);
+        trace.done(iters);
+        if (threadIdx.x == 0) atomicAdd(A.stats + 1, 1u);
+        if (next >= count) break;
+        i = next;
+        __syncthreads();  // the next node reuses the shared-memory arrays
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -904,6 +998,8 @@ __global__ void __launch_bounds__(kFitThreads, 1) rpw_fit_levels_kernel(FitArgs 
     FitSmem S = carve_smem(smem_raw, A.smem_cap, TT / 32);
     __shared__ uint32_t s_fetch;
     uint32_t n_done = 0, pre = 0, bar_target = 0;
+    if (blockIdx.x == 0 && threadIdx.x < kClsWords && A.host_counts)  // grid estimate for the next launch group (zero-copy store)
+        A.host_counts[threadIdx.x] = threadIdx.x < kNumFitClasses ? __ldcg(A.cls_count + threadIdx.x) : (uint32_t)A.n_scans;
     Tick ktick(A.timing);
     int level = 0;
     for (;;) {
@@ -924,8 +1020,11 @@ __global__ void __launch_bounds__(kFitThreads, 1) rpw_fit_levels_kernel(FitArgs 
             NodeRef nd;
             const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(q + id));
             nd.start = raw.x; nd.n = raw.y; nd.root = raw.z; nd.pad = 0;
-            if (nd.n <= (uint32_t)A.smem_cap) process_node<TT, true, EXACT>(A, nd, level, S);
-            else process_node<TT, false, EXACT>(A, nd, level, S);
+            TraceScope trace(A, nd.n, level, 0xFFFF);
+            int iters;
+            if (nd.n <= (uint32_t)A.smem_cap) iters = process_node<TT, true, EXACT>(A, nd, level, S);
+            else iters = process_node<TT, false, EXACT>(A, nd, level, S);
+            trace.done(iters);
             n_done++;
             if (A.timing && threadIdx.x == 0) ktick.last = clock64();
         }
@@ -969,20 +1068,35 @@ __global__ void rpw_normal_kernel(const float* __restrict__ sc, size_t count, in
     const size_t i = blockIdx.x;
     if (i >= count) return;
     const float* a = sc + i * 6;
-    const float s0 = a[0], s1 = a[1], s2 = a[2], s3 = a[3], s4 = a[4], s5 = a[5];
-    __syncwarp();
-    const long long t0 = clock64();
-    float nx, ny, nz;
-    if (mode == 1) {
-        const Eig3 E = eig3_sym(s0, s1, s2, s3, s4, s5);
-        nx = E.vec[0][0]; ny = E.vec[1][0]; nz = E.vec[2][0];
-    } else if (mode == 2) {  // the latency-restructured QR the fit kernel runs (must equal mode 1 bit for bit)
-        eig3_smallest_qr(s0, s1, s2, s3, s4, s5, nx, ny, nz);
-    } else {
-        smallest_eigvec_psd(s0, s1, s2, s3, s4, s5, nx, ny, nz);
+    float s0 = a[0], s1 = a[1], s2 = a[2], s3 = a[3], s4 = a[4], s5 = a[5];
+    float nx = 0.f, ny = 0.f, nz = 0.f;
+    long long t0 = 0, t1 = 0;
+    // two passes: the first warms the instruction cache, the second is the one timed and reported
+    // (its input depends on the first result so that the compiler cannot merge them)
+#pragma unroll 1
+    for (int rep = 0; rep < 2; ++rep) {
+        __syncwarp();
+        t0 = clock64();
+        if (mode == 1) {
+            const Eig3 E = eig3_sym(s0, s1, s2, s3, s4, s5);
+            nx = E.vec[0][0]; ny = E.vec[1][0]; nz = E.vec[2][0];
+        } else if (mode == 2) {  // the latency-restructured QR on the compiler's IEEE operations (must equal mode 1 bit for bit)
+            eig3_smallest_qr(s0, s1, s2, s3, s4, s5, nx, ny, nz);
+        } else if (mode == 3) {  // what the fit kernel runs: branch-free arithmetic + IEEE fallback (must equal mode 1 too)
+            ArithSpec ar;
+            eig3_smallest_qr_t(ar, s0, s1, s2, s3, s4, s5, nx, ny, nz);
+            if (!ar.ok()) eig3_smallest_qr_slow(s0, s1, s2, s3, s4, s5, nx, ny, nz);
+        } else if (mode == 4) {  // mode 3 without the fallback: nz = 2 marks solves whose operands left the fast range
+            ArithSpec ar;
+            eig3_smallest_qr_t(ar, s0, s1, s2, s3, s4, s5, nx, ny, nz);
+            if (!ar.ok()) { nx = 0.f; ny = 0.f; nz = 2.f; }
+        } else {
+            smallest_eigvec_psd(s0, s1, s2, s3, s4, s5, nx, ny, nz);
+        }
+        if (nz < 0.f) { nx = -nx; ny = -ny; nz = -nz; }
+        t1 = clock64();
+        if (nx != nx) s0 = nx;  // never true for finite input, but ties the second pass to the first
     }
-    if (nz < 0.f) { nx = -nx; ny = -ny; nz = -nz; }
-    const long long t1 = clock64();
     if (threadIdx.x == 0) {
         normals[i * 3] = nx; normals[i * 3 + 1] = ny; normals[i * 3 + 2] = nz;
         cycles[i] = (uint32_t)(t1 - t0);
@@ -998,32 +1112,33 @@ __global__ void rpw_atan2_kernel(const float* __restrict__ y, const float* __res
 // host-side launchers
 // =============================================================================================
 size_t fit_smem_bytes(int smem_cap, int threads) {
-    return (size_t)smem_cap * 13 + (2 * (threads / 32) * kRedMax + 256 + 16) * 4 + 16;
+    return (size_t)smem_cap * 13 + (2 * (threads / 32) * kRedMax + 256 + kMiscWords) * 4 + 16;
 }
 
 cudaError_t launch_bin(cudaStream_t st, const PointLayout& lay, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
-                       const ZoneModel& zm, uint16_t* keys, uint8_t* labels, uint32_t* blk_hist, uint32_t* patch_total,
+                       const ZoneModel& zm, uint16_t* keys, uint8_t* labels, uint32_t* blk_hist, uint32_t* cls_count,
                        const FusionTable* fusion, int max_chunks, int batch) {
     dim3 grid(max_chunks, batch);
     const size_t smem = (size_t)zm.num_patches * 4;
-    if (lay.vec4) rpw_bin_kernel<true><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, zm, keys, labels, blk_hist, patch_total, fusion);
-    else rpw_bin_kernel<false><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, zm, keys, labels, blk_hist, patch_total, fusion);
+    if (lay.vec4) rpw_bin_kernel<true><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, zm, keys, labels, blk_hist, cls_count, fusion);
+    else rpw_bin_kernel<false><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, zm, keys, labels, blk_hist, cls_count, fusion);
     return cudaGetLastError();
 }
 
 cudaError_t launch_offsets(cudaStream_t st, const uint64_t* scan_off, const uint32_t* chunk_base, uint32_t* blk_hist,
-                           uint32_t* patch_start, uint32_t* patch_total, int P, int batch) {
-    rpw_offsets_kernel<<<batch, 256, (size_t)(P + 1) * 4, st>>>(scan_off, chunk_base, blk_hist, patch_start, patch_total, P);
+                           uint32_t* patch_start, uint32_t* cls_count, uint4* cls_list, uint32_t cls_cap, int P, int batch) {
+    rpw_offsets_kernel<<<batch, 256, (size_t)(2 * P) * 4, st>>>(scan_off, chunk_base, blk_hist, patch_start, cls_count, cls_list, cls_cap,
+                                                                fit_class_bounds(), P);
     return cudaGetLastError();
 }
 
 cudaError_t launch_scatter(cudaStream_t st, const PointLayout& lay, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
                            const uint16_t* keys, const uint32_t* blk_hist, const uint32_t* patch_start, float4* sorted,
-                           const uint32_t* patch_total, uint32_t* patch_order, int P, const FusionTable* fusion, int max_chunks, int batch) {
+                           int P, const FusionTable* fusion, int max_chunks, int batch) {
     dim3 grid(max_chunks, batch);
     const size_t smem = (size_t)(kBinThreads / 32) * P * 4;
-    if (lay.vec4) rpw_scatter_kernel<true><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, keys, blk_hist, patch_start, sorted, patch_total, patch_order, P, fusion);
-    else rpw_scatter_kernel<false><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, keys, blk_hist, patch_start, sorted, patch_total, patch_order, P, fusion);
+    if (lay.vec4) rpw_scatter_kernel<true><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, keys, blk_hist, patch_start, sorted, P, fusion);
+    else rpw_scatter_kernel<false><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, keys, blk_hist, patch_start, sorted, P, fusion);
     return cudaGetLastError();
 }
 
@@ -1065,23 +1180,28 @@ cudaError_t fit_configure(int smem_cap, int* blocks_per_sm) {
     return cudaSuccess;
 }
 
+ClassBounds fit_class_bounds() {
+    ClassBounds cb;
+    for (int c = 0; c < kNumFitClasses; ++c) cb.hi[c] = kFitClasses[c].hi;
+    return cb;
+}
+
 template <int TT>
-static void launch_roots_tt(cudaStream_t st, const FitArgs& args, uint32_t lo, uint32_t hi, int cap) {
-    const unsigned grid = (unsigned)args.n_roots;
+static void launch_roots_tt(cudaStream_t st, const FitArgs& args, int cls, int cap, unsigned grid) {
     const size_t sm = fit_smem_bytes(cap, TT);
-    if (args.fp.exact_eig) rpw_fit_roots_kernel<TT, true><<<grid, TT, sm, st>>>(args, lo, hi, cap);
-    else rpw_fit_roots_kernel<TT, false><<<grid, TT, sm, st>>>(args, lo, hi, cap);
+    if (args.fp.exact_eig) rpw_fit_roots_kernel<TT, true><<<grid, TT, sm, st>>>(args, cls, cap);
+    else rpw_fit_roots_kernel<TT, false><<<grid, TT, sm, st>>>(args, cls, cap);
 }
 
 // size class cls in [0, kNumFitClasses): patches with kFitClasses[cls-1].hi < n <= kFitClasses[cls].hi
-cudaError_t launch_fit_roots(cudaStream_t st, const FitArgs& args, int cls) {
+cudaError_t launch_fit_roots(cudaStream_t st, const FitArgs& args, int cls, unsigned grid) {
     const FitClass& c = kFitClasses[cls];
-    const uint32_t lo = cls == 0 ? 0u : kFitClasses[cls - 1].hi;
+    if (grid == 0) grid = 1;
     switch (c.threads) {
-        case 64: launch_roots_tt<64>(st, args, lo, c.hi, c.cap); break;
-        case 128: launch_roots_tt<128>(st, args, lo, c.hi, c.cap); break;
-        case 256: launch_roots_tt<256>(st, args, lo, c.hi, c.cap); break;
-        default: launch_roots_tt<512>(st, args, lo, c.hi, c.cap); break;
+        case 64: launch_roots_tt<64>(st, args, cls, c.cap, grid); break;
+        case 128: launch_roots_tt<128>(st, args, cls, c.cap, grid); break;
+        case 256: launch_roots_tt<256>(st, args, cls, c.cap, grid); break;
+        default: launch_roots_tt<512>(st, args, cls, c.cap, grid); break;
     }
     return cudaGetLastError();
 }

@@ -24,14 +24,22 @@ struct FitArgs {
     uint8_t* gmask;            // per-slot mask scratch for nodes that do not fit in shared memory
     uint8_t* labels;           // per input point
     const uint32_t* patch_start;  // [batch][P + 1]
-    const uint32_t* patch_order;  // [P] patches by batch-wide size, largest first
+    const uint32_t* cls_count;    // [kNumFitClasses] non-empty root patches per size class (this launch group)
+    const uint4* cls_list;        // [kNumFitClasses][cls_cap] (start, n, scan * P + patch, -) per class, in arrival order
+    uint32_t* host_counts;        // mapped host memory: the class counts, [kClsWords-1] the group's scan count (grid estimate
+                                  // of the next launch group; never needed for correctness)
+    uint32_t cls_cap;
     float* root_mean;          // [batch * P] mean range of the root patch (Q4)
     NodeRef* queue[2];         // next-level queues, ping-pong by level parity
     uint32_t* q_count;         // [levels_cap] nodes enqueued for level l
     uint32_t* fetch_ctr;       // [levels_cap] dynamic fetch cursor of level l
     uint32_t* stats;           // [0] levels run (out) [1] nodes processed (accumulator) [2] block arrival [3] nodes (out)
     uint32_t* overflow;        // set if a queue would overflow
+    uint32_t* sm_ticket;       // [1024] per-SM round-robin counter (placement of the eigensolve warps)
     unsigned long long* timing; // optional [16] cycle accounting (rpw_debug_fit_timing)
+    rpw_trace_rec* trace;      // optional per-node timeline (rpw_debug_fit_trace)
+    uint32_t* trace_count;
+    uint32_t trace_cap;
     rpw_node_rec* dbg_nodes;   // optional
     uint32_t* dbg_count;
     uint32_t dbg_cap;
@@ -45,18 +53,21 @@ struct FitArgs {
 };
 
 constexpr int kNumFitClasses = 6;  // size classes of the level-0 fit kernel (rpw_kernels.cu: kFitClasses)
+constexpr int kClsWords = 16;      // words of a class-count array: counts [0, kNumFitClasses), scan count in the last
+struct ClassBounds { uint32_t hi[kNumFitClasses]; };  // class c holds patches with hi[c-1] < n <= hi[c]
+ClassBounds fit_class_bounds();
 size_t fit_smem_bytes(int smem_cap, int threads);
 cudaError_t fit_configure(int smem_cap, int* blocks_per_sm);
 
 cudaError_t launch_bin(cudaStream_t st, const PointLayout& lay, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
-                       const ZoneModel& zm, uint16_t* keys, uint8_t* labels, uint32_t* blk_hist, uint32_t* patch_total,
+                       const ZoneModel& zm, uint16_t* keys, uint8_t* labels, uint32_t* blk_hist, uint32_t* cls_count,
                        const FusionTable* fusion, int max_chunks, int batch);
 cudaError_t launch_offsets(cudaStream_t st, const uint64_t* scan_off, const uint32_t* chunk_base, uint32_t* blk_hist,
-                           uint32_t* patch_start, uint32_t* patch_total, int P, int batch);
+                           uint32_t* patch_start, uint32_t* cls_count, uint4* cls_list, uint32_t cls_cap, int P, int batch);
 cudaError_t launch_scatter(cudaStream_t st, const PointLayout& lay, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
                            const uint16_t* keys, const uint32_t* blk_hist, const uint32_t* patch_start, float4* sorted,
-                           const uint32_t* patch_total, uint32_t* patch_order, int P, const FusionTable* fusion, int max_chunks, int batch);
-cudaError_t launch_fit_roots(cudaStream_t st, const FitArgs& args, int size_class);
+                           int P, const FusionTable* fusion, int max_chunks, int batch);
+cudaError_t launch_fit_roots(cudaStream_t st, const FitArgs& args, int size_class, unsigned grid_blocks);
 cudaError_t launch_fit_levels(cudaStream_t st, const FitArgs& args, int grid_blocks);
 cudaError_t launch_eig3(cudaStream_t st, const float* mats, size_t count, float* evals, float* evecs);
 cudaError_t launch_normal(cudaStream_t st, const float* sc, size_t count, int mode, float* normals, uint32_t* cycles);

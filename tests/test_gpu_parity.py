@@ -156,9 +156,32 @@ def test_restructured_qr_is_the_generic_qr(h):
     A[2] = np.diag([1.0, 1.0, 0.0])
     A[3, :, :] = np.outer([1, 2, 3], [1, 2, 3])  # rank 1
     sc = np.stack([A[:, 0, 0], A[:, 1, 0], A[:, 1, 1], A[:, 2, 0], A[:, 2, 1], A[:, 2, 2]], 1).astype(np.float32)
+    # plane-like scatter matrices (what the fit feeds the solver), tiny and huge scales, exact zeros
+    planes = []
+    for i in range(20000):
+        ext = rng.uniform(0.5, 30, 2)
+        p = rng.normal(size=(int(rng.integers(3, 400)), 3)) * np.array([ext[0], ext[1], rng.uniform(0.0, 0.2)])
+        a, b = rng.uniform(-0.3, 0.3, 2)
+        p[:, 2] += a * p[:, 0] + b * p[:, 1]
+        d = (p - p.mean(0)).astype(np.float32)
+        S = (d.T @ d) / np.float32(len(p) - 1)
+        planes.append([S[0, 0], S[1, 0], S[1, 1], S[2, 0], S[2, 1], S[2, 2]])
+    planes = np.array(planes, np.float32)
+    planes[:200] *= np.float32(1e-30)
+    planes[200:400] *= np.float32(1e30)
+    planes[400:600, 3:5] = 0
+    planes[600:700, 1] = 0
+    planes[700:800] *= np.float32(1e-38)
+    sc = np.concatenate([sc, planes])
     generic, _ = h.debug_normal(sc, 1)
     fast, _ = h.debug_normal(sc, 2)
     assert np.array_equal(generic.view(np.uint32), fast.view(np.uint32))
+    spec, _ = h.debug_normal(sc, 3)  # branch-free arithmetic + IEEE fallback: what the fit kernel runs
+    assert np.array_equal(generic.view(np.uint32), spec.view(np.uint32))
+    raw, _ = h.debug_normal(sc, 4)   # without the fallback: in-range solves must already be exact, and most are in range
+    inr = raw[:, 2] != 2.0
+    assert np.array_equal(generic[inr].view(np.uint32), raw[inr].view(np.uint32))
+    assert inr[-len(planes) + 800:].mean() > 0.99
 
 
 def test_closed_form_solver_accuracy(h):
