@@ -108,7 +108,7 @@ def cpu_reference_throughput(scans, cfg, seconds_budget, threads):
         kind = "port"
     ccfg = oracle_lib.to_cfg(cfg)
     t_one = ref.time_scan(ccfg, scans[0], 1)  # warm-up + estimate
-    n_jobs = max(threads, min(len(scans) * 4, int(seconds_budget / max(t_one, 1e-4) * threads)))
+    n_jobs = max(threads, min(4000, int(seconds_budget / max(t_one, 1e-4))))  # ~seconds_budget CPU-seconds of work in total
     jobs = [scans[i % len(scans)] for i in range(n_jobs)]
     t0 = time.perf_counter()
     with ThreadPoolExecutor(max_workers=threads) as ex:
@@ -177,7 +177,7 @@ def main():
     ap.add_argument("--solver", default="eigen_qr", choices=["eigen_qr", "closed_form"],
                     help="plane-normal solver: eigen_qr = reference-faithful default, closed_form = faster (see include/rpw_b200.h)")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="handles the end-to-end arm ping-pongs over (copy/compute overlap)")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU-seconds of work in the cpu_baseline sample (summed over threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -407,7 +407,7 @@ def main():
                        "l2": f"batch is {total * 16 / 1e6:.0f} MB of float4 input per GPU > 126 MB L2 (no flush needed)"},
             "mpoints_per_sec": value * POINTS_PER_SCAN / 1e6,
             "hbm_fraction_whole_path": ALG_BYTES_PER_POINT * (value / world) * POINTS_PER_SCAN / 1e9 / peak,
-            "roofline": {"bound": "hbm", "kernel": "fit phase = rpw_fit_roots_kernel<64|128|256> (three size classes, concurrent streams) + rpw_fit_levels_kernel, timed as one unit", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "fit phase = rpw_fit_roots_kernel<64|128|256|512> (six size classes on concurrent prioritised streams) + rpw_fit_levels_kernel, timed as one unit", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_point": ALG_BYTES_PER_POINT, "ms_per_launch": fit_ms},
             "kernels": kernels,

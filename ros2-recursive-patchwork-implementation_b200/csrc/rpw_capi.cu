@@ -43,7 +43,6 @@ struct rpw_handle {
     Lane lane[kLanes];
     cudaEvent_t ev_call = nullptr;
     uint32_t* d_dbg_count = nullptr;
-    uint32_t* d_sm_ticket = nullptr;
     int n_waves = 1;  // launch groups per call (1: within one call more groups only add tails)
     size_t cap_points = 0, cap_batch = 0;
     int P = 0;
@@ -225,7 +224,7 @@ void rpw_destroy(rpw_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_in); cudaFree(h->d_keys); cudaFree(h->d_labels); cudaFree(h->d_sortedA); cudaFree(h->d_bufB);
-    cudaFree(h->d_bufC); cudaFree(h->d_gmask); cudaFree(h->d_dbg_count); cudaFree(h->d_sm_ticket); cudaFree(h->d_trace); cudaFree(h->d_trace_count);
+    cudaFree(h->d_bufC); cudaFree(h->d_gmask); cudaFree(h->d_dbg_count); cudaFree(h->d_trace); cudaFree(h->d_trace_count);
     cudaFree(h->d_scan_off); cudaFree(h->d_chunk_base); cudaFree(h->d_dbg_nodes); cudaFree(h->d_timing); cudaFree(h->d_fusion);
     if (h->h_fusion) cudaFreeHost(h->h_fusion);
     free_patch_buffers(h);
@@ -307,8 +306,6 @@ int rpw_create(const rpw_config* cfg, int device, size_t max_total_points, size_
     TRYC(cudaEventCreateWithFlags(&h->ev_call, cudaEventDisableTiming));
     TRYC(cudaMalloc(&h->d_dbg_count, sizeof(uint32_t)));
     TRYC(cudaMemset(h->d_dbg_count, 0, sizeof(uint32_t)));
-    TRYC(cudaMalloc(&h->d_sm_ticket, 1024 * sizeof(uint32_t)));
-    TRYC(cudaMemset(h->d_sm_ticket, 0, 1024 * sizeof(uint32_t)));
     const size_t N = max_total_points;
     TRYC(cudaMalloc(&h->d_in, N * 16));
     h->d_in_bytes = N * 16;
@@ -507,7 +504,6 @@ static int run_group(rpw_handle* h, rpw_handle::Lane& L, cudaStream_t st, const 
     A.q_count = L.d_counters + h->levels_cap;
     A.stats = L.d_counters + 2 * (size_t)h->levels_cap;
     A.overflow = A.stats + 8;
-    A.sm_ticket = h->d_sm_ticket;
     A.timing = h->timing_enabled ? h->d_timing : nullptr;
     A.trace = h->trace_cap ? h->d_trace : nullptr;
     A.trace_count = h->d_trace_count;

@@ -247,8 +247,7 @@ struct FitSmem {
 };
 
 constexpr int kRedMax = 16;
-// FitSmem::misc, in words: [0, 1] radix select, [2..4] heap-select replay, [5] eigensolve sub-partition,
-// [8..10] plane normal
+// FitSmem::misc, in words: [0, 1] radix select, [2..4] heap-select replay, [8..10] plane normal
 constexpr int kMiscWords = 16;
 constexpr int kCapTiny = 1024;   // points a 64-thread block keeps in shared memory
 constexpr int kCapSmall = 4096;  // points a 128-thread block keeps in shared memory
@@ -505,25 +504,24 @@ struct Tick {
 };
 
 // Plane normal from the scatter sums of the current inliers (fitPlanePCA, :86-95): smallest-
-// eigenvalue eigenvector, flipped to z >= 0.  Computed by ONE warp, broadcast through shared memory.
-// The eigensolve is a long dependent chain of FP32 instructions that keeps an SM sub-partition's FMA
-// pipe about half busy; which warp runs it is chosen per node (qr_warp) so that the solves of the
-// blocks sharing an SM land on different sub-partitions instead of all on warp 0's.
+// eigenvalue eigenvector, flipped to z >= 0.  Computed by warp 0, broadcast through shared memory.
+// (Which warp runs the solve makes no measurable difference: first, last, or spread round-robin over
+// the SM's sub-partitions all give the same throughput.)
 template <bool EXACT>
 __device__ __forceinline__ void plane_normal(const float (&cv)[6], float cnt, float* bc, float& nx, float& ny, float& nz,
-                                             int qr_warp, unsigned long long* timing = nullptr) {
-    if ((int)(threadIdx.x >> 5) == qr_warp) {
+                                             unsigned long long* timing = nullptr) {
+    if (threadIdx.x < 32) {
         float ax, ay, az;
         if (EXACT) {
             long long t0 = 0;
-            if (timing && (threadIdx.x & 31) == 0) t0 = clock64();
+            if (timing && threadIdx.x == 0) t0 = clock64();
             plane_normal_exact(cv, cnt - 1.f, ax, ay, az);  // computeCovariance divides by n-1 (point_cloud_processor.cpp:84)
-            if (timing && (threadIdx.x & 31) == 0) atomicAdd(timing + 14, (unsigned long long)(clock64() - t0));
+            if (timing && threadIdx.x == 0) atomicAdd(timing + 14, (unsigned long long)(clock64() - t0));
         } else {
             smallest_eigvec_psd(cv[0], cv[1], cv[2], cv[3], cv[4], cv[5], ax, ay, az);
         }
         if (az < 0.f) { ax = -ax; ay = -ay; az = -az; }  // :93-95
-        if ((threadIdx.x & 31) == 0) { bc[0] = ax; bc[1] = ay; bc[2] = az; }
+        if (threadIdx.x == 0) { bc[0] = ax; bc[1] = ay; bc[2] = az; }
     }
     __syncthreads();
     nx = bc[0]; ny = bc[1]; nz = bc[2];
@@ -562,14 +560,6 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
         label_const<TT>(A, nd, 0);
         if (tid == 0) dbg_record(A, nd, depth, RPW_NODE_SMALL, 0, 0, -1, 0, 0, 0, 0, 0, 1, FLT_MAX, 0, 0);
         return 0;
-    }
-    // round-robin ticket of this SM: which sub-partition the node's eigensolves should run on
-    // (issued now, consumed after the load pass)
-    uint32_t ticket = 0;
-    if (tid == 0) {
-        uint32_t smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        ticket = atomicAdd(A.sm_ticket + (smid & 1023u), 1u);
     }
     NodeView<SMEM> nv;
     nv.s = S;
@@ -646,14 +636,7 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
         nv.set_mask(i, m ? 1 : 0);
         acc[0] += m ? 1.f : 0.f; acc[1] += m ? x : 0.f; acc[2] += m ? y : 0.f; acc[3] += m ? z : 0.f;
     });
-    if (tid == 0) {
-        uint32_t wid;
-        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
-        // warps of a block sit on consecutive hardware warp slots, slot % 4 is the sub-partition
-        S.misc[5] = ((ticket & 3u) - (wid & 3u)) & 3u;
-    }
     block_sum<TT, 4>(acc, S.red, phase);
-    const int qr_warp = (int)(S.misc[5] % (uint32_t)(TT / 32));
     if (acc[0] < 3.f) {
         // the three lowest-z points (std::partial_sort over indices, :173-181).  Parallel pick by
         // (z, index); if z ties reach across the cut the SET libstdc++'s heap-select keeps depends on
@@ -743,7 +726,7 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
         if (cnt < 3.f) break;  // :196 — collapsed mask is kept (Q3)
         if (!have_cv) covariance_pass();
         tick(2);
-        plane_normal<EXACT>(cv, cnt, bc, nx, ny, nz, qr_warp, A.timing);
+        plane_normal<EXACT>(cv, cnt, bc, nx, ny, nz, A.timing);
         iters++;
         tick(3);
         // distances, new mask, convergence, residual of the fit just made, moments of the new mask
@@ -781,7 +764,7 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
     if (!have_final) {
         if (cnt >= 3.f) {
             if (!have_cv) covariance_pass();
-            plane_normal<EXACT>(cv, cnt, bc, nx, ny, nz, qr_warp, A.timing);
+            plane_normal<EXACT>(cv, cnt, bc, nx, ny, nz, A.timing);
             float rs[1] = {0.f};
             for_points<TT, SMEM, true>(nv, n, [&](uint32_t, float x, float y, float z, uint8_t m) {
                 rs[0] += m ? plane_dist(x, y, z, cx, cy, cz, nx, ny, nz) : 0.f;

@@ -35,7 +35,6 @@ struct FitArgs {
     uint32_t* fetch_ctr;       // [levels_cap] dynamic fetch cursor of level l
     uint32_t* stats;           // [0] levels run (out) [1] nodes processed (accumulator) [2] block arrival [3] nodes (out)
     uint32_t* overflow;        // set if a queue would overflow
-    uint32_t* sm_ticket;       // [1024] per-SM round-robin counter (placement of the eigensolve warps)
     unsigned long long* timing; // optional [16] cycle accounting (rpw_debug_fit_timing)
     rpw_trace_rec* trace;      // optional per-node timeline (rpw_debug_fit_trace)
     uint32_t* trace_count;
