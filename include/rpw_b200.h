@@ -197,7 +197,19 @@ typedef struct rpw_sensor_cloud {
 int rpw_segment_fused(rpw_handle* h, const rpw_sensor_cloud* sensors, size_t n_sensors, size_t stride_bytes,
                       uint8_t* const* labels_out, rpw_stats* stats);
 
-/* One scan, with the two clouds the reference returns, in the reference's order.
+/* Result assembly (RP/src/recursive_patchwork.cpp:402-419) for the scans of this handle's LAST rpw_segment* call
+ * (host or device path, single, batch, PointCloud2 or fused), done on the device by a stable compaction over
+ * the labels: per scan the ground cloud (ground points in input order) and the non-ground cloud (non-ground
+ * points in input order, then the beyond-radius points in input order), packed xyz (12 bytes per point);
+ * fused frames in vehicle coordinates.  Dropped (non-finite) and ego points are in neither, as in the reference.
+ * Both buffers hold 3 * (total points of the call) floats; the clouds of scan b start at record
+ * (offset of scan b inside the call).  on_device != 0: device buffers (must not alias the input); else
+ * host buffers, either may be NULL, only the used part of every scan's range is written.
+ * counts: HOST array, 2 per scan: ground points, non-ground points.  The input of the last call must still
+ * be alive (device path: the caller's d_points). */
+int rpw_last_clouds(rpw_handle* h, float* ground_xyz, float* nonground_xyz, int on_device, uint64_t* counts);
+
+/* One scan, with the two clouds the reference returns, in the reference's order (rpw_segment + rpw_last_clouds).
  * ground_xyz / nonground_xyz: caller buffers of 3*n floats each (either may be NULL). */
 int rpw_segment_clouds(rpw_handle* h, const float* xyz, size_t n, size_t stride_bytes, uint8_t* labels_out,
                        float* ground_xyz, size_t* n_ground, float* nonground_xyz, size_t* n_nonground);

@@ -53,7 +53,7 @@ NODE_DTYPE = np.dtype([("scan", "<i4"), ("root", "<i4"), ("depth", "<i4"), ("sta
 # Every symbol include/rpw_b200.h declares (tests check that the library exports all of them).
 EXPORTS = ["rpw_default_config", "rpw_zone_model", "rpw_create", "rpw_destroy", "rpw_set_config", "rpw_get_config",
            "rpw_set_plane_solver", "rpw_set_stream", "rpw_last_error", "rpw_segment", "rpw_segment_batch", "rpw_segment_batch_async", "rpw_wait",
-           "rpw_segment_pc2", "rpw_segment_fused", "rpw_segment_clouds", "rpw_segment_device", "rpw_debug_keys", "rpw_debug_enable_nodes", "rpw_debug_nodes",
+           "rpw_segment_pc2", "rpw_segment_fused", "rpw_segment_clouds", "rpw_last_clouds", "rpw_segment_device", "rpw_debug_keys", "rpw_debug_enable_nodes", "rpw_debug_nodes",
            "rpw_debug_eig3", "rpw_debug_normal", "rpw_debug_atan2", "rpw_debug_fit_timing", "rpw_debug_fit_trace", "rpw_profile_enable", "rpw_profile_read", "rpw_host_alloc", "rpw_host_free", "rpw_kernel_launches", "rpw_abi_version"]
 
 _lib = None
@@ -95,6 +95,8 @@ def load_library() -> C.CDLL:
     lib.rpw_segment_fused.restype = C.c_int
     lib.rpw_segment_clouds.argtypes = [vp, vp, sz, sz, vp, vp, C.POINTER(sz), vp, C.POINTER(sz)]
     lib.rpw_segment_clouds.restype = C.c_int
+    lib.rpw_last_clouds.argtypes = [vp, vp, vp, C.c_int, C.POINTER(C.c_uint64)]
+    lib.rpw_last_clouds.restype = C.c_int
     lib.rpw_segment_device.argtypes = [vp, vp, C.POINTER(C.c_uint64), sz, vp]; lib.rpw_segment_device.restype = C.c_int
     lib.rpw_debug_keys.argtypes = [vp, vp, sz]; lib.rpw_debug_keys.restype = C.c_int
     lib.rpw_debug_enable_nodes.argtypes = [vp, C.c_int]; lib.rpw_debug_enable_nodes.restype = C.c_int
@@ -270,6 +272,25 @@ class Handle:
         self._check(self.lib.rpw_segment_clouds(self._h, a.ctypes.data, n, a.shape[1] * 4, labels.ctypes.data,
                                                 g.ctypes.data, C.byref(n_g), ng.ctypes.data, C.byref(n_ng)))
         return g[:n_g.value], ng[:n_ng.value], labels
+
+    def last_clouds(self, scan_counts, total=None):
+        """Ground / non-ground clouds of the last call's scans, assembled on the device (host copies).
+        scan_counts: points per scan of that call.  Returns a list of (ground, nonground) arrays."""
+        n = np.asarray(scan_counts, np.uint64)
+        off = np.zeros(len(n) + 1, np.uint64); off[1:] = np.cumsum(n)
+        total = int(off[-1]) if total is None else total
+        g = np.empty((max(total, 1), 3), np.float32)
+        ng = np.empty((max(total, 1), 3), np.float32)
+        cnt = (C.c_uint64 * (2 * len(n)))()
+        self._check(self.lib.rpw_last_clouds(self._h, g.ctypes.data, ng.ctypes.data, 0, cnt))
+        return [(g[int(off[b]):int(off[b]) + int(cnt[2 * b])].copy(), ng[int(off[b]):int(off[b]) + int(cnt[2 * b + 1])].copy())
+                for b in range(len(n))]
+
+    def last_clouds_device(self, d_ground_ptr: int, d_nonground_ptr: int, n_scans: int):
+        """Same with caller-provided device buffers (3 floats per point of the call each); returns counts [n_scans, 2]."""
+        cnt = (C.c_uint64 * (2 * n_scans))()
+        self._check(self.lib.rpw_last_clouds(self._h, C.c_void_p(d_ground_ptr), C.c_void_p(d_nonground_ptr), 1, cnt))
+        return np.array(cnt[:], np.uint64).reshape(n_scans, 2)
 
     def segment_device(self, d_points_ptr: int, scan_offsets, d_labels_ptr: int):
         off = np.ascontiguousarray(scan_offsets, dtype=np.uint64)

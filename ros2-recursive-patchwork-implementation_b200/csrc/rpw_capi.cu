@@ -75,6 +75,16 @@ struct rpw_handle {
     rpw_node* d_dbg_nodes = nullptr;
     unsigned long long* d_timing = nullptr;  // [16], allocated by rpw_debug_fit_timing
     rpw_trace_rec* d_trace = nullptr;        // rpw_debug_fit_trace
+    // result assembly (rpw_last_clouds): what the last call ran on, and lazily allocated buffers
+    const float* last_pts = nullptr;
+    PointLayout last_lay{};
+    uint8_t* last_labels = nullptr;
+    bool last_fused = false;
+    uint32_t* d_cmp_cnt = nullptr;      // [chunk rows][4] label counts per 4096-point chunk
+    uint32_t* d_scan_counts = nullptr;  // [cap_batch][2] ground / non-ground points per scan
+    uint32_t* h_scan_counts = nullptr;  // pinned copy
+    float* d_cloud_g = nullptr;         // 3 floats x cap_points each, only for host-bound clouds
+    float* d_cloud_ng = nullptr;
     uint32_t* d_trace_count = nullptr;
     uint32_t trace_cap = 0;
     bool timing_enabled = false;
@@ -224,7 +234,8 @@ void rpw_destroy(rpw_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_in); cudaFree(h->d_keys); cudaFree(h->d_labels); cudaFree(h->d_sortedA); cudaFree(h->d_bufB);
-    cudaFree(h->d_bufC); cudaFree(h->d_gmask); cudaFree(h->d_dbg_count); cudaFree(h->d_trace); cudaFree(h->d_trace_count);
+    cudaFree(h->d_bufC); cudaFree(h->d_gmask); cudaFree(h->d_dbg_count); cudaFree(h->d_trace); cudaFree(h->d_trace_count); cudaFree(h->d_cmp_cnt); cudaFree(h->d_scan_counts); cudaFree(h->d_cloud_g); cudaFree(h->d_cloud_ng);
+    if (h->h_scan_counts) cudaFreeHost(h->h_scan_counts);
     cudaFree(h->d_scan_off); cudaFree(h->d_chunk_base); cudaFree(h->d_dbg_nodes); cudaFree(h->d_timing); cudaFree(h->d_fusion);
     if (h->h_fusion) cudaFreeHost(h->h_fusion);
     free_patch_buffers(h);
@@ -564,6 +575,7 @@ static int run_group(rpw_handle* h, rpw_handle::Lane& L, cudaStream_t st, const 
 // Enqueues K1..K3 for scans [0, batch) whose points are device resident at `d_pts`.
 static int run_pipeline(rpw_handle* h, const float* d_pts, const PointLayout& lay, uint8_t* d_labels, size_t batch) {
     h->launches_call = 0;
+    h->last_pts = d_pts; h->last_lay = lay; h->last_labels = d_labels; h->last_fused = h->fusion_arg != nullptr;
     // stats[0] (levels) and stats[3] (nodes) accumulate over the call's launch groups
     for (auto& L : h->lane) {
         uint32_t* st = L.d_counters + 2 * (size_t)h->levels_cap;
@@ -866,34 +878,75 @@ int rpw_segment_fused(rpw_handle* h, const rpw_sensor_cloud* sensors, size_t n_s
     return RPW_OK;
 }
 
+int rpw_last_clouds(rpw_handle* h, float* ground_xyz, float* nonground_xyz, int on_device, uint64_t* counts) {
+    if (!h) return RPW_ERR_BAD_ARG;
+    if (!counts) RPW_FAIL(h, RPW_ERR_BAD_ARG, "counts must not be NULL");
+    const size_t batch = h->last_batch;
+    for (size_t b = 0; b < 2 * batch; ++b) counts[b] = 0;
+    if (batch == 0 || h->last_total == 0) return RPW_OK;
+    if (!h->last_pts || !h->last_labels) RPW_FAIL(h, RPW_ERR_BAD_ARG, "no segmented scans to assemble clouds from");
+    if (on_device && (!ground_xyz || !nonground_xyz)) RPW_FAIL(h, RPW_ERR_BAD_ARG, "device cloud buffers must not be NULL");
+    RPW_CUDA(h, cudaSetDevice(h->device));
+    if (!h->d_cmp_cnt) {
+        const size_t rows = h->cap_points / kBinChunk + h->cap_batch + 1;
+        RPW_CUDA(h, cudaMalloc(&h->d_cmp_cnt, rows * 4 * sizeof(uint32_t)));
+        RPW_CUDA(h, cudaMalloc(&h->d_scan_counts, h->cap_batch * 2 * sizeof(uint32_t)));
+        RPW_CUDA(h, cudaMallocHost(&h->h_scan_counts, h->cap_batch * 2 * sizeof(uint32_t)));
+    }
+    float* dg = ground_xyz;
+    float* dng = nonground_xyz;
+    if (!on_device) {
+        if (!h->d_cloud_g) {
+            RPW_CUDA(h, cudaMalloc(&h->d_cloud_g, h->cap_points * 3 * sizeof(float)));
+            RPW_CUDA(h, cudaMalloc(&h->d_cloud_ng, h->cap_points * 3 * sizeof(float)));
+        }
+        dg = h->d_cloud_g; dng = h->d_cloud_ng;
+    }
+    const uint64_t* so = h->last_off.data();
+    uint64_t max_n = 0;
+    for (size_t i = 0; i < batch; ++i) max_n = so[i + 1] - so[i] > max_n ? so[i + 1] - so[i] : max_n;
+    const int max_chunks = (int)((max_n + kBinChunk - 1) / kBinChunk);
+    RPW_CUDA(h, launch_compact(h->stream, h->last_lay, h->last_pts, h->last_labels, h->d_scan_off, h->d_chunk_base, h->d_cmp_cnt,
+                               h->last_fused ? h->d_fusion : nullptr, dg, dng, h->d_scan_counts, max_chunks, (int)batch));
+    h->launches += 2;
+    RPW_CUDA(h, cudaMemcpyAsync(h->h_scan_counts, h->d_scan_counts, batch * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    RPW_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (size_t b = 0; b < 2 * batch; ++b) counts[b] = h->h_scan_counts[b];
+    if (!on_device) {
+        // exactly the bytes of the clouds: scan b's clouds start at record (scan offset b) of the caller's buffers
+        for (size_t b = 0; b < batch; ++b) {
+            const size_t o = (size_t)(so[b] - so[0]) * 3;
+            if (ground_xyz && counts[2 * b])
+                RPW_CUDA(h, cudaMemcpyAsync(ground_xyz + o, dg + o, counts[2 * b] * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+            if (nonground_xyz && counts[2 * b + 1])
+                RPW_CUDA(h, cudaMemcpyAsync(nonground_xyz + o, dng + o, counts[2 * b + 1] * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        }
+        RPW_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    return RPW_OK;
+}
+
 int rpw_segment_clouds(rpw_handle* h, const float* xyz, size_t n, size_t stride_bytes, uint8_t* labels_out,
                        float* ground_xyz, size_t* n_ground, float* nonground_xyz, size_t* n_nonground) {
     if (!h) return RPW_ERR_BAD_ARG;
     if (n_ground) *n_ground = 0;
     if (n_nonground) *n_nonground = 0;
     if (n == 0) return RPW_OK;
-    std::vector<uint8_t> tmp;
-    uint8_t* lab = labels_out;
-    if (!lab) { tmp.resize(n); lab = tmp.data(); }
-    int rc = rpw_segment(h, xyz, n, stride_bytes, lab, nullptr);
+    int rc;
+    if (labels_out) {
+        rc = rpw_segment(h, xyz, n, stride_bytes, labels_out, nullptr);
+    } else {
+        rc = ensure_stage(h, n * stride_bytes);
+        if (rc != RPW_OK) return rc;
+        rc = rpw_segment(h, xyz, n, stride_bytes, h->h_stage_labels, nullptr);
+    }
     if (rc != RPW_OK) return rc;
-    // Cloud assembly in the reference's order (RP/src/recursive_patchwork.cpp:402-419): ground in
-    // input order; non-ground in input order, then the beyond-radius points in input order.
-    const size_t sf = stride_bytes / 4;
-    size_t g = 0, ng = 0;
-    for (size_t i = 0; i < n; ++i) {
-        const float* p = xyz + i * sf;
-        if (lab[i] == RPW_LABEL_GROUND) { if (ground_xyz) { ground_xyz[3 * g] = p[0]; ground_xyz[3 * g + 1] = p[1]; ground_xyz[3 * g + 2] = p[2]; } ++g; }
-        else if (lab[i] == RPW_LABEL_NONGROUND) { if (nonground_xyz) { nonground_xyz[3 * ng] = p[0]; nonground_xyz[3 * ng + 1] = p[1]; nonground_xyz[3 * ng + 2] = p[2]; } ++ng; }
-    }
-    for (size_t i = 0; i < n; ++i) {
-        if (lab[i] != RPW_LABEL_BEYOND) continue;
-        const float* p = xyz + i * sf;
-        if (nonground_xyz) { nonground_xyz[3 * ng] = p[0]; nonground_xyz[3 * ng + 1] = p[1]; nonground_xyz[3 * ng + 2] = p[2]; }
-        ++ng;
-    }
-    if (n_ground) *n_ground = g;
-    if (n_nonground) *n_nonground = ng;
+    // cloud assembly in the reference's order (RP/src/recursive_patchwork.cpp:402-419) by the K4 kernels
+    uint64_t counts[2] = {0, 0};
+    rc = rpw_last_clouds(h, ground_xyz, nonground_xyz, 0, counts);
+    if (rc != RPW_OK) return rc;
+    if (n_ground) *n_ground = (size_t)counts[0];
+    if (n_nonground) *n_nonground = (size_t)counts[1];
     return RPW_OK;
 }
 

@@ -1032,6 +1032,122 @@ __global__ void __launch_bounds__(kFitThreads, 1) rpw_fit_levels_kernel(FitArgs 
 }
 
 // =============================================================================================
+// K4: result assembly on the device (RP/src/recursive_patchwork.cpp:402-419): the two clouds the
+// reference returns, in the reference's order -- ground points in input order; non-ground points
+// in input order followed by the beyond-radius points in input order.  Stable stream compaction
+// by label: K4a counts labels per 4096-point chunk, K4b derives every chunk's bases from the
+// counts of the chunks before it (no scan kernel, no atomics claiming slots: the order is
+// deterministic) and writes packed 12-byte xyz records.  Fused frames are written in vehicle
+// coordinates (the same fuse_point as K1); ego and non-finite points appear in neither cloud.
+// Cloud slot i of scan b is record (scan_off[b] + i) of the output buffers.
+// =============================================================================================
+__global__ void __launch_bounds__(kBinThreads) rpw_compact_count_kernel(const uint8_t* __restrict__ labels, const uint64_t* __restrict__ scan_off,
+                                                                       const uint32_t* __restrict__ chunk_base, uint32_t* __restrict__ cnt) {
+    __shared__ uint32_t s_c[3];
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const uint64_t off = scan_off[b];
+    const uint32_t n = (uint32_t)(scan_off[b + 1] - off);
+    const uint32_t base = (uint32_t)chunk * kBinChunk;
+    if (base >= n) return;
+    if (threadIdx.x < 3) s_c[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t c0 = 0, c1 = 0, c2 = 0;
+#pragma unroll 4
+    for (int k = 0; k < kBinChunk / kBinThreads; ++k) {
+        const uint32_t i = base + k * kBinThreads + threadIdx.x;
+        const uint32_t l = i < n ? labels[off + i] : 255u;
+        c0 += l == 0; c1 += l == 1; c2 += l == 2;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        c0 += __shfl_xor_sync(0xffffffffu, c0, d);
+        c1 += __shfl_xor_sync(0xffffffffu, c1, d);
+        c2 += __shfl_xor_sync(0xffffffffu, c2, d);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_c[0], c0); atomicAdd(&s_c[1], c1); atomicAdd(&s_c[2], c2); }
+    __syncthreads();
+    if (threadIdx.x < 3) cnt[((size_t)chunk_base[b] + chunk) * 4 + threadIdx.x] = s_c[threadIdx.x];
+}
+
+template <bool VEC4>
+__global__ void __launch_bounds__(kBinThreads) rpw_compact_scatter_kernel(const float* __restrict__ pts, PointLayout lay, const uint8_t* __restrict__ labels,
+                                                                         const uint64_t* __restrict__ scan_off, const uint32_t* __restrict__ chunk_base,
+                                                                         const uint32_t* __restrict__ cnt, const FusionTable* __restrict__ fusion,
+                                                                         float* __restrict__ ground, float* __restrict__ nonground,
+                                                                         uint32_t* __restrict__ scan_counts) {
+    constexpr int kWarps = kBinThreads / 32;
+    constexpr int kPerWarp = kBinChunk / kWarps;
+    __shared__ uint32_t s_base[4];          // ground, non-ground, beyond bases of this chunk; [3] label-0 total of the scan
+    __shared__ uint32_t s_warp[kWarps][3];  // per-warp counts, then exclusive offsets
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const uint64_t off = scan_off[b];
+    const uint32_t n = (uint32_t)(scan_off[b + 1] - off);
+    const uint32_t base = (uint32_t)chunk * kBinChunk;
+    if (base >= n) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < 4) s_base[threadIdx.x] = 0;
+    __syncthreads();
+    // bases: label counts of the chunks before this one; total label-0 and beyond counts of the scan
+    {
+        const int chunks = (int)((n + kBinChunk - 1) / kBinChunk);
+        const uint32_t* c = cnt + (size_t)chunk_base[b] * 4;
+        uint32_t g = 0, ng = 0, by = 0, ng_all = 0, g_all = 0, by_all = 0;
+        for (int q = threadIdx.x; q < chunks; q += kBinThreads) {
+            const uint32_t a0 = c[q * 4 + 0], a1 = c[q * 4 + 1], a2 = c[q * 4 + 2];
+            if (q < chunk) { ng += a0; g += a1; by += a2; }
+            ng_all += a0; g_all += a1; by_all += a2;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            g += __shfl_xor_sync(0xffffffffu, g, d); ng += __shfl_xor_sync(0xffffffffu, ng, d); by += __shfl_xor_sync(0xffffffffu, by, d);
+            ng_all += __shfl_xor_sync(0xffffffffu, ng_all, d); g_all += __shfl_xor_sync(0xffffffffu, g_all, d);
+            by_all += __shfl_xor_sync(0xffffffffu, by_all, d);
+        }
+        if (lane == 0) {
+            atomicAdd(&s_base[0], g); atomicAdd(&s_base[1], ng); atomicAdd(&s_base[2], by); atomicAdd(&s_base[3], ng_all);
+            if (chunk == 0) { atomicAdd(&scan_counts[2 * b], g_all); atomicAdd(&scan_counts[2 * b + 1], ng_all + by_all); }
+        }
+    }
+    // per-warp counts over the warp's contiguous run of the chunk
+    uint32_t wc0 = 0, wc1 = 0, wc2 = 0;
+    for (int r = 0; r < kPerWarp / 32; ++r) {
+        const uint32_t i = base + warp * kPerWarp + r * 32 + lane;
+        const uint32_t l = i < n ? labels[off + i] : 255u;
+        wc0 += __popc(__ballot_sync(0xffffffffu, l == 0));
+        wc1 += __popc(__ballot_sync(0xffffffffu, l == 1));
+        wc2 += __popc(__ballot_sync(0xffffffffu, l == 2));
+    }
+    if (lane == 0) { s_warp[warp][0] = wc0; s_warp[warp][1] = wc1; s_warp[warp][2] = wc2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        uint32_t run = 0;
+        for (int w = 0; w < kWarps; ++w) { const uint32_t v = s_warp[w][threadIdx.x]; s_warp[w][threadIdx.x] = run; run += v; }
+    }
+    __syncthreads();
+    uint32_t o_ng = s_base[1] + s_warp[warp][0];
+    uint32_t o_g = s_base[0] + s_warp[warp][1];
+    uint32_t o_by = s_base[3] + s_base[2] + s_warp[warp][2];  // beyond-radius points follow ALL label-0 points of the scan
+    const unsigned lt = (1u << lane) - 1u;
+    for (int r = 0; r < kPerWarp / 32; ++r) {
+        const uint32_t i = base + warp * kPerWarp + r * 32 + lane;
+        const bool valid = i < n;
+        const uint32_t l = valid ? labels[off + i] : 255u;
+        const unsigned m0 = __ballot_sync(0xffffffffu, l == 0), m1 = __ballot_sync(0xffffffffu, l == 1), m2 = __ballot_sync(0xffffffffu, l == 2);
+        if (l <= 2u) {
+            float x, y, z;
+            load_xyz<VEC4>(pts, off + i, lay, x, y, z);
+            if (fusion != nullptr) fuse_point(*fusion, i, x, y);
+            float* dst;
+            if (l == 1u) dst = ground + 3 * (off + o_g + __popc(m1 & lt));
+            else if (l == 0u) dst = nonground + 3 * (off + o_ng + __popc(m0 & lt));
+            else dst = nonground + 3 * (off + o_by + __popc(m2 & lt));
+            dst[0] = x; dst[1] = y; dst[2] = z;
+        }
+        o_ng += __popc(m0); o_g += __popc(m1); o_by += __popc(m2);
+    }
+}
+
+// =============================================================================================
 // unit-test entry points
 // =============================================================================================
 __global__ void rpw_eig3_kernel(const float* __restrict__ mats, size_t count, float* __restrict__ evals, float* __restrict__ evecs) {
@@ -1177,6 +1293,18 @@ static void launch_roots_tt(cudaStream_t st, const FitArgs& args, int cls, int c
 }
 
 // size class cls in [0, kNumFitClasses): patches with kFitClasses[cls-1].hi < n <= kFitClasses[cls].hi
+cudaError_t launch_compact(cudaStream_t st, const PointLayout& lay, const float* pts, const uint8_t* labels, const uint64_t* scan_off,
+                           const uint32_t* chunk_base, uint32_t* cnt, const FusionTable* fusion, float* ground, float* nonground,
+                           uint32_t* scan_counts, int max_chunks, int batch) {
+    dim3 grid(max_chunks, batch);
+    cudaError_t e = cudaMemsetAsync(scan_counts, 0, (size_t)batch * 2 * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    rpw_compact_count_kernel<<<grid, kBinThreads, 0, st>>>(labels, scan_off, chunk_base, cnt);
+    if (lay.vec4) rpw_compact_scatter_kernel<true><<<grid, kBinThreads, 0, st>>>(pts, lay, labels, scan_off, chunk_base, cnt, fusion, ground, nonground, scan_counts);
+    else rpw_compact_scatter_kernel<false><<<grid, kBinThreads, 0, st>>>(pts, lay, labels, scan_off, chunk_base, cnt, fusion, ground, nonground, scan_counts);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_fit_roots(cudaStream_t st, const FitArgs& args, int cls, unsigned grid) {
     const FitClass& c = kFitClasses[cls];
     if (grid == 0) grid = 1;

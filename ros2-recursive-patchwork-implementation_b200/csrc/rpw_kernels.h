@@ -66,6 +66,9 @@ cudaError_t launch_offsets(cudaStream_t st, const uint64_t* scan_off, const uint
 cudaError_t launch_scatter(cudaStream_t st, const PointLayout& lay, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
                            const uint16_t* keys, const uint32_t* blk_hist, const uint32_t* patch_start, float4* sorted,
                            int P, const FusionTable* fusion, int max_chunks, int batch);
+cudaError_t launch_compact(cudaStream_t st, const PointLayout& lay, const float* pts, const uint8_t* labels, const uint64_t* scan_off,
+                           const uint32_t* chunk_base, uint32_t* cnt, const FusionTable* fusion, float* ground, float* nonground,
+                           uint32_t* scan_counts, int max_chunks, int batch);
 cudaError_t launch_fit_roots(cudaStream_t st, const FitArgs& args, int size_class, unsigned grid_blocks);
 cudaError_t launch_fit_levels(cudaStream_t st, const FitArgs& args, int grid_blocks);
 cudaError_t launch_eig3(cudaStream_t st, const float* mats, size_t count, float* evals, float* evecs);

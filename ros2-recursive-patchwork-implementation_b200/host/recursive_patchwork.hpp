@@ -96,18 +96,17 @@ public:
         labels.assign(points.size(), RPW_LABEL_DROPPED);
         if (points.empty()) return out;  // empty in, two empty clouds out
         ensure(points.size());
-        check(rpw_segment(handle_, &points[0].x, points.size(), sizeof(Point3D), labels.data(), nullptr));
-        std::size_t n_ground = 0, n_non = 0, n_beyond = 0;
-        for (std::uint8_t l : labels) { n_ground += l == RPW_LABEL_GROUND; n_non += l == RPW_LABEL_NONGROUND; n_beyond += l == RPW_LABEL_BEYOND; }
-        out.first.reserve(n_ground);
-        out.second.reserve(n_non + n_beyond);
-        for (std::size_t i = 0; i < points.size(); ++i) {
-            if (labels[i] == RPW_LABEL_GROUND) out.first.push_back(points[i]);
-            else if (labels[i] == RPW_LABEL_NONGROUND) out.second.push_back(points[i]);
-        }
-        if (n_beyond)
-            for (std::size_t i = 0; i < points.size(); ++i)
-                if (labels[i] == RPW_LABEL_BEYOND) out.second.push_back(points[i]);
+        // labels and both clouds come from the device: the result assembly of recursive_patchwork.cpp:402-419
+        // (ground in input order; non-ground in input order, then the beyond-radius points) is a stable
+        // compaction kernel, the host only receives the bytes
+        static_assert(sizeof(Point3D) == 3 * sizeof(float), "Point3D must be packed xyz");
+        out.first.resize(points.size());
+        out.second.resize(points.size());
+        std::size_t n_ground = 0, n_non = 0;
+        check(rpw_segment_clouds(handle_, &points[0].x, points.size(), sizeof(Point3D), labels.data(), &out.first[0].x, &n_ground,
+                                 &out.second[0].x, &n_non));
+        out.first.resize(n_ground);
+        out.second.resize(n_non);
         return out;
     }
 
@@ -138,22 +137,17 @@ public:
             ensure(total);
             check(rpw_segment_fused(handle_, sens.data(), k, sizeof(Point3D), lp.data(), nullptr));
         }
-        // vehicle-frame coordinates with the operations LidarFusion::applyRotation2D uses
-        auto emit = [&](std::uint8_t want, std::vector<Point3D>& dst) {
-            for (std::size_t i = 0; i < k; ++i) {
-                const bool rot = std::abs(configs[i].rotation_angle) > 1e-6f;
-                const float a = configs[i].rotation_angle * M_PI / 180.0f;
-                const float c = std::cos(a), s = std::sin(a);
-                for (std::size_t j = 0; j < clouds[i].size(); ++j) {
-                    if (local[i][j] != want) continue;
-                    const Point3D& p = clouds[i][j];
-                    dst.push_back(rot ? Point3D(p.x * c - p.y * s, p.x * s + p.y * c, p.z) : p);
-                }
-            }
-        };
-        emit(RPW_LABEL_GROUND, out.first);
-        emit(RPW_LABEL_NONGROUND, out.second);
-        emit(RPW_LABEL_BEYOND, out.second);
+        // the two clouds in vehicle-frame coordinates, assembled on the device (rotation with the
+        // operations LidarFusion::applyRotation2D uses, ego points removed)
+        if (total) {
+            static_assert(sizeof(Point3D) == 3 * sizeof(float), "Point3D must be packed xyz");
+            out.first.resize(total);
+            out.second.resize(total);
+            std::uint64_t counts[2] = {0, 0};
+            check(rpw_last_clouds(handle_, &out.first[0].x, &out.second[0].x, 0, counts));
+            out.first.resize(static_cast<std::size_t>(counts[0]));
+            out.second.resize(static_cast<std::size_t>(counts[1]));
+        }
         if (labels) *labels = std::move(local);
         return out;
     }

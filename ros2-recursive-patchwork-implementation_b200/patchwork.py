@@ -41,7 +41,8 @@ class PatchworkConfig:
 def clouds_from_labels(points: np.ndarray, labels: np.ndarray):
     """The two clouds of filterGroundPoints, in the reference's order
     (RP/src/recursive_patchwork.cpp:402-419): ground in input order; non-ground in input order
-    followed by the beyond-radius points in input order."""
+    followed by the beyond-radius points in input order.  Host-side helper for callers that
+    only asked for labels; filterGroundPoints itself gets the clouds from the device."""
     p = points[:, :3]
     ground = p[labels == capi.LABEL_GROUND]
     non_ground = np.concatenate([p[labels == capi.LABEL_NONGROUND], p[labels == capi.LABEL_BEYOND]])
@@ -77,8 +78,8 @@ class RecursivePatchwork:
         a = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, np.shape(points)[-1] if np.ndim(points) == 2 else 3)
         if len(a) == 0:
             return np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32)
-        labels = self._handle.segment(a)
-        return clouds_from_labels(a, labels)
+        ground, non_ground, _ = self._handle.segment_clouds(a)  # assembled on the device (K4), the host only copies
+        return ground, non_ground
 
     def filterGroundLabels(self, points) -> np.ndarray:
         """The north-star addition: per-input-point labels (0 non-ground, 1 ground, 2 beyond

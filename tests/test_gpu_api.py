@@ -96,6 +96,64 @@ def test_clouds_follow_reference_order(rpw, h, oracle):
     assert np.array_equal(ng, np.concatenate([p[o == 0], p[o == 2]]))
 
 
+def _expected_clouds(p, labels):
+    """The reference's assembly (RP/src/recursive_patchwork.cpp:402-419) from per-point labels."""
+    return p[labels == 1], np.concatenate([p[labels == 0], p[labels == 2]])
+
+
+def test_device_result_assembly_batch(rpw, h, oracle):
+    """SURVEY section 8a row a13 on the device: stable compaction of a whole batch (ragged scans, an
+    empty scan, non-finite points, beyond-radius points), host and device destinations."""
+    import torch
+    cfg = rpw.PatchworkConfig(filtering_radius=30.0)
+    h.set_config(cfg.to_c())
+    scans = [rpw.synth.testsuite_cloud(200 + i, n) for i, n in enumerate((9000, 1, 0, 4097, 12000, 4096, 33))]
+    scans[0][5:9, 0] = np.nan
+    scans[4][100, 2] = np.inf
+    labels = h.segment_batch(scans)
+    for a, l in zip(scans, labels):
+        if len(a):
+            assert np.array_equal(l, oracle.run(cfg, a)["labels"])
+    counts = [len(a) for a in scans]
+    clouds = h.last_clouds(counts)
+    for a, l, (g, ng) in zip(scans, labels, clouds):
+        eg, eng = _expected_clouds(a[:, :3], l)
+        assert np.array_equal(g.view(np.uint32), eg.view(np.uint32)) and np.array_equal(ng.view(np.uint32), eng.view(np.uint32))
+    # device path in, device clouds out
+    off = np.zeros(len(scans) + 1, np.uint64); off[1:] = np.cumsum(counts)
+    total = int(off[-1])
+    d_pts = torch.from_numpy(np.concatenate([a for a in scans if len(a)])).cuda()
+    d_lab = torch.empty(total, dtype=torch.uint8, device="cuda")
+    d_g = torch.full((total, 3), -7.0, dtype=torch.float32, device="cuda")
+    d_ng = torch.full((total, 3), -7.0, dtype=torch.float32, device="cuda")
+    st = torch.cuda.Stream(); h.set_stream(st.cuda_stream)
+    h.segment_device(d_pts.data_ptr(), off, d_lab.data_ptr())
+    cnt = h.last_clouds_device(d_g.data_ptr(), d_ng.data_ptr(), len(scans))
+    st.synchronize(); h.set_stream(None)
+    gh, ngh = d_g.cpu().numpy(), d_ng.cpu().numpy()
+    for b, (a, l) in enumerate(zip(scans, labels)):
+        eg, eng = _expected_clouds(a[:, :3], l)
+        o = int(off[b])
+        assert tuple(cnt[b]) == (len(eg), len(eng))
+        assert np.array_equal(gh[o:o + len(eg)], eg) and np.array_equal(ngh[o:o + len(eng)], eng)
+        assert np.all(gh[o + len(eg):int(off[b + 1])] == -7.0)  # nothing written past a scan's cloud
+
+
+def test_device_result_assembly_fused(rpw, h, oracle):
+    """Clouds of a fused multi-LiDAR frame come out in vehicle coordinates, ego points removed:
+    equal to the reference's fusion (oracle.fuse) followed by its assembly."""
+    from test_oracle import sensor_frames
+    clouds, yaws, ego = sensor_frames(rpw, seed=11)
+    cfg = rpw.PatchworkConfig()
+    h.set_config(cfg.to_c())
+    labels = np.concatenate(h.segment_fused(clouds, yaws, ego))
+    (g, ng), = h.last_clouds([sum(map(len, clouds))])
+    fused, src = oracle.fuse(clouds, yaws, ego)
+    eg, eng = _expected_clouds(fused[:, :3], labels[src])
+    assert np.array_equal(g.view(np.uint32), eg.view(np.uint32))
+    assert np.array_equal(ng.view(np.uint32), eng.view(np.uint32))
+
+
 def test_python_mirror_class(rpw, oracle):
     cfg = rpw.PatchworkConfig(sensor_height=1.2, filtering_radius=50.0, num_sectors=8, max_iter=50)  # testBasicFunctionality's config
     rp = rpw.RecursivePatchwork(cfg, max_points=1 << 16)
