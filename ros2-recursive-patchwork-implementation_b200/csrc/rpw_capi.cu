@@ -169,6 +169,8 @@ static void apply_config(rpw_handle* h, const rpw_config* c) {
     h->cfg = *c;
     rpw_zone_model(c, h->zm.ring_edges, &h->zm.sector_angle);
     h->zm.inv_sector_angle = 1.0f / h->zm.sector_angle;
+    h->zm.rings_increasing = 1;
+    for (int i = 0; i < RPW_NUM_RINGS; ++i) if (!(h->zm.ring_edges[i] < h->zm.ring_edges[i + 1])) h->zm.rings_increasing = 0;
     h->zm.radius = c->filtering_radius;
     h->zm.num_sectors = c->num_sectors;
     h->zm.num_patches = RPW_NUM_RINGS * c->num_sectors;

@@ -193,11 +193,20 @@ __global__ void __launch_bounds__(kBinThreads) rpw_scatter_kernel(const float* _
     __syncthreads();
     uint32_t* my = s_off + warp * P;
     const uint32_t wbase = base + warp * kPerWarp;
-    // phase 1: per-warp counts
-    for (int r = 0; r < kPerWarp / 32; ++r) {
+    // the warp's keys are read once, all loads in flight together, and kept for both phases
+    constexpr int kRounds = kPerWarp / 32;
+    uint32_t kreg[kRounds];
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
         const uint32_t i = wbase + r * 32 + lane;
         uint32_t kk = 0xFFFFFFFFu;
-        if (i < n) { const uint16_t key = keys[off + i]; if (key < kKeySpecialMin) kk = key; }
+        if (i < n) { const uint16_t key = __ldg(keys + off + i); if (key < kKeySpecialMin) kk = key; }
+        kreg[r] = kk;
+    }
+    // phase 1: per-warp counts
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+        const uint32_t kk = kreg[r];
         const unsigned peers = __match_any_sync(0xffffffffu, kk);
         if (kk != 0xFFFFFFFFu && lane == __ffs(peers) - 1) my[kk] += __popc(peers);
         __syncwarp();
@@ -216,23 +225,32 @@ __global__ void __launch_bounds__(kBinThreads) rpw_scatter_kernel(const float* _
         }
     }
     __syncthreads();
-    // phase 3: ranks and scatter
-    for (int r = 0; r < kPerWarp / 32; ++r) {
-        const uint32_t i = wbase + r * 32 + lane;
-        uint32_t kk = 0xFFFFFFFFu;
-        if (i < n) { const uint16_t key = keys[off + i]; if (key < kKeySpecialMin) kk = key; }
-        const unsigned peers = __match_any_sync(0xffffffffu, kk);
-        if (kk != 0xFFFFFFFFu) {
-            const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-            const uint32_t pos = my[kk] + rank;
-            float x, y, z;
-            load_xyz<VEC4>(pts, off + i, lay, x, y, z);
-            if (fusion != nullptr) fuse_point(*fusion, i, x, y);  // the patches hold vehicle-frame coordinates
-            sorted[pos] = make_float4(x, y, z, __uint_as_float((uint32_t)(off + i)));
+    // phase 3: ranks and scatter, four rounds per trip with their point loads issued together
+    constexpr int kGroup = 4;
+#pragma unroll
+    for (int r0 = 0; r0 < kRounds; r0 += kGroup) {
+        float x[kGroup], y[kGroup], z[kGroup];
+#pragma unroll
+        for (int u = 0; u < kGroup; ++u) {
+            const uint32_t i = wbase + (r0 + u) * 32 + lane;
+            x[u] = y[u] = z[u] = 0.f;
+            if (kreg[r0 + u] != 0xFFFFFFFFu) load_xyz<VEC4>(pts, off + i, lay, x[u], y[u], z[u]);
         }
-        __syncwarp();
-        if (kk != 0xFFFFFFFFu && lane == __ffs(peers) - 1) my[kk] += __popc(peers);
-        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < kGroup; ++u) {
+            const uint32_t i = wbase + (r0 + u) * 32 + lane;
+            const uint32_t kk = kreg[r0 + u];
+            const unsigned peers = __match_any_sync(0xffffffffu, kk);
+            if (kk != 0xFFFFFFFFu) {
+                const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+                const uint32_t pos = my[kk] + rank;
+                if (fusion != nullptr) fuse_point(*fusion, i, x[u], y[u]);  // the patches hold vehicle-frame coordinates
+                sorted[pos] = make_float4(x[u], y[u], z[u], __uint_as_float((uint32_t)(off + i)));
+            }
+            __syncwarp();
+            if (kk != 0xFFFFFFFFu && lane == __ffs(peers) - 1) my[kk] += __popc(peers);
+            __syncwarp();
+        }
     }
 }
 
