@@ -125,7 +125,7 @@ def run_reference(args, emit):
     cfg = rpw.PatchworkConfig(filtering_radius=80.0)
     threads = os.cpu_count() or 1
     scans = gen_scans(rpw, range(1000, 1000 + 16), threads)
-    per_step = max(threads * 2, 16)
+    per_step = max(threads * 16, 64)  # large enough that the thread pool's start-up does not show
     sys.path.insert(0, str(ROOT / "tests"))
     import oracle_lib
     ref = oracle_lib.try_reference("fast")
@@ -134,16 +134,16 @@ def run_reference(args, emit):
         ref = oracle_lib.Oracle()
     ccfg = oracle_lib.to_cfg(cfg)
 
-    def step():
-        with ThreadPoolExecutor(max_workers=threads) as ex:
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        def step():
             list(ex.map(lambda i: ref.time_scan(ccfg, scans[i % len(scans)], 1), range(per_step)))
 
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = time.perf_counter() - t0
+        for _ in range(args.warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        dt = time.perf_counter() - t0
     val = per_step * args.steps / dt
     sample = f"{per_step} scans per step ({len(scans)} distinct C2 scans) on {threads} host threads"
     emit({
