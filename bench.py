@@ -174,8 +174,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scans", type=int, default=512, help="scans per step per GPU (BASELINE configs[2]: 4096 scans over 8 GPUs)")
-    ap.add_argument("--solver", default="eigen_qr", choices=["eigen_qr", "closed_form"],
-                    help="plane-normal solver: eigen_qr = reference-faithful default, closed_form = faster (see include/rpw_b200.h)")
+    ap.add_argument("--solver", default="hybrid", choices=["eigen_qr", "closed_form", "hybrid"],
+                    help="plane-normal solver: hybrid = the library default, eigen_qr = the reference's float QR throughout (see include/rpw_b200.h)")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="handles the end-to-end arm ping-pongs over (copy/compute overlap)")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU-seconds of work in the cpu_baseline sample (summed over threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -208,7 +208,7 @@ def main():
     offsets[1:] = np.cumsum(n_pts)
 
     h = rpw.Handle(cfg.to_c(), local_rank, total, B)
-    solver_id = rpw.capi.SOLVER_EIGEN_QR if args.solver == "eigen_qr" else rpw.capi.SOLVER_CLOSED_FORM
+    solver_id = {"eigen_qr": rpw.capi.SOLVER_EIGEN_QR, "closed_form": rpw.capi.SOLVER_CLOSED_FORM, "hybrid": rpw.capi.SOLVER_HYBRID}[args.solver]
     h.set_plane_solver(solver_id)
     # a real (non-NULL) stream: the C-ABI reads NULL as "the handle's own stream", and CUDA events
     # only see the stream they are recorded on
@@ -285,22 +285,34 @@ def main():
     assert torch.equal(d_labels, d_labels2)
     h2.close()
 
-    # ---- alternative solver, same timed loop (reported beside the headline, not instead of it) ----
-    other_id = rpw.capi.SOLVER_CLOSED_FORM if solver_id == rpw.capi.SOLVER_EIGEN_QR else rpw.capi.SOLVER_EIGEN_QR
-    h.set_plane_solver(other_id)
-    for _ in range(3):
-        step_resident()
-    barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step_resident()
-    e1.record(stream)
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    other_value = world * B * args.steps / (float(t.item()) * 1e-3)
+    # ---- the other solvers, same timed loop (reported beside the headline, not instead of it) ----
+    def timed_with(sid):
+        h.set_plane_solver(sid)
+        for _ in range(3):
+            step_resident()
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_resident()
+        e1.record(stream)
+        barrier()
+        tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return world * B * args.steps / (float(tt.item()) * 1e-3)
+
+    names = {rpw.capi.SOLVER_EIGEN_QR: "eigen_qr", rpw.capi.SOLVER_CLOSED_FORM: "closed_form", rpw.capi.SOLVER_HYBRID: "hybrid"}
+    other_values = {names[sid]: timed_with(sid) for sid in names if sid != solver_id}
+    # label agreement of the timed solver with the reference's own QR sequence over this rank's batch
+    h.set_plane_solver(rpw.capi.SOLVER_EIGEN_QR)
+    step_resident()
+    torch.cuda.synchronize()
+    labels_qr = d_labels.clone()
     h.set_plane_solver(solver_id)
+    step_resident()
+    torch.cuda.synchronize()
+    n_diff_vs_qr = int((labels_qr != d_labels).sum().item())
+    del labels_qr
 
     # ---- end-to-end arm: pinned host xyz (12 B/pt, the reference's Point3D layout) -> labels ----
     # The public C-ABI call a user makes (rpw_segment_batch_async + rpw_wait) on host buffers; the
@@ -419,7 +431,8 @@ def main():
             "pipelined_two_handles": {"value": pipelined_value, "unit": UNIT,
                                       "note": "same steps alternating over two handles / streams (frame-level pipelining by the caller)"},
             "solver": args.solver,
-            "other_solver": {"name": "closed_form" if solver_id == rpw.capi.SOLVER_EIGEN_QR else "eigen_qr", "value": other_value, "unit": UNIT},
+            "other_solvers": {k: {"value": v, "unit": UNIT} for k, v in other_values.items()},
+            "labels_differing_from_eigen_qr": {"count": n_diff_vs_qr, "of": total, "note": "this rank's batch, timed solver vs the reference's float QR sequence"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

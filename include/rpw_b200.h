@@ -135,17 +135,22 @@ int rpw_get_config(const rpw_handle* h, rpw_config* out);
 
 /* How the plane normal (smallest-eigenvalue eigenvector of the inlier covariance,
  * RP/src/recursive_patchwork.cpp:89-90) is computed on the device.
- *   RPW_SOLVER_EIGEN_QR (default): the operation sequence of Eigen 3.4.0's
- *     SelfAdjointEigenSolver<Matrix3f> in float — given the same covariance bits it returns the
- *     reference's bits, so even chaotic patches (two-layer clutter, where a 1e-6 rad change of
- *     one normal sends the fit to a different fixed point) reproduce the reference's labels.
- *   RPW_SOLVER_CLOSED_FORM: closed-form FP64 eigenvector, ~1.4x faster end to end and more accurate
- *     than the reference's float QR, but it is not the reference's rounding: identical labels on
- *     ordinary scans, 99.5 % on the worst chaotic synthetic scene — the same spread the reference
- *     shows between its own -O2 and -O3 -ffast-math builds.
- * Environment override at rpw_create: RPW_PLANE_SOLVER=0|1. */
+ *   RPW_SOLVER_EIGEN_QR: the operation sequence of Eigen 3.4.0's SelfAdjointEigenSolver<Matrix3f> in
+ *     float — given the same covariance bits it returns the reference's bits.  The serial 3x3 QR is
+ *     about half of every plane-fit iteration.
+ *   RPW_SOLVER_CLOSED_FORM: closed-form FP64 eigenvector (Newton on the characteristic cubic + row cross
+ *     products), ~1.25x faster end to end and more accurate than the reference's float QR, but not the
+ *     reference's rounding: where the two smallest eigenvalues nearly coincide the float QR's answer is
+ *     far from the true eigenvector and only the QR reproduces it (one stress scan in 64 fell to 99.5 %).
+ *   RPW_SOLVER_HYBRID (default): the closed form wherever the eigenvector is well conditioned (the two
+ *     smallest eigenvalues further apart than 2 % of the matrix scale: both solvers then agree to
+ *     ~1e-6 rad), the QR sequence for the rest (a few percent of the solves).  Measured against
+ *     RPW_SOLVER_EIGEN_QR: 1 label of 61.4 M differs over 512 ordinary scans, at most 31 of 262 k on the
+ *     two-layer stress scans (tests/gpu_solver_agreement.py); every parity test runs with both.
+ * Environment override at rpw_create: RPW_PLANE_SOLVER=0|1|2. */
 #define RPW_SOLVER_EIGEN_QR 0
 #define RPW_SOLVER_CLOSED_FORM 1
+#define RPW_SOLVER_HYBRID 2
 int rpw_set_plane_solver(rpw_handle* h, int solver);
 
 /* Use a caller-owned CUDA stream (cudaStream_t passed as void*; NULL = the handle's own stream).

@@ -16,7 +16,7 @@ LIB_PATH = Path(os.environ["RPW_B200_LIB"]) if os.environ.get("RPW_B200_LIB") el
 RPW_OK, RPW_ERR_BAD_ARG, RPW_ERR_NO_DEVICE, RPW_ERR_CUDA, RPW_ERR_CAPACITY, RPW_ERR_ALLOC = range(6)
 LABEL_NONGROUND, LABEL_GROUND, LABEL_BEYOND, LABEL_DROPPED, LABEL_EGO = 0, 1, 2, 3, 4
 KEY_DROPPED, KEY_BEYOND, KEY_UNBINNED, KEY_EGO = 0xFFFF, 0xFFFE, 0xFFFD, 0xFFFC
-SOLVER_EIGEN_QR, SOLVER_CLOSED_FORM = 0, 1
+SOLVER_EIGEN_QR, SOLVER_CLOSED_FORM, SOLVER_HYBRID = 0, 1, 2
 NODE_SMALL, NODE_AREA, NODE_FLAT, NODE_FIT, NODE_SPLIT = 1, 2, 3, 4, 5
 
 
@@ -193,7 +193,7 @@ class Handle:
         return c
 
     def set_plane_solver(self, solver: int):
-        """SOLVER_EIGEN_QR (0, default, reference-faithful) or SOLVER_CLOSED_FORM (1, faster)."""
+        """SOLVER_HYBRID (2, default), SOLVER_EIGEN_QR (0, the reference's own float QR sequence) or SOLVER_CLOSED_FORM (1)."""
         self._check(self.lib.rpw_set_plane_solver(self._h, int(solver)))
 
     def set_stream(self, cuda_stream: int | None):

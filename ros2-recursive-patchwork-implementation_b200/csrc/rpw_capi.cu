@@ -51,7 +51,7 @@ struct rpw_handle {
     uint32_t q_cap = 0;
     int smem_cap = 0;
     int fit_blocks = 0;
-    int solver = RPW_SOLVER_EIGEN_QR;
+    int solver = RPW_SOLVER_HYBRID;
 
     // device buffers
     float* d_in = nullptr;       // staged input records of host-path calls
@@ -182,6 +182,7 @@ static void apply_config(rpw_handle* h, const rpw_config* c) {
     h->fp.adaptive_seed_height = c->adaptive_seed_height;
     h->fp.max_split_depth = c->max_split_depth;
     h->fp.exact_eig = h->solver == RPW_SOLVER_EIGEN_QR ? 1 : 0;
+    h->fp.hybrid = h->solver == RPW_SOLVER_HYBRID ? 1 : 0;
 }
 
 static void free_patch_buffers(rpw_handle* h) {
@@ -288,7 +289,10 @@ int rpw_create(const rpw_config* cfg, int device, size_t max_total_points, size_
     h->num_sms = prop.multiProcessorCount;
     h->cap_points = max_total_points;
     h->cap_batch = max_batch;
-    if (const char* s = getenv("RPW_PLANE_SOLVER")) h->solver = atoi(s) == RPW_SOLVER_CLOSED_FORM ? RPW_SOLVER_CLOSED_FORM : RPW_SOLVER_EIGEN_QR;
+    if (const char* s = getenv("RPW_PLANE_SOLVER")) {
+        const int v = atoi(s);
+        h->solver = v == RPW_SOLVER_CLOSED_FORM || v == RPW_SOLVER_EIGEN_QR ? v : RPW_SOLVER_HYBRID;
+    }
     apply_config(h, &c);
     int rc = RPW_OK;
     auto fail = [&](int code) { g_create_error = h->err; rpw_destroy(h); return code; };
@@ -379,9 +383,11 @@ int rpw_set_config(rpw_handle* h, const rpw_config* cfg) {
 
 int rpw_set_plane_solver(rpw_handle* h, int solver) {
     if (!h) return RPW_ERR_BAD_ARG;
-    if (solver != RPW_SOLVER_EIGEN_QR && solver != RPW_SOLVER_CLOSED_FORM) RPW_FAIL(h, RPW_ERR_BAD_ARG, "unknown plane solver %d", solver);
+    if (solver != RPW_SOLVER_EIGEN_QR && solver != RPW_SOLVER_CLOSED_FORM && solver != RPW_SOLVER_HYBRID)
+        RPW_FAIL(h, RPW_ERR_BAD_ARG, "unknown plane solver %d", solver);
     h->solver = solver;
     h->fp.exact_eig = solver == RPW_SOLVER_EIGEN_QR ? 1 : 0;
+    h->fp.hybrid = solver == RPW_SOLVER_HYBRID ? 1 : 0;
     return RPW_OK;
 }
 

@@ -527,7 +527,7 @@ struct Tick {
 // the SM's sub-partitions all give the same throughput.)
 template <bool EXACT>
 __device__ __forceinline__ void plane_normal(const float (&cv)[6], float cnt, float* bc, float& nx, float& ny, float& nz,
-                                             unsigned long long* timing = nullptr) {
+                                             bool hybrid, unsigned long long* timing = nullptr) {
     if (threadIdx.x < 32) {
         float ax, ay, az;
         if (EXACT) {
@@ -536,7 +536,11 @@ __device__ __forceinline__ void plane_normal(const float (&cv)[6], float cnt, fl
             plane_normal_exact(cv, cnt - 1.f, ax, ay, az);  // computeCovariance divides by n-1 (point_cloud_processor.cpp:84)
             if (timing && threadIdx.x == 0) atomicAdd(timing + 14, (unsigned long long)(clock64() - t0));
         } else {
-            smallest_eigvec_psd(cv[0], cv[1], cv[2], cv[3], cv[4], cv[5], ax, ay, az);
+            bool small_gap;
+            smallest_eigvec_psd(cv[0], cv[1], cv[2], cv[3], cv[4], cv[5], ax, ay, az, &small_gap);
+            // hybrid solver: where the eigenvector is ill-conditioned only the reference's own operation
+            // sequence reproduces the reference's answer
+            if (hybrid && small_gap) plane_normal_exact(cv, cnt - 1.f, ax, ay, az);
         }
         if (az < 0.f) { ax = -ax; ay = -ay; az = -az; }  // :93-95
         if (threadIdx.x == 0) { bc[0] = ax; bc[1] = ay; bc[2] = az; }
@@ -744,7 +748,7 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
         if (cnt < 3.f) break;  // :196 — collapsed mask is kept (Q3)
         if (!have_cv) covariance_pass();
         tick(2);
-        plane_normal<EXACT>(cv, cnt, bc, nx, ny, nz, A.timing);
+        plane_normal<EXACT>(cv, cnt, bc, nx, ny, nz, fp.hybrid != 0, A.timing);
         iters++;
         tick(3);
         // distances, new mask, convergence, residual of the fit just made, moments of the new mask
@@ -782,7 +786,7 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
     if (!have_final) {
         if (cnt >= 3.f) {
             if (!have_cv) covariance_pass();
-            plane_normal<EXACT>(cv, cnt, bc, nx, ny, nz, A.timing);
+            plane_normal<EXACT>(cv, cnt, bc, nx, ny, nz, fp.hybrid != 0, A.timing);
             float rs[1] = {0.f};
             for_points<TT, SMEM, true>(nv, n, [&](uint32_t, float x, float y, float z, uint8_t m) {
                 rs[0] += m ? plane_dist(x, y, z, cx, cy, cz, nx, ny, nz) : 0.f;

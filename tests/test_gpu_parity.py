@@ -61,10 +61,16 @@ CASES = {
 }
 
 
+@pytest.mark.parametrize("solver", ["hybrid", "eigen_qr"])
 @pytest.mark.parametrize("case", sorted(CASES))
-def test_parity_against_oracle(case, rpw, h, oracle):
+def test_parity_against_oracle(case, solver, rpw, h, oracle):
+    """Every scene with the default solver (hybrid) and with the reference's own QR sequence."""
     cfg, pts = CASES[case](rpw)
-    labels, keys, nodes, o = run_case(h, oracle, cfg, pts)
+    h.set_plane_solver(rpw.capi.SOLVER_HYBRID if solver == "hybrid" else rpw.capi.SOLVER_EIGEN_QR)
+    try:
+        labels, keys, nodes, o = run_case(h, oracle, cfg, pts)
+    finally:
+        h.set_plane_solver(rpw.capi.SOLVER_HYBRID)
     rep = parity.compare_scan(labels, keys, o)
     nrep = parity.compare_nodes(nodes, o["nodes"])
     print(case, rep, nrep)
@@ -196,6 +202,13 @@ def test_closed_form_solver_accuracy(h):
         d = (p - p.mean(0)).astype(np.float32)
         S = d.T @ d
         mats.append([S[0, 0], S[1, 0], S[1, 1], S[2, 0], S[2, 1], S[2, 2]])
+    # two smallest eigenvalues close to each other (Newton on the cubic meets a nearly double root): a
+    # seed set seen on the C5 stress scene (eigenvalues 1419.6, 1453.0, 4160.9) and rotated diag(1, 1+g, 3)
+    mats.append([3264.94, 1280.3462, 2328.6538, -30.985556, -41.74468, 1439.9283])
+    for g in (3e-1, 1e-1, 3e-2, 1e-2, 3e-3, 1e-3, 3e-4):
+        q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        S = q @ np.diag([1.0, 1.0 + g, 3.0]) @ q.T
+        mats.append([S[0, 0], S[1, 0], S[1, 1], S[2, 0], S[2, 1], S[2, 2]])
     mats = np.array(mats, np.float32)
     full = np.zeros((len(mats), 3, 3))
     full[:, 0, 0] = mats[:, 0]; full[:, 1, 0] = full[:, 0, 1] = mats[:, 1]; full[:, 1, 1] = mats[:, 2]
@@ -213,11 +226,9 @@ def test_closed_form_solver_accuracy(h):
 @pytest.mark.parametrize("case", ["C1_10000_splits", "C2_120k", "C4_300k", "C5_262k_deep"])
 def test_closed_form_solver_label_parity(case, rpw, gpu_handle_factory, oracle):
     """The faster solver is not the reference's rounding, so the tree of fits may differ in chaotic
-    patches (a plane fit sitting between two layers tips over on a 1e-6 rad change).  Ordinary scenes
-    clear the 99.9 % bar; the two-layer stress scene C5 is held to 97 % here (98.3 % measured: one near-degenerate
-    inner-ring patch, whose two smallest covariance eigenvalues nearly coincide, tips the other way) — the reference's own -O2
-    and -O3 -ffast-math builds do not agree with each other to 99.9 % on such scenes either
-    (DESIGN.md section 4).  The default solver reproduces C5 exactly (test_parity_against_oracle)."""
+    patches (a plane fit sitting between two layers tips over on a 1e-6 rad change).  All scenes,
+    the two-layer stress scene C5 included, clear the 99.9 % bar; the default solver reproduces them
+    exactly (test_parity_against_oracle)."""
     hd = gpu_handle_factory(None, 1 << 19, 1)
     hd.set_plane_solver(rpw.capi.SOLVER_CLOSED_FORM)
     cfg, pts = CASES[case](rpw)
@@ -228,7 +239,7 @@ def test_closed_form_solver_label_parity(case, rpw, gpu_handle_factory, oracle):
     rep = parity.compare_scan(labels, keys, o)
     print(case, rep)
     assert rep["key_mismatch"] == 0 and rep["n_flips_nonpatch"] == 0
-    assert rep["label_agreement"] >= (0.97 if case.startswith("C5") else LABEL_BAR)
+    assert rep["label_agreement"] >= LABEL_BAR
 
 
 def test_sector_edges_take_the_exact_path(rpw, h, oracle):
