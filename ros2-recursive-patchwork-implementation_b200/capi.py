@@ -339,7 +339,7 @@ class Handle:
         """Reads+clears the fit kernel's cycle counters, then switches the accounting on/off."""
         out = (C.c_uint64 * 16)()
         self._check(self.lib.rpw_debug_fit_timing(self._h, 1 if enable else 0, out))
-        names = ["load", "seeds", "cov", "eig", "dist", "final", "label", "split", "fetch", "gridsync", "nodes", "iters", "cov_reduce", "dist_reduce", "qr_only"]
+        names = ["load", "seeds", "cov", "eig", "dist", "final", "label", "split", "fetch", "gridsync", "nodes", "iters", "load_loop", "dist_reduce", "qr_only"]
         return {k: int(out[i]) for i, k in enumerate(names)}
 
     TRACE_DTYPE = np.dtype([("t_start_ns", "<u8"), ("t_end_ns", "<u8"), ("sm", "<u4"), ("n", "<u4"), ("depth", "<u2"),

@@ -598,14 +598,16 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
             mm[3] = fminf(mm[3], -v.x); mm[4] = fminf(mm[4], -v.y); mm[5] = fminf(mm[5], -v.z);
             if (depth == 0) sd[0] += range2d(v.x, v.y);
         };
-        // eight independent 16-byte loads in flight per thread: the pass is DRAM/L2-latency bound
+        // many independent 16-byte loads in flight per thread (16 where the register budget allows, else
+        // 8): the pass is DRAM/L2-latency bound, every trip costs a full memory round trip
+        constexpr int kWide = TT <= 256 ? 16 : 8;
         uint32_t i = tid;
-        for (; i + 7 * TT < n; i += 8 * TT) {
-            float4 v[8];
+        for (; i + (kWide - 1) * TT < n; i += kWide * TT) {
+            float4 v[kWide];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = __ldcg(nv.src + i + u * TT);
+            for (int u = 0; u < kWide; ++u) v[u] = __ldcg(nv.src + i + u * TT);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) take(i + u * TT, v[u]);
+            for (int u = 0; u < kWide; ++u) take(i + u * TT, v[u]);
         }
         for (; i + 3 * TT < n; i += 4 * TT) {
             float4 v[4];
@@ -616,6 +618,7 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
         }
         for (; i < n; i += TT) take(i, __ldcg(nv.src + i));
     }
+    tick(12);
     block_min<TT, 6>(mm, S.red, phase);
     float mean_dist;
     if (depth == 0) {
@@ -652,13 +655,23 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
     const float tau = fp.th_dist * (1.0f + 0.2f * rel_dist);  // :203
 
     // ---- seeds (:163-182) -------------------------------------------------------------------
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};  // count, sum x, sum y, sum z over the mask
+    // One pass builds the seed mask AND its first/second moments about a fixed pivot (bounding-box
+    // centre, lowest z): the seed centroid is pivot + s/n and its scatter S' - s s^T / n, so the first
+    // plane fit needs no separate covariance pass.  The subtraction is harmless while the pivot sits
+    // inside the seed cloud; a compact seed set far from the pivot (S' >> scatter) falls back to the
+    // covariance pass about the centroid.
+    const float px = 0.5f * (x_min + x_max), py = 0.5f * (y_min + y_max), pz = z_min;
+    float acc[10] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // count, s, S' (xx yx yy zx zy zz)
     for_points<TT, SMEM, false>(nv, n, [&](uint32_t i, float x, float y, float z, uint8_t) {
         const bool m = z < z_th;
         nv.set_mask(i, m ? 1 : 0);
-        acc[0] += m ? 1.f : 0.f; acc[1] += m ? x : 0.f; acc[2] += m ? y : 0.f; acc[3] += m ? z : 0.f;
+        const float dx = m ? x - px : 0.f, dy = m ? y - py : 0.f, dz = m ? z - pz : 0.f;
+        acc[0] += m ? 1.f : 0.f; acc[1] += dx; acc[2] += dy; acc[3] += dz;
+        acc[4] = fmaf(dx, dx, acc[4]); acc[5] = fmaf(dy, dx, acc[5]); acc[6] = fmaf(dy, dy, acc[6]);
+        acc[7] = fmaf(dz, dx, acc[7]); acc[8] = fmaf(dz, dy, acc[8]); acc[9] = fmaf(dz, dz, acc[9]);
     });
-    block_sum<TT, 4>(acc, S.red, phase);
+    block_sum<TT, 10>(acc, S.red, phase);
+    bool seeds_by_height = true;
     if (acc[0] < 3.f) {
         // the three lowest-z points (std::partial_sort over indices, :173-181).  Parallel pick by
         // (z, index); if z ties reach across the cut the SET libstdc++'s heap-select keeps depends on
@@ -716,6 +729,7 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
             nv.get(chosen[r], x, y, z);
             acc[1] += x; acc[2] += y; acc[3] += z;
         }
+        seeds_by_height = false;
     }
 
     tick(1);
@@ -725,10 +739,17 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
     // the next scatter matrix is S' - s s^T / n (the shift s/n is small, so nothing cancels badly).
     // Only the very first fit (seeds) needs a separate covariance pass.
     float cnt = acc[0];
-    float cx = acc[1] / cnt, cy = acc[2] / cnt, cz = acc[3] / cnt;  // computeCentroid
+    float cx = acc[1] / cnt, cy = acc[2] / cnt, cz = acc[3] / cnt;  // computeCentroid (seeds by height: relative to the pivot)
     float nx = 0.f, ny = 0.f, nz = 1.f, residual = FLT_MAX;
     float cv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // scatter of the current mask about (cx, cy, cz): xx yx yy zx zy zz
     bool have_cv = false;
+    if (seeds_by_height) {
+        cv[0] = fmaf(-acc[1], cx, acc[4]); cv[1] = fmaf(-acc[2], cx, acc[5]); cv[2] = fmaf(-acc[2], cy, acc[6]);
+        cv[3] = fmaf(-acc[3], cx, acc[7]); cv[4] = fmaf(-acc[3], cy, acc[8]); cv[5] = fmaf(-acc[3], cz, acc[9]);
+        cx += px; cy += py; cz += pz;
+        // more than four bits lost to the pivot offset: take the covariance pass about the centroid instead
+        have_cv = !((acc[4] + acc[6] + acc[9]) > 16.f * (cv[0] + cv[2] + cv[5]));
+    }
     int iters = 0;
     bool have_final = false;  // final plane (:220-228) already known
     float* bc = reinterpret_cast<float*>(S.misc + 8);
@@ -809,13 +830,14 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
         // leaf: slot j labels input point sortedA[start + j].w (positional read-back, Q1)
         {
             const float4* rec = A.sortedA + nd.start;
+            constexpr int kWide = TT <= 256 ? 16 : 8;
             uint32_t i = tid;
-            for (; i + 7 * TT < n; i += 8 * TT) {
-                uint32_t w[8];
+            for (; i + (kWide - 1) * TT < n; i += kWide * TT) {
+                uint32_t w[kWide];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) w[u] = __float_as_uint(__ldcg(&rec[i + u * TT].w));
+                for (int u = 0; u < kWide; ++u) w[u] = __float_as_uint(__ldcg(&rec[i + u * TT].w));
 #pragma unroll
-                for (int u = 0; u < 8; ++u) A.labels[w[u]] = nv.mask(i + u * TT);
+                for (int u = 0; u < kWide; ++u) A.labels[w[u]] = nv.mask(i + u * TT);
             }
             for (; i + 3 * TT < n; i += 4 * TT) {
                 uint32_t w[4];
