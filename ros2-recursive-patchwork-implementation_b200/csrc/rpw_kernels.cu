@@ -590,13 +590,16 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
 
     // ---- pass 1: load, bounding box, (root only) mean range ------------------------------
     float mm[6] = {FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX};  // min x,y,z, min -x,-y,-z
-    float sd[1] = {0.f};
+    float sd[2] = {0.f, 0.f};  // sum of ranges; [1]: a square root left the branch-free sequence's range
     {
+        // sqrtf carries a branch to its slow path, which would keep the rows' 40-cycle chains from
+        // overlapping; the branch-free copy (ArithSpec, bit-identical in range) is checked once at the end
+        ArithSpec ar;
         auto take = [&](uint32_t i, const float4 v) {
             if (SMEM) { S.x[i] = v.x; S.y[i] = v.y; S.z[i] = v.z; }
             mm[0] = fminf(mm[0], v.x); mm[1] = fminf(mm[1], v.y); mm[2] = fminf(mm[2], v.z);
             mm[3] = fminf(mm[3], -v.x); mm[4] = fminf(mm[4], -v.y); mm[5] = fminf(mm[5], -v.z);
-            if (depth == 0) sd[0] += range2d(v.x, v.y);
+            if (depth == 0) sd[0] += ar.sqrt(v.x * v.x + v.y * v.y);  // range2d
         };
         // many independent 16-byte loads in flight per thread (16 where the register budget allows, else
         // 8): the pass is DRAM/L2-latency bound, every trip costs a full memory round trip
@@ -617,12 +620,18 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
             for (int u = 0; u < 4; ++u) take(i + u * TT, v[u]);
         }
         for (; i < n; i += TT) take(i, __ldcg(nv.src + i));
+        sd[1] = ar.ok() ? 0.f : 1.f;
     }
     tick(12);
     block_min<TT, 6>(mm, S.red, phase);
     float mean_dist;
     if (depth == 0) {
-        block_sum<TT, 1>(sd, S.red, phase);
+        block_sum<TT, 2>(sd, S.red, phase);
+        if (sd[1] != 0.f) {  // (never for patch points, whose range is at least 1 m: kept for safety)
+            sd[0] = 0.f;
+            for (uint32_t i = tid; i < n; i += TT) sd[0] += range2d(nv.coord(i, 0), nv.coord(i, 1));
+            block_sum<TT, 2>(sd, S.red, phase);
+        }
         mean_dist = sd[0] / (float)n;  // :383-387
         if (tid == 0) A.root_mean[nd.root] = mean_dist;
     } else {
