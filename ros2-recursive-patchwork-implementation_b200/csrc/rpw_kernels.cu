@@ -19,6 +19,10 @@
 // contraction, so no tensor-core path.  Compiled with -fmad=false (see rpw_device.cuh).
 #include "rpw_kernels.h"
 
+#ifndef RPW_LB128
+#define RPW_LB128 5  // resident blocks per SM the 128-thread fit kernels are compiled for (5 x 40 KB slots fill an SM)
+#endif
+
 namespace rpw {
 
 // =============================================================================================
@@ -976,7 +980,7 @@ __device__ __forceinline__ FitSmem carve_smem(unsigned char* raw, int cap, int w
 // float solver, which is enough to tip chaotic two-layer patches the other way).
 // ---------------------------------------------------------------------------------------------
 template <int TT, bool EXACT>
-__global__ void __launch_bounds__(TT, (TT <= 64 ? 8 : TT <= 128 ? 4 : TT <= 256 ? 3 : 2))
+__global__ void __launch_bounds__(TT, (TT <= 64 ? 8 : TT <= 128 ? RPW_LB128 : TT <= 256 ? 3 : 2))
 rpw_fit_roots_kernel(FitArgs A, int cls, int cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // The class's work list and its length are read together (independent addresses, one latency).
