@@ -334,3 +334,42 @@ def test_edge_cases_against_oracle(case, rpw, gpu_handle_factory, oracle):
     assert rep["label_agreement"] >= LABEL_BAR
     assert nrep["n_shared"] >= 0.98 * nrep["n_oracle"]
     hd.close()
+
+
+def _fuzz_case(rpw, k):
+    """Seeded random configuration + cloud: every live PatchworkConfig field, all three cloud generators,
+    scaled / shifted so that sensor height, radius and thresholds meet the data in different regimes."""
+    rng = np.random.default_rng(9000 + k)
+    cfg = rpw.PatchworkConfig(
+        sensor_height=float(rng.choice([1.2, 0.4, 2.0, -0.5, 0.05])),
+        num_sectors=int(rng.choice([1, 2, 3, 7, 10, 16, 31, 64, 128])),
+        max_iter=int(rng.choice([0, 1, 2, 5, 20, 100])),
+        adaptive_seed_height=bool(rng.integers(0, 2)),
+        th_seeds=float(rng.choice([0.05, 0.15, 0.5])),
+        th_dist=float(rng.choice([0.02, 0.1, 0.2, 0.6])),
+        filtering_radius=float(rng.choice([1.5, 12.0, 40.0, 80.0, 150.0, 400.0])),
+        max_split_depth=int(rng.choice([0, 1, 3, 1000])))
+    kind = int(rng.integers(0, 3))
+    if kind == 0:
+        pts = rpw.synth.testsuite_cloud(int(rng.integers(1, 1 << 30)), int(rng.integers(200, 40000)))
+    elif kind == 1:
+        pts = rpw.synth.spinning_scan(int(rng.integers(1, 1 << 30)), int(rng.choice([16, 32, 64])), int(rng.integers(100, 900)),
+                                      int(rng.integers(0, 2)), int(rng.choice([0, 200, 20000])))
+    else:
+        pts = rpw.synth.solidstate_merged(int(rng.integers(1, 1 << 30)), int(rng.integers(40, 200)), int(rng.integers(30, 120)))
+    pts = np.ascontiguousarray(pts[:, :3], np.float32).copy()
+    pts *= np.float32(rng.choice([1.0, 1.0, 0.25, 3.0]))
+    pts[:, 2] += np.float32(rng.choice([0.0, 0.0, 0.3, -0.3]))
+    return cfg, pts
+
+
+@pytest.mark.parametrize("k", range(32))
+def test_randomised_configs_against_oracle(k, rpw, h, oracle):
+    cfg, pts = _fuzz_case(rpw, k)
+    labels, keys, nodes, o = run_case(h, oracle, cfg, pts)
+    rep = parity.compare_scan(labels, keys, o)
+    nrep = parity.compare_nodes(nodes, o["nodes"])
+    print(k, cfg, len(pts), rep, {q: nrep[q] for q in ("n_gpu", "n_oracle", "n_shared", "outcome_mismatch", "max_angle")})
+    assert rep["key_mismatch"] == 0 and rep["n_flips_nonpatch"] == 0
+    assert rep["label_agreement"] >= LABEL_BAR
+    assert nrep["n_shared"] >= 0.98 * nrep["n_oracle"]
