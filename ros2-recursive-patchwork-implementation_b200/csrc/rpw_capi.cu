@@ -561,6 +561,9 @@ static int run_group(rpw_handle* h, rpw_handle::Lane& L, cudaStream_t st, const 
             if (est_scans && !no_est) {
                 const uint64_t est = ((uint64_t)L.h_counts[c] * nb + est_scans - 1) / est_scans;
                 g = est + est / 32 + 2;
+                // never fewer than two blocks per SM: if the scene changes (a class that was empty fills up)
+                // the list is still walked in parallel; surplus blocks cost one load each
+                if (g < 2u * (uint64_t)h->num_sms) g = 2u * (uint64_t)h->num_sms;
                 if (g > bound) g = bound;
             }
             grids[c] = (unsigned)(g ? g : 1);
