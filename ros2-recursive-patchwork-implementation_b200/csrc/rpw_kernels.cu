@@ -2,18 +2,22 @@
 //
 //   K1  rpw_bin_kernel      clean + range + radius + angle + ring/sector key, per-block patch
 //                           histogram (RP/src/recursive_patchwork.cpp:315-378 steps 1-6a)
-//   K1b rpw_offsets_kernel  per-scan exclusive scan of the block histograms -> stable offsets
+//   K1b rpw_offsets_kernel  per-scan exclusive scan of the block histograms -> stable offsets; per-size-class
+//                           work lists of the non-empty root patches
 //   K2  rpw_scatter_kernel  stable counting-sort scatter of (x, y, z, input index) into
 //                           ring/sector patch segments (input order inside every patch, Q1)
 //   K3a rpw_fit_roots_kernel  fitPlaneAndSplit at depth 0 (RP/src/recursive_patchwork.cpp:109-308), one
-//                           block per ring/sector patch, three size classes running concurrently;
+//                           block per listed ring/sector patch, six size classes (block shape and shared-
+//                           memory slot per class) launched on concurrent, prioritised streams;
 //                           per node: early-outs, seeds, iterated PCA plane fit with a register
 //                           3x3 eigensolve, residual mask, split (variance axis, exact radix-select
 //                           median, stable partition), child enqueue, label scatter
 //   K3b rpw_fit_levels_kernel persistent cooperative kernel (one block per SM, grid barrier in global memory):
 //                           level-synchronous device worklist over the children of split nodes
 //                           (depth >= 1), no host round trips
-//   dbg rpw_eig3_kernel / rpw_atan2_kernel   unit-test entry points for the device math
+//   K4  rpw_compact_count_kernel / rpw_compact_scatter_kernel   result assembly (:402-419): the ground and
+//                           non-ground clouds in the reference's order, a stable compaction by label
+//   dbg rpw_eig3_kernel / rpw_normal_kernel / rpw_atan2_kernel   unit-test entry points for the device math
 //
 // All of it is HBM/L2/shared-memory bound integer-and-float SIMT work; there is no dense
 // contraction, so no tensor-core path.  Compiled with -fmad=false (see rpw_device.cuh).
