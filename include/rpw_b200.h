@@ -214,6 +214,16 @@ int rpw_segment_fused(rpw_handle* h, const rpw_sensor_cloud* sensors, size_t n_s
  * be alive (device path: the caller's d_points). */
 int rpw_last_clouds(rpw_handle* h, float* ground_xyz, float* nonground_xyz, int on_device, uint64_t* counts);
 
+/* RecursivePatchwork::sampleGroundAndObstacles (RP/src/recursive_patchwork.cpp:428-465) for the scan of this handle's
+ * LAST single-scan call, computed on the device from the clouds of rpw_last_clouds: first a context sample of
+ * min(sample_size, #ground) distinct ground points (the reference uses 2000 and an unseeded std::mt19937; seed = 0
+ * seeds from std::random_device as it does, any other value makes the draw reproducible), then the obstacles: the
+ * non-ground points with sqrtf(x*x+y*y) > ego_radius (reference: 2.5) and |z - target_height| <= base_tol (1.1 / 0.5),
+ * in the non-ground cloud's order.  A scan without non-ground points returns its whole ground cloud (:435-437).
+ * out_xyz: HOST buffer of 3 * out_cap_points floats (sample_size + #non-ground points always suffices). */
+int rpw_sample_ground_and_obstacles(rpw_handle* h, float target_height, float base_tol, float ego_radius, size_t sample_size,
+                                    uint64_t seed, float* out_xyz, size_t out_cap_points, size_t* n_ground_sample, size_t* n_obstacles);
+
 /* One scan, with the two clouds the reference returns, in the reference's order (rpw_segment + rpw_last_clouds).
  * ground_xyz / nonground_xyz: caller buffers of 3*n floats each (either may be NULL). */
 int rpw_segment_clouds(rpw_handle* h, const float* xyz, size_t n, size_t stride_bytes, uint8_t* labels_out,

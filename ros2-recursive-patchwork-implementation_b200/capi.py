@@ -53,7 +53,7 @@ NODE_DTYPE = np.dtype([("scan", "<i4"), ("root", "<i4"), ("depth", "<i4"), ("sta
 # Every symbol include/rpw_b200.h declares (tests check that the library exports all of them).
 EXPORTS = ["rpw_default_config", "rpw_zone_model", "rpw_create", "rpw_destroy", "rpw_set_config", "rpw_get_config",
            "rpw_set_plane_solver", "rpw_set_stream", "rpw_last_error", "rpw_segment", "rpw_segment_batch", "rpw_segment_batch_async", "rpw_wait",
-           "rpw_segment_pc2", "rpw_segment_fused", "rpw_segment_clouds", "rpw_last_clouds", "rpw_segment_device", "rpw_debug_keys", "rpw_debug_enable_nodes", "rpw_debug_nodes",
+           "rpw_segment_pc2", "rpw_segment_fused", "rpw_segment_clouds", "rpw_last_clouds", "rpw_sample_ground_and_obstacles", "rpw_segment_device", "rpw_debug_keys", "rpw_debug_enable_nodes", "rpw_debug_nodes",
            "rpw_debug_eig3", "rpw_debug_normal", "rpw_debug_atan2", "rpw_debug_fit_timing", "rpw_debug_fit_trace", "rpw_profile_enable", "rpw_profile_read", "rpw_host_alloc", "rpw_host_free", "rpw_kernel_launches", "rpw_abi_version"]
 
 _lib = None
@@ -97,6 +97,8 @@ def load_library() -> C.CDLL:
     lib.rpw_segment_clouds.restype = C.c_int
     lib.rpw_last_clouds.argtypes = [vp, vp, vp, C.c_int, C.POINTER(C.c_uint64)]
     lib.rpw_last_clouds.restype = C.c_int
+    lib.rpw_sample_ground_and_obstacles.argtypes = [vp, C.c_float, C.c_float, C.c_float, sz, C.c_uint64, vp, sz, C.POINTER(sz), C.POINTER(sz)]
+    lib.rpw_sample_ground_and_obstacles.restype = C.c_int
     lib.rpw_segment_device.argtypes = [vp, vp, C.POINTER(C.c_uint64), sz, vp]; lib.rpw_segment_device.restype = C.c_int
     lib.rpw_debug_keys.argtypes = [vp, vp, sz]; lib.rpw_debug_keys.restype = C.c_int
     lib.rpw_debug_enable_nodes.argtypes = [vp, C.c_int]; lib.rpw_debug_enable_nodes.restype = C.c_int
@@ -285,6 +287,15 @@ class Handle:
         self._check(self.lib.rpw_last_clouds(self._h, g.ctypes.data, ng.ctypes.data, 0, cnt))
         return [(g[int(off[b]):int(off[b]) + int(cnt[2 * b])].copy(), ng[int(off[b]):int(off[b]) + int(cnt[2 * b + 1])].copy())
                 for b in range(len(n))]
+
+    def sample_ground_and_obstacles(self, n_points, target_height=1.1, base_tol=0.5, ego_radius=2.5, sample_size=2000, seed=0):
+        """sampleGroundAndObstacles for the last single-scan call: (ground sample, obstacles) as (k, 3) arrays."""
+        cap = int(n_points) + int(sample_size)
+        out = np.empty((max(cap, 1), 3), np.float32)
+        ng, no = C.c_size_t(), C.c_size_t()
+        self._check(self.lib.rpw_sample_ground_and_obstacles(self._h, target_height, base_tol, ego_radius, int(sample_size), int(seed),
+                                                             out.ctypes.data, cap, C.byref(ng), C.byref(no)))
+        return out[:ng.value].copy(), out[ng.value:ng.value + no.value].copy()
 
     def last_clouds_device(self, d_ground_ptr: int, d_nonground_ptr: int, n_scans: int):
         """Same with caller-provided device buffers (3 floats per point of the call each); returns counts [n_scans, 2]."""

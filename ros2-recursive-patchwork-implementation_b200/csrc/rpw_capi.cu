@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <new>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -85,6 +86,8 @@ struct rpw_handle {
     uint32_t* h_scan_counts = nullptr;  // pinned copy
     float* d_cloud_g = nullptr;         // 3 floats x cap_points each, only for host-bound clouds
     float* d_cloud_ng = nullptr;
+    uint32_t* d_sample_idx = nullptr;   // rpw_sample_ground_and_obstacles: indices of the ground context sample
+    size_t sample_idx_cap = 0;
     uint32_t* d_trace_count = nullptr;
     uint32_t trace_cap = 0;
     bool timing_enabled = false;
@@ -237,7 +240,7 @@ void rpw_destroy(rpw_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_in); cudaFree(h->d_keys); cudaFree(h->d_labels); cudaFree(h->d_sortedA); cudaFree(h->d_bufB);
-    cudaFree(h->d_bufC); cudaFree(h->d_gmask); cudaFree(h->d_dbg_count); cudaFree(h->d_trace); cudaFree(h->d_trace_count); cudaFree(h->d_cmp_cnt); cudaFree(h->d_scan_counts); cudaFree(h->d_cloud_g); cudaFree(h->d_cloud_ng);
+    cudaFree(h->d_bufC); cudaFree(h->d_gmask); cudaFree(h->d_dbg_count); cudaFree(h->d_trace); cudaFree(h->d_trace_count); cudaFree(h->d_cmp_cnt); cudaFree(h->d_scan_counts); cudaFree(h->d_cloud_g); cudaFree(h->d_cloud_ng); cudaFree(h->d_sample_idx);
     if (h->h_scan_counts) cudaFreeHost(h->h_scan_counts);
     cudaFree(h->d_scan_off); cudaFree(h->d_chunk_base); cudaFree(h->d_dbg_nodes); cudaFree(h->d_timing); cudaFree(h->d_fusion);
     if (h->h_fusion) cudaFreeHost(h->h_fusion);
@@ -936,6 +939,69 @@ int rpw_last_clouds(rpw_handle* h, float* ground_xyz, float* nonground_xyz, int 
         }
         RPW_CUDA(h, cudaStreamSynchronize(h->stream));
     }
+    return RPW_OK;
+}
+
+int rpw_sample_ground_and_obstacles(rpw_handle* h, float target_height, float base_tol, float ego_radius, size_t sample_size,
+                                    uint64_t seed, float* out_xyz, size_t out_cap_points, size_t* n_ground_sample, size_t* n_obstacles) {
+    if (!h) return RPW_ERR_BAD_ARG;
+    if (n_ground_sample) *n_ground_sample = 0;
+    if (n_obstacles) *n_obstacles = 0;
+    if (!out_xyz) RPW_FAIL(h, RPW_ERR_BAD_ARG, "out_xyz must not be NULL");
+    if (h->last_batch > 1) RPW_FAIL(h, RPW_ERR_BAD_ARG, "the last call segmented %zu scans; this post-filter takes one", h->last_batch);
+    if (h->last_batch == 0 || h->last_total == 0) return RPW_OK;
+    uint64_t counts[2] = {0, 0};
+    int rc = rpw_last_clouds(h, nullptr, nullptr, 0, counts);  // the two clouds, left on the device
+    if (rc != RPW_OK) return rc;
+    const size_t n_g = (size_t)counts[0], n_ng = (size_t)counts[1];
+    if (n_ng == 0) {  // :435-437: without non-ground points the whole ground cloud is returned
+        if (n_g > out_cap_points) RPW_FAIL(h, RPW_ERR_CAPACITY, "%zu points do not fit the output buffer (%zu)", n_g, out_cap_points);
+        if (n_g) RPW_CUDA(h, cudaMemcpyAsync(out_xyz, h->d_cloud_g, n_g * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        RPW_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (n_ground_sample) *n_ground_sample = n_g;
+        return RPW_OK;
+    }
+    // ground context: `sample_size` distinct indices drawn as PointCloudProcessor::randomSubsample draws them
+    // (uniform draws, repeats rejected, order of the draws kept; point_cloud_processor.cpp:122-148)
+    std::vector<uint32_t> idx;
+    if (n_g <= sample_size) {
+        idx.resize(n_g);
+        for (size_t i = 0; i < n_g; ++i) idx[i] = (uint32_t)i;
+    } else {
+        std::mt19937 gen(seed ? (std::mt19937::result_type)seed : std::random_device{}());
+        std::uniform_int_distribution<size_t> dis(0, n_g - 1);
+        std::vector<bool> selected(n_g, false);
+        idx.reserve(sample_size);
+        while (idx.size() < sample_size) {
+            const size_t i = dis(gen);
+            if (!selected[i]) { selected[i] = true; idx.push_back((uint32_t)i); }
+        }
+    }
+    const size_t k = idx.size();
+    if (3 * (k + n_ng) > 4 * h->cap_points) RPW_FAIL(h, RPW_ERR_CAPACITY, "sample of %zu points exceeds the device scratch", k);
+    if (k > h->sample_idx_cap) {
+        cudaFree(h->d_sample_idx);
+        h->d_sample_idx = nullptr;
+        h->sample_idx_cap = 0;
+        RPW_CUDA(h, cudaMalloc(&h->d_sample_idx, k * sizeof(uint32_t)));
+        h->sample_idx_cap = k;
+    }
+    float* d_out = reinterpret_cast<float*>(h->d_bufB);  // a level buffer of the fit: free between calls
+    if (k) {
+        RPW_CUDA(h, cudaMemcpyAsync(h->d_sample_idx, idx.data(), k * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+        RPW_CUDA(h, launch_gather_xyz(h->stream, h->d_cloud_g, h->d_sample_idx, (uint32_t)k, d_out));
+    }
+    RPW_CUDA(h, launch_obstacles(h->stream, h->d_cloud_ng, (uint32_t)n_ng, target_height, base_tol, ego_radius, h->d_cmp_cnt,
+                                 d_out + 3 * k, h->d_scan_counts));
+    h->launches += 3;
+    RPW_CUDA(h, cudaMemcpyAsync(h->h_scan_counts, h->d_scan_counts, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    RPW_CUDA(h, cudaStreamSynchronize(h->stream));  // (also orders the index upload before `idx` goes out of scope)
+    const size_t n_obs = h->h_scan_counts[0];
+    if (k + n_obs > out_cap_points) RPW_FAIL(h, RPW_ERR_CAPACITY, "%zu points do not fit the output buffer (%zu)", k + n_obs, out_cap_points);
+    if (k + n_obs) RPW_CUDA(h, cudaMemcpyAsync(out_xyz, d_out, (k + n_obs) * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    RPW_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (n_ground_sample) *n_ground_sample = k;
+    if (n_obstacles) *n_obstacles = n_obs;
     return RPW_OK;
 }
 

@@ -1209,6 +1209,85 @@ __global__ void __launch_bounds__(kBinThreads) rpw_compact_scatter_kernel(const 
 }
 
 // =============================================================================================
+// K5: sampleGroundAndObstacles post-filter (RP/src/recursive_patchwork.cpp:428-465) on the two clouds K4
+// left on the device: obstacles = non-ground points outside the ego radius (computeDistance2D > r, :64-75)
+// whose height is within base_tol of target_height, order kept (the same stable compaction as K4 with a
+// predicate instead of a label); ground context = the ground points at indices the host drew.
+// =============================================================================================
+__device__ __forceinline__ bool is_obstacle(const float* __restrict__ p, float target, float tol, float ego) {
+    return range2d(p[0], p[1]) > ego && fabsf(p[2] - target) <= tol;
+}
+
+__global__ void __launch_bounds__(kBinThreads) rpw_obstacle_count_kernel(const float* __restrict__ xyz, uint32_t n, float target, float tol, float ego,
+                                                                        uint32_t* __restrict__ cnt) {
+    __shared__ uint32_t s_c;
+    const uint32_t base = blockIdx.x * kBinChunk;
+    if (threadIdx.x == 0) s_c = 0;
+    __syncthreads();
+    uint32_t c = 0;
+    for (int k = 0; k < kBinChunk / kBinThreads; ++k) {
+        const uint32_t i = base + k * kBinThreads + threadIdx.x;
+        c += i < n && is_obstacle(xyz + 3 * (size_t)i, target, tol, ego);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_c, c);
+    __syncthreads();
+    if (threadIdx.x == 0) cnt[blockIdx.x] = s_c;
+}
+
+__global__ void __launch_bounds__(kBinThreads) rpw_obstacle_scatter_kernel(const float* __restrict__ xyz, uint32_t n, float target, float tol, float ego,
+                                                                          const uint32_t* __restrict__ cnt, float* __restrict__ out,
+                                                                          uint32_t* __restrict__ total) {
+    constexpr int kWarps = kBinThreads / 32;
+    constexpr int kPerWarp = kBinChunk / kWarps;
+    __shared__ uint32_t s_base, s_warp[kWarps];
+    const uint32_t base = blockIdx.x * kBinChunk;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    {
+        uint32_t before = 0, all = 0;
+        for (uint32_t q = threadIdx.x; q < gridDim.x; q += kBinThreads) { const uint32_t v = cnt[q]; all += v; if (q < blockIdx.x) before += v; }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { before += __shfl_xor_sync(0xffffffffu, before, d); all += __shfl_xor_sync(0xffffffffu, all, d); }
+        if (lane == 0) { atomicAdd(&s_base, before); if (blockIdx.x == 0) atomicAdd(total, all); }
+    }
+    uint32_t wc = 0;
+    for (int r = 0; r < kPerWarp / 32; ++r) {
+        const uint32_t i = base + warp * kPerWarp + r * 32 + lane;
+        wc += __popc(__ballot_sync(0xffffffffu, i < n && is_obstacle(xyz + 3 * (size_t)i, target, tol, ego)));
+    }
+    if (lane == 0) s_warp[warp] = wc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int w = 0; w < kWarps; ++w) { const uint32_t v = s_warp[w]; s_warp[w] = run; run += v; }
+    }
+    __syncthreads();
+    uint32_t o = s_base + s_warp[warp];
+    const unsigned lt = (1u << lane) - 1u;
+    for (int r = 0; r < kPerWarp / 32; ++r) {
+        const uint32_t i = base + warp * kPerWarp + r * 32 + lane;
+        const bool keep = i < n && is_obstacle(xyz + 3 * (size_t)i, target, tol, ego);
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            float* dst = out + 3 * (size_t)(o + __popc(m & lt));
+            const float* src = xyz + 3 * (size_t)i;
+            dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+        }
+        o += __popc(m);
+    }
+}
+
+__global__ void rpw_gather_xyz_kernel(const float* __restrict__ xyz, const uint32_t* __restrict__ idx, uint32_t k, float* __restrict__ out) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= k) return;
+    const float* src = xyz + 3 * (size_t)idx[j];
+    out[3 * (size_t)j] = src[0]; out[3 * (size_t)j + 1] = src[1]; out[3 * (size_t)j + 2] = src[2];
+}
+
+// =============================================================================================
 // unit-test entry points
 // =============================================================================================
 __global__ void rpw_eig3_kernel(const float* __restrict__ mats, size_t count, float* __restrict__ evals, float* __restrict__ evecs) {
@@ -1363,6 +1442,23 @@ cudaError_t launch_compact(cudaStream_t st, const PointLayout& lay, const float*
     rpw_compact_count_kernel<<<grid, kBinThreads, 0, st>>>(labels, scan_off, chunk_base, cnt);
     if (lay.vec4) rpw_compact_scatter_kernel<true><<<grid, kBinThreads, 0, st>>>(pts, lay, labels, scan_off, chunk_base, cnt, fusion, ground, nonground, scan_counts);
     else rpw_compact_scatter_kernel<false><<<grid, kBinThreads, 0, st>>>(pts, lay, labels, scan_off, chunk_base, cnt, fusion, ground, nonground, scan_counts);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_obstacles(cudaStream_t st, const float* nonground_xyz, uint32_t n, float target, float tol, float ego, uint32_t* cnt,
+                             float* out, uint32_t* total) {
+    cudaError_t e = cudaMemsetAsync(total, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    if (n == 0) return cudaSuccess;
+    const unsigned grid = (n + kBinChunk - 1) / kBinChunk;
+    rpw_obstacle_count_kernel<<<grid, kBinThreads, 0, st>>>(nonground_xyz, n, target, tol, ego, cnt);
+    rpw_obstacle_scatter_kernel<<<grid, kBinThreads, 0, st>>>(nonground_xyz, n, target, tol, ego, cnt, out, total);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather_xyz(cudaStream_t st, const float* xyz, const uint32_t* idx, uint32_t k, float* out) {
+    if (k == 0) return cudaSuccess;
+    rpw_gather_xyz_kernel<<<(k + 255) / 256, 256, 0, st>>>(xyz, idx, k, out);
     return cudaGetLastError();
 }
 

@@ -167,29 +167,19 @@ public:
     // the reference too, so only sizes are reproducible.
     std::vector<Point3D> sampleGroundAndObstacles(const std::vector<Point3D>& points, float target_height = 1.1f,
                                                   float base_tol = 0.5f) {
-        auto clouds = filterGroundPoints(points);
-        std::vector<Point3D>& ground = clouds.first;
-        if (clouds.second.empty()) return ground;
-        std::vector<Point3D> obstacles;
-        for (const Point3D& p : clouds.second) {
-            if (!(std::sqrt(p.x * p.x + p.y * p.y) > 2.5f)) continue;  // ego vehicle
-            if (std::abs(p.z - target_height) <= base_tol) obstacles.push_back(p);
-        }
+        // segmentation, cloud assembly, ego / height-band filter and the 2000-point ground context sample all on
+        // the device (RP/src/recursive_patchwork.cpp:428-465); the host only draws the sample's indices
         std::vector<Point3D> result;
-        const std::size_t want = std::min<std::size_t>(2000, ground.size());
-        if (ground.size() <= want) {
-            result = ground;
-        } else {
-            std::mt19937 gen{std::random_device{}()};
-            std::uniform_int_distribution<std::size_t> pick(0, ground.size() - 1);
-            std::vector<bool> taken(ground.size(), false);
-            result.reserve(want + obstacles.size());
-            while (result.size() < want) {
-                const std::size_t i = pick(gen);
-                if (!taken[i]) { taken[i] = true; result.push_back(ground[i]); }
-            }
-        }
-        result.insert(result.end(), obstacles.begin(), obstacles.end());
+        if (points.empty()) return result;
+        ensure(points.size());
+        std::vector<std::uint8_t> labels(points.size());
+        check(rpw_segment(handle_, &points[0].x, points.size(), sizeof(Point3D), labels.data(), nullptr));
+        static_assert(sizeof(Point3D) == 3 * sizeof(float), "Point3D must be packed xyz");
+        result.resize(points.size() + 2000);
+        std::size_t n_ground = 0, n_obstacles = 0;
+        check(rpw_sample_ground_and_obstacles(handle_, target_height, base_tol, 2.5f, 2000, 0, &result[0].x, result.size(),
+                                              &n_ground, &n_obstacles));
+        result.resize(n_ground + n_obstacles);
         return result;
     }
 

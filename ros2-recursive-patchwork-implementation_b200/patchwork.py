@@ -81,6 +81,17 @@ class RecursivePatchwork:
         ground, non_ground, _ = self._handle.segment_clouds(a)  # assembled on the device (K4), the host only copies
         return ground, non_ground
 
+    def sampleGroundAndObstacles(self, points, target_height: float = 1.1, base_tol: float = 0.5, seed: int = 0):
+        """RP/src/recursive_patchwork.cpp:428-465: a 2000-point random ground context sample followed by the
+        non-ground points outside the 2.5 m ego radius within base_tol of target_height.  All on the device;
+        seed = 0 draws like the reference (unseeded), any other value is reproducible."""
+        a = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, np.shape(points)[-1] if np.ndim(points) == 2 else 3)
+        if len(a) == 0:
+            return np.zeros((0, 3), np.float32)
+        self._handle.segment(a)
+        ground, obstacles = self._handle.sample_ground_and_obstacles(len(a), target_height, base_tol, 2.5, 2000, seed)
+        return np.concatenate([ground, obstacles])
+
     def filterGroundLabels(self, points) -> np.ndarray:
         """The north-star addition: per-input-point labels (0 non-ground, 1 ground, 2 beyond
         the filtering radius, 3 dropped as non-finite)."""

@@ -154,6 +154,43 @@ def test_device_result_assembly_fused(rpw, h, oracle):
     assert np.array_equal(ng.view(np.uint32), eng.view(np.uint32))
 
 
+def test_sample_ground_and_obstacles_on_device(rpw, h, oracle):
+    """SURVEY section 8f row 2 (RP/src/recursive_patchwork.cpp:428-465): obstacles exactly as the reference's
+    loops select them from the non-ground cloud, ground context = 2000 distinct ground points (the reference
+    draws them unseeded, so only membership and count are comparable)."""
+    cfg = rpw.PatchworkConfig(filtering_radius=60.0)
+    h.set_config(cfg.to_c())
+    pts = rpw.synth.spinning_scan(1500, 64, 600)
+    labels = h.segment(pts)
+    o = oracle.run(cfg, pts)["labels"]
+    assert (labels == o).mean() >= 0.999
+    p = pts[:, :3]
+    eg, eng = _expected_clouds(p, labels)
+    for target, tol in ((1.1, 0.5), (0.3, 0.25)):
+        sample, obstacles = h.sample_ground_and_obstacles(len(pts), target, tol, 2.5, 2000, seed=7)
+        d = np.sqrt(eng[:, 0] * eng[:, 0] + eng[:, 1] * eng[:, 1], dtype=np.float32)
+        want = eng[(d > np.float32(2.5)) & (np.abs(eng[:, 2] - np.float32(target)) <= np.float32(tol))]
+        assert np.array_equal(obstacles, want) and len(want) > 0
+        assert len(sample) == min(2000, len(eg))
+        as_rows = lambda a: {r.tobytes() for r in np.ascontiguousarray(a)}
+        assert len(as_rows(sample)) == len(sample) or len(as_rows(eg)) < len(eg)  # distinct draws (unless the cloud itself repeats a point)
+        assert as_rows(sample) <= as_rows(eg)
+    again, _ = h.sample_ground_and_obstacles(len(pts), 1.1, 0.5, 2.5, 2000, seed=7)
+    first, _ = h.sample_ground_and_obstacles(len(pts), 1.1, 0.5, 2.5, 2000, seed=7)
+    assert np.array_equal(again, first)  # a seed makes the draw reproducible
+    # fewer ground points than the sample size: all of them, in order; no non-ground points: the whole ground cloud
+    small = rpw.synth.testsuite_cloud(61, 900)
+    lab = h.segment(small)
+    sg, so = h.sample_ground_and_obstacles(len(small), 1.1, 0.5, 2.5, 2000, seed=3)
+    assert np.array_equal(sg, small[:, :3][lab == 1])
+    flat = np.zeros((500, 3), np.float32)
+    flat[:, 0] = np.linspace(3.0, 3.4, 500); flat[:, 1] = np.linspace(0.1, 0.2, 500); flat[:, 2] = 0.01  # one flat patch
+    lab = h.segment(flat)
+    assert (lab == 1).all()
+    sg, so = h.sample_ground_and_obstacles(len(flat), 1.1, 0.5, 2.5, 100, seed=3)
+    assert np.array_equal(sg, flat) and len(so) == 0
+
+
 def test_python_mirror_class(rpw, oracle):
     cfg = rpw.PatchworkConfig(sensor_height=1.2, filtering_radius=50.0, num_sectors=8, max_iter=50)  # testBasicFunctionality's config
     rp = rpw.RecursivePatchwork(cfg, max_points=1 << 16)
