@@ -224,6 +224,18 @@ int rpw_last_clouds(rpw_handle* h, float* ground_xyz, float* nonground_xyz, int 
 int rpw_sample_ground_and_obstacles(rpw_handle* h, float target_height, float base_tol, float ego_radius, size_t sample_size,
                                     uint64_t seed, float* out_xyz, size_t out_cap_points, size_t* n_ground_sample, size_t* n_obstacles);
 
+/* Bird's-eye-view rasters of RP/src/visualization.cpp:18-113 for the scan of this handle's LAST single-scan call, drawn
+ * on the device from the clouds of rpw_last_clouds.  bgr_out: HOST buffer of height * width * 3 bytes, row-major BGR
+ * (the layout of the reference's cv::Mat CV_8UC3), black background; pixel = int((p - min) * size / (max - min)) with
+ * the reference's float operations; where several points share a pixel the last one drawn wins, as in the reference.
+ *   RPW_BEV_CLASSES: createGroundNonGroundImage(ground, non_ground) (:47-80): ground green, then non-ground red.
+ *   RPW_BEV_HEIGHT_NONGROUND: createBEVImage(non_ground) (:18-45, main.cpp:297): (i, i, 255), i = clamp((z + 2) * 50).
+ *   RPW_BEV_HEIGHT_ALL: createBEVImage over the ground cloud followed by the non-ground cloud. */
+#define RPW_BEV_CLASSES 0
+#define RPW_BEV_HEIGHT_NONGROUND 1
+#define RPW_BEV_HEIGHT_ALL 2
+int rpw_bev_image(rpw_handle* h, int mode, int width, int height, float x_min, float y_min, float x_max, float y_max, uint8_t* bgr_out);
+
 /* One scan, with the two clouds the reference returns, in the reference's order (rpw_segment + rpw_last_clouds).
  * ground_xyz / nonground_xyz: caller buffers of 3*n floats each (either may be NULL). */
 int rpw_segment_clouds(rpw_handle* h, const float* xyz, size_t n, size_t stride_bytes, uint8_t* labels_out,

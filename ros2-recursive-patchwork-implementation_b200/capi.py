@@ -53,7 +53,7 @@ NODE_DTYPE = np.dtype([("scan", "<i4"), ("root", "<i4"), ("depth", "<i4"), ("sta
 # Every symbol include/rpw_b200.h declares (tests check that the library exports all of them).
 EXPORTS = ["rpw_default_config", "rpw_zone_model", "rpw_create", "rpw_destroy", "rpw_set_config", "rpw_get_config",
            "rpw_set_plane_solver", "rpw_set_stream", "rpw_last_error", "rpw_segment", "rpw_segment_batch", "rpw_segment_batch_async", "rpw_wait",
-           "rpw_segment_pc2", "rpw_segment_fused", "rpw_segment_clouds", "rpw_last_clouds", "rpw_sample_ground_and_obstacles", "rpw_segment_device", "rpw_debug_keys", "rpw_debug_enable_nodes", "rpw_debug_nodes",
+           "rpw_segment_pc2", "rpw_segment_fused", "rpw_segment_clouds", "rpw_last_clouds", "rpw_sample_ground_and_obstacles", "rpw_bev_image", "rpw_segment_device", "rpw_debug_keys", "rpw_debug_enable_nodes", "rpw_debug_nodes",
            "rpw_debug_eig3", "rpw_debug_normal", "rpw_debug_atan2", "rpw_debug_fit_timing", "rpw_debug_fit_trace", "rpw_profile_enable", "rpw_profile_read", "rpw_host_alloc", "rpw_host_free", "rpw_kernel_launches", "rpw_abi_version"]
 
 _lib = None
@@ -99,6 +99,8 @@ def load_library() -> C.CDLL:
     lib.rpw_last_clouds.restype = C.c_int
     lib.rpw_sample_ground_and_obstacles.argtypes = [vp, C.c_float, C.c_float, C.c_float, sz, C.c_uint64, vp, sz, C.POINTER(sz), C.POINTER(sz)]
     lib.rpw_sample_ground_and_obstacles.restype = C.c_int
+    lib.rpw_bev_image.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, vp]
+    lib.rpw_bev_image.restype = C.c_int
     lib.rpw_segment_device.argtypes = [vp, vp, C.POINTER(C.c_uint64), sz, vp]; lib.rpw_segment_device.restype = C.c_int
     lib.rpw_debug_keys.argtypes = [vp, vp, sz]; lib.rpw_debug_keys.restype = C.c_int
     lib.rpw_debug_enable_nodes.argtypes = [vp, C.c_int]; lib.rpw_debug_enable_nodes.restype = C.c_int
@@ -296,6 +298,14 @@ class Handle:
         self._check(self.lib.rpw_sample_ground_and_obstacles(self._h, target_height, base_tol, ego_radius, int(sample_size), int(seed),
                                                              out.ctypes.data, cap, C.byref(ng), C.byref(no)))
         return out[:ng.value].copy(), out[ng.value:ng.value + no.value].copy()
+
+    BEV_CLASSES, BEV_HEIGHT_NONGROUND, BEV_HEIGHT_ALL = 0, 1, 2
+
+    def bev_image(self, mode, width, height, x_min, y_min, x_max, y_max):
+        """BEV raster of the last single-scan call: (height, width, 3) uint8, BGR."""
+        img = np.empty((int(height), int(width), 3), np.uint8)
+        self._check(self.lib.rpw_bev_image(self._h, int(mode), int(width), int(height), x_min, y_min, x_max, y_max, img.ctypes.data))
+        return img
 
     def last_clouds_device(self, d_ground_ptr: int, d_nonground_ptr: int, n_scans: int):
         """Same with caller-provided device buffers (3 floats per point of the call each); returns counts [n_scans, 2]."""

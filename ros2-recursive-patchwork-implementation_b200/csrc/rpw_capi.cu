@@ -87,6 +87,8 @@ struct rpw_handle {
     float* d_cloud_g = nullptr;         // 3 floats x cap_points each, only for host-bound clouds
     float* d_cloud_ng = nullptr;
     uint32_t* d_sample_idx = nullptr;   // rpw_sample_ground_and_obstacles: indices of the ground context sample
+    uint32_t* d_bev_owner = nullptr;    // rpw_bev_image: winning draw index per pixel, then the BGR image behind it
+    size_t bev_pixels_cap = 0;
     size_t sample_idx_cap = 0;
     uint32_t* d_trace_count = nullptr;
     uint32_t trace_cap = 0;
@@ -240,7 +242,7 @@ void rpw_destroy(rpw_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_in); cudaFree(h->d_keys); cudaFree(h->d_labels); cudaFree(h->d_sortedA); cudaFree(h->d_bufB);
-    cudaFree(h->d_bufC); cudaFree(h->d_gmask); cudaFree(h->d_dbg_count); cudaFree(h->d_trace); cudaFree(h->d_trace_count); cudaFree(h->d_cmp_cnt); cudaFree(h->d_scan_counts); cudaFree(h->d_cloud_g); cudaFree(h->d_cloud_ng); cudaFree(h->d_sample_idx);
+    cudaFree(h->d_bufC); cudaFree(h->d_gmask); cudaFree(h->d_dbg_count); cudaFree(h->d_trace); cudaFree(h->d_trace_count); cudaFree(h->d_cmp_cnt); cudaFree(h->d_scan_counts); cudaFree(h->d_cloud_g); cudaFree(h->d_cloud_ng); cudaFree(h->d_sample_idx); cudaFree(h->d_bev_owner);
     if (h->h_scan_counts) cudaFreeHost(h->h_scan_counts);
     cudaFree(h->d_scan_off); cudaFree(h->d_chunk_base); cudaFree(h->d_dbg_nodes); cudaFree(h->d_timing); cudaFree(h->d_fusion);
     if (h->h_fusion) cudaFreeHost(h->h_fusion);
@@ -1002,6 +1004,39 @@ int rpw_sample_ground_and_obstacles(rpw_handle* h, float target_height, float ba
     RPW_CUDA(h, cudaStreamSynchronize(h->stream));
     if (n_ground_sample) *n_ground_sample = k;
     if (n_obstacles) *n_obstacles = n_obs;
+    return RPW_OK;
+}
+
+int rpw_bev_image(rpw_handle* h, int mode, int width, int height, float x_min, float y_min, float x_max, float y_max, uint8_t* bgr_out) {
+    if (!h) return RPW_ERR_BAD_ARG;
+    if (!bgr_out || width <= 0 || height <= 0 || (long long)width * height > (1ll << 28))
+        RPW_FAIL(h, RPW_ERR_BAD_ARG, "bad image buffer or size %d x %d", width, height);
+    if (mode != RPW_BEV_CLASSES && mode != RPW_BEV_HEIGHT_NONGROUND && mode != RPW_BEV_HEIGHT_ALL) RPW_FAIL(h, RPW_ERR_BAD_ARG, "unknown BEV mode %d", mode);
+    if (h->last_batch > 1) RPW_FAIL(h, RPW_ERR_BAD_ARG, "the last call segmented %zu scans; the raster takes one", h->last_batch);
+    const size_t n_pixels = (size_t)width * (size_t)height;
+    if (h->last_batch == 0 || h->last_total == 0) { memset(bgr_out, 0, n_pixels * 3); return RPW_OK; }
+    uint64_t counts[2] = {0, 0};
+    int rc = rpw_last_clouds(h, nullptr, nullptr, 0, counts);  // the two clouds, left on the device
+    if (rc != RPW_OK) return rc;
+    if (n_pixels > h->bev_pixels_cap) {
+        cudaFree(h->d_bev_owner);
+        h->d_bev_owner = nullptr;
+        h->bev_pixels_cap = 0;
+        RPW_CUDA(h, cudaMalloc(&h->d_bev_owner, n_pixels * (sizeof(uint32_t) + 3)));
+        h->bev_pixels_cap = n_pixels;
+    }
+    uint8_t* d_img = reinterpret_cast<uint8_t*>(h->d_bev_owner + n_pixels);
+    // scale factors as the reference computes them (visualization.cpp:28-29)
+    const float x_scale = static_cast<float>(width) / (x_max - x_min), y_scale = static_cast<float>(height) / (y_max - y_min);
+    const uint32_t n_g = (uint32_t)counts[0], n_ng = (uint32_t)counts[1];
+    if (mode == RPW_BEV_HEIGHT_NONGROUND)
+        RPW_CUDA(h, launch_bev(h->stream, 1, h->d_cloud_ng, n_ng, nullptr, 0, width, height, x_min, y_min, x_scale, y_scale, h->d_bev_owner, d_img));
+    else
+        RPW_CUDA(h, launch_bev(h->stream, mode == RPW_BEV_CLASSES ? 0 : 1, h->d_cloud_g, n_g, h->d_cloud_ng, n_ng, width, height, x_min, y_min,
+                               x_scale, y_scale, h->d_bev_owner, d_img));
+    h->launches += 3;
+    RPW_CUDA(h, cudaMemcpyAsync(bgr_out, d_img, n_pixels * 3, cudaMemcpyDeviceToHost, h->stream));
+    RPW_CUDA(h, cudaStreamSynchronize(h->stream));
     return RPW_OK;
 }
 

@@ -1288,6 +1288,42 @@ __global__ void rpw_gather_xyz_kernel(const float* __restrict__ xyz, const uint3
 }
 
 // =============================================================================================
+// K6: bird's-eye-view rasters (RP/src/visualization.cpp:18-113) from K4's device-resident clouds.  The reference
+// draws the points one after the other, so the LAST point that falls on a pixel colours it; here every
+// point bids for its pixel with its draw-order index (atomicMax) and a second kernel colours each pixel
+// from the winner.  Pixel coordinates with the reference's operations: int((p - min) * scale), truncation.
+// =============================================================================================
+__global__ void rpw_bev_bid_kernel(const float* __restrict__ xyz, uint32_t n, uint32_t order0, int width, int height, float x_min, float y_min,
+                                   float x_scale, float y_scale, uint32_t* __restrict__ owner) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int x = (int)((xyz[3 * (size_t)j] - x_min) * x_scale);
+    const int y = (int)((xyz[3 * (size_t)j + 1] - y_min) * y_scale);
+    if (x >= 0 && x < width && y >= 0 && y < height) atomicMax(&owner[(size_t)y * width + x], order0 + j + 1u);
+}
+
+// mode 0: ground green / non-ground red (createGroundNonGroundImage, :47-80); mode 1: height colouring
+// (createBEVImage, :18-45).  Draw order: the n_first points of cloud a, then cloud b.
+__global__ void rpw_bev_paint_kernel(const uint32_t* __restrict__ owner, int n_pixels, int mode, const float* __restrict__ a, uint32_t n_first,
+                                     const float* __restrict__ b, uint8_t* __restrict__ bgr) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pixels) return;
+    const uint32_t o = owner[p];
+    uint8_t c0 = 0, c1 = 0, c2 = 0;  // cv::Scalar(0, 0, 0) background
+    if (o) {
+        const uint32_t j = o - 1u;
+        if (mode == 0) {
+            if (j < n_first) c1 = 255; else c2 = 255;  // Vec3b(0, 255, 0) / Vec3b(0, 0, 255)
+        } else {
+            const float z = j < n_first ? a[3 * (size_t)j + 2] : b[3 * (size_t)(j - n_first) + 2];
+            const int intensity = (int)fminf(255.0f, fmaxf(0.0f, (z + 2.0f) * 50.0f));
+            c0 = (uint8_t)intensity; c1 = (uint8_t)intensity; c2 = 255;
+        }
+    }
+    bgr[3 * (size_t)p] = c0; bgr[3 * (size_t)p + 1] = c1; bgr[3 * (size_t)p + 2] = c2;
+}
+
+// =============================================================================================
 // unit-test entry points
 // =============================================================================================
 __global__ void rpw_eig3_kernel(const float* __restrict__ mats, size_t count, float* __restrict__ evals, float* __restrict__ evecs) {
@@ -1442,6 +1478,17 @@ cudaError_t launch_compact(cudaStream_t st, const PointLayout& lay, const float*
     rpw_compact_count_kernel<<<grid, kBinThreads, 0, st>>>(labels, scan_off, chunk_base, cnt);
     if (lay.vec4) rpw_compact_scatter_kernel<true><<<grid, kBinThreads, 0, st>>>(pts, lay, labels, scan_off, chunk_base, cnt, fusion, ground, nonground, scan_counts);
     else rpw_compact_scatter_kernel<false><<<grid, kBinThreads, 0, st>>>(pts, lay, labels, scan_off, chunk_base, cnt, fusion, ground, nonground, scan_counts);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bev(cudaStream_t st, int mode, const float* a, uint32_t n_a, const float* b, uint32_t n_b, int width, int height,
+                       float x_min, float y_min, float x_scale, float y_scale, uint32_t* owner, uint8_t* bgr) {
+    const int n_pixels = width * height;
+    cudaError_t e = cudaMemsetAsync(owner, 0, (size_t)n_pixels * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    if (n_a) rpw_bev_bid_kernel<<<(n_a + 255) / 256, 256, 0, st>>>(a, n_a, 0u, width, height, x_min, y_min, x_scale, y_scale, owner);
+    if (n_b) rpw_bev_bid_kernel<<<(n_b + 255) / 256, 256, 0, st>>>(b, n_b, n_a, width, height, x_min, y_min, x_scale, y_scale, owner);
+    rpw_bev_paint_kernel<<<(n_pixels + 255) / 256, 256, 0, st>>>(owner, n_pixels, mode, a, n_a, b, bgr);
     return cudaGetLastError();
 }
 

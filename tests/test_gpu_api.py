@@ -191,6 +191,47 @@ def test_sample_ground_and_obstacles_on_device(rpw, h, oracle):
     assert np.array_equal(sg, flat) and len(so) == 0
 
 
+def _bev_reference(clouds_colours, width, height, x_min, y_min, x_max, y_max):
+    """Sequential drawing of RP/src/visualization.cpp (createBEVImage / createGroundNonGroundImage): float scale
+    factors, int truncation, later points overwrite earlier ones."""
+    img = np.zeros((height, width, 3), np.uint8)
+    xs = np.float32(width) / (np.float32(x_max) - np.float32(x_min))
+    ys = np.float32(height) / (np.float32(y_max) - np.float32(y_min))
+    for pts, colour in clouds_colours:
+        x = ((pts[:, 0] - np.float32(x_min)) * xs).astype(np.int32)   # C++ static_cast<int>: truncation
+        y = ((pts[:, 1] - np.float32(y_min)) * ys).astype(np.int32)
+        ok = (x >= 0) & (x < width) & (y >= 0) & (y < height)
+        col = colour(pts) if callable(colour) else np.broadcast_to(np.array(colour, np.uint8), (len(pts), 3))
+        for xi, yi, c in zip(x[ok], y[ok], col[ok]):  # in order: the last point on a pixel wins
+            img[yi, xi] = c
+    return img
+
+
+def test_bev_rasters_on_device(rpw, h, oracle):
+    """SURVEY section 8f row 4 (RP/src/visualization.cpp:18-113): the three rasters the CLI writes, drawn on the
+    device from the device-resident clouds, pixel for pixel equal to the reference's sequential drawing."""
+    cfg = rpw.PatchworkConfig(filtering_radius=60.0)
+    h.set_config(cfg.to_c())
+    pts = rpw.synth.spinning_scan(1600, 32, 500)
+    labels = h.segment(pts)
+    eg, eng = _expected_clouds(pts[:, :3], labels)
+
+    def height_colour(p):
+        i = np.minimum(np.float32(255.0), np.maximum(np.float32(0.0), (p[:, 2] + np.float32(2.0)) * np.float32(50.0))).astype(np.int32)
+        return np.stack([i, i, np.full_like(i, 255)], 1).astype(np.uint8)
+
+    for (w, hh, x0, y0, x1, y1) in ((200, 160, -40.0, -32.0, 40.0, 32.0), (64, 48, -10.0, 0.0, 30.0, 30.0)):
+        got = h.bev_image(h.BEV_CLASSES, w, hh, x0, y0, x1, y1)
+        assert np.array_equal(got, _bev_reference([(eg, (0, 255, 0)), (eng, (0, 0, 255))], w, hh, x0, y0, x1, y1))
+        got = h.bev_image(h.BEV_HEIGHT_NONGROUND, w, hh, x0, y0, x1, y1)
+        assert np.array_equal(got, _bev_reference([(eng, height_colour)], w, hh, x0, y0, x1, y1))
+        got = h.bev_image(h.BEV_HEIGHT_ALL, w, hh, x0, y0, x1, y1)
+        assert np.array_equal(got, _bev_reference([(eg, height_colour), (eng, height_colour)], w, hh, x0, y0, x1, y1))
+        assert got.any()
+    with pytest.raises(rpw.RpwError):
+        h.bev_image(7, 10, 10, 0, 0, 1, 1)
+
+
 def test_python_mirror_class(rpw, oracle):
     cfg = rpw.PatchworkConfig(sensor_height=1.2, filtering_radius=50.0, num_sectors=8, max_iter=50)  # testBasicFunctionality's config
     rp = rpw.RecursivePatchwork(cfg, max_points=1 << 16)
