@@ -272,7 +272,8 @@ int rpw_debug_atan2(rpw_handle* h, const float* y, const float* x, size_t count,
  * clears the 16 counters, then enables/disables the accounting for later calls.  Slots: 0 load+bbox,
  * 1 seeds, 2 covariance pass, 3 eigensolve, 4 distance/mask pass, 5 final fit, 6 leaf label write,
  * 7 split, 8 fetch, 9 grid barrier, 10 nodes, 11 plane-fit iterations, 12 load loop alone (before its reductions),
- * 13 block reduction of the distance pass, 14 eigensolve alone (QR solver). */
+ * 13 block reduction of the distance pass, 14 eigensolve alone (QR solver: cycles; hybrid solver: number of solves that
+ * took the QR path -- 3-4 % on the C4 / C5 test scenes). */
 int rpw_debug_fit_timing(rpw_handle* h, int enable, uint64_t* cycles16);
 
 /* Per-node timeline of the fit kernels (scheduling analysis: which SM ran which node when).

@@ -548,7 +548,10 @@ __device__ __forceinline__ void plane_normal(const float (&cv)[6], float cnt, fl
             smallest_eigvec_psd(cv[0], cv[1], cv[2], cv[3], cv[4], cv[5], ax, ay, az, &small_gap);
             // hybrid solver: where the eigenvector is ill-conditioned only the reference's own operation
             // sequence reproduces the reference's answer
-            if (hybrid && small_gap) plane_normal_exact(cv, cnt - 1.f, ax, ay, az);
+            if (hybrid && small_gap) {
+                plane_normal_exact(cv, cnt - 1.f, ax, ay, az);
+                if (timing && threadIdx.x == 0) atomicAdd(timing + 14, 1ull);  // (hybrid: slot 14 counts the QR solves)
+            }
         }
         if (az < 0.f) { ax = -ax; ay = -ay; az = -az; }  // :93-95
         if (threadIdx.x == 0) { bc[0] = ax; bc[1] = ay; bc[2] = az; }
