@@ -351,14 +351,18 @@ int rpw_create(const rpw_config* cfg, int device, size_t max_total_points, size_
     TRY(alloc_patch_buffers(h));
     TRY(alloc_level_buffers(h));
     // shared-memory budget of the fit kernel: points a block keeps resident
-    int cap = 8192;
+    // (the levels kernel: kLevelBlocksPerSm persistent blocks per SM share the shared memory; nodes of depth >= 1
+    // are mostly small, larger ones stream from L2)
+    int cap = ((220 * 1024 / kLevelBlocksPerSm) - 4096) / 13 / 256 * 256;
+    if (cap > 8192) cap = 8192;
     if (const char* s = getenv("RPW_FIT_SMEM_CAP")) { const int v = atoi(s); if (v >= 256 && v <= 16384) cap = v; }
     if (const char* s = getenv("RPW_WAVES")) { const int v = atoi(s); if (v >= 0) h->n_waves = v; }
     h->smem_cap = cap;
     int bps = 0;
     TRYC(fit_configure(cap, &bps));
     if (bps < 1) { h->err = "fit kernel does not fit on an SM"; return fail(RPW_ERR_CUDA); }
-    h->fit_blocks = h->num_sms;  // the levels kernel: one persistent block per SM
+    if (bps > kLevelBlocksPerSm) bps = kLevelBlocksPerSm;
+    h->fit_blocks = h->num_sms * bps;  // the levels kernel: persistent blocks, all resident (cooperative launch)
 #undef TRY
 #undef TRYC
     *out = h;

@@ -1039,7 +1039,7 @@ __device__ __forceinline__ void grid_barrier(uint32_t* ctr, uint32_t target) {
 }
 
 template <bool EXACT>
-__global__ void __launch_bounds__(kFitThreads, 1) rpw_fit_levels_kernel(FitArgs A) {
+__global__ void __launch_bounds__(kFitThreads, kLevelBlocksPerSm) rpw_fit_levels_kernel(FitArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int TT = kFitThreads;
     FitSmem S = carve_smem(smem_raw, A.smem_cap, TT / 32);
