@@ -232,6 +232,34 @@ def test_bev_rasters_on_device(rpw, h, oracle):
         h.bev_image(7, 10, 10, 0, 0, 1, 1)
 
 
+def test_changing_workload_on_one_handle(rpw, gpu_handle_factory, oracle):
+    """The fit kernels' grids are sized from the previous call's per-class patch counts; results must not
+    depend on how wrong that estimate is.  One handle sees very different calls in a row (a batch of
+    spinning scans, one big-patch frame, a tiny cloud, a deep-recursion scan, an empty call, the batch
+    again); every call is compared with the oracle."""
+    cfg = rpw.PatchworkConfig(filtering_radius=80.0)
+    hd = gpu_handle_factory(cfg, 1 << 20, 8)
+    batch = [rpw.synth.spinning_scan(7000 + i, 32, 700) for i in range(6)]
+    big = rpw.synth.solidstate_merged(2500, 300, 200)
+    tiny = rpw.synth.testsuite_cloud(71, 40)
+    deep = rpw.synth.spinning_scan(3300, 64, 1024, 1)
+    want = {id(a): oracle.run(cfg, a)["labels"] for a in batch + [big, tiny, deep]}
+
+    def check(clouds):
+        got = hd.segment_batch(clouds)
+        for a, l in zip(clouds, got):
+            assert (l == want[id(a)]).mean() >= 0.999, len(a)
+
+    for _ in range(2):
+        check(batch)
+        check([big])
+        check([tiny])
+        check([deep])
+        assert len(hd.segment(np.zeros((0, 3), np.float32))) == 0
+        check([tiny, big, batch[0], deep])
+    hd.close()
+
+
 def test_python_mirror_class(rpw, oracle):
     cfg = rpw.PatchworkConfig(sensor_height=1.2, filtering_radius=50.0, num_sectors=8, max_iter=50)  # testBasicFunctionality's config
     rp = rpw.RecursivePatchwork(cfg, max_points=1 << 16)
