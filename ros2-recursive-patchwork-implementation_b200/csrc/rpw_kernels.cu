@@ -277,7 +277,8 @@ constexpr int kRedMax = 16;
 constexpr int kMiscWords = 16;
 constexpr int kCapTiny = 1024;   // points a 64-thread block keeps in shared memory
 constexpr int kCapSmall = 4096;  // points a 128-thread block keeps in shared memory
-constexpr int kCapLarge = 8192;  // 512-thread block; larger patches stream from L2
+constexpr int kCapLarge = 8192;  // largest shared-memory slot (256-thread block); larger patches stream from L2 ...
+constexpr int kCapStream = 256;  // ... in 512-thread blocks that keep nothing resident
 
 // Sum of K floats over the block; every thread receives the totals (bitwise identical in all
 // threads).  One __syncthreads per call; the scratch area alternates so that back-to-back calls do
@@ -1430,7 +1431,8 @@ static cudaError_t set_smem(KernelT k, size_t bytes) {
 // blocks twice the memory it needs for its whole 40 us life), which is what bounds the fit phase.
 struct FitClass { int threads; uint32_t hi; int cap; };
 static const FitClass kFitClasses[kNumFitClasses] = {
-    {64, 1024, 1024}, {64, 2048, 2048}, {128, 3072, 3072}, {128, 4096, 4096}, {256, 5632, 5632}, {512, 0xFFFFFFFFu, kCapLarge},
+    {64, 1024, 1024}, {64, 2048, 2048}, {128, 3072, 3072}, {128, 4096, 4096}, {256, 5632, 5632}, {256, kCapLarge, kCapLarge},
+    {512, 0xFFFFFFFFu, kCapStream},
 };
 
 template <int TT>

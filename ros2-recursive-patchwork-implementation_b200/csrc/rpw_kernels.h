@@ -51,7 +51,7 @@ struct FitArgs {
     FitParams fp;
 };
 
-constexpr int kNumFitClasses = 6;  // size classes of the level-0 fit kernel (rpw_kernels.cu: kFitClasses)
+constexpr int kNumFitClasses = 7;  // size classes of the level-0 fit kernel (rpw_kernels.cu: kFitClasses)
 constexpr int kClsWords = 16;      // words of a class-count array: counts [0, kNumFitClasses), scan count in the last
 struct ClassBounds { uint32_t hi[kNumFitClasses]; };  // class c holds patches with hi[c-1] < n <= hi[c]
 ClassBounds fit_class_bounds();

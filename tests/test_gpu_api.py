@@ -14,7 +14,7 @@ def h(gpu_handle_factory):
 def test_native_library_is_the_one_running(rpw, h):
     before = h.kernel_launches()
     h.segment(rpw.synth.testsuite_cloud(1, 1000))
-    assert h.kernel_launches() - before == 10  # bin, offsets, scatter, fit roots x6 size classes, fit levels
+    assert h.kernel_launches() - before == 11  # bin, offsets, scatter, fit roots x7 size classes, fit levels
 
 
 def test_degenerate_inputs(rpw, h, oracle):
