@@ -366,7 +366,7 @@ def main():
     clocks = sampler.stop()
 
     # ---- single-scan latency: the reference's own use (one scan per ROS2 callback), synchronous
-    # rpw_segment on pinned host buffers, H2D + 10 launches + D2H per call ----
+    # rpw_segment on pinned host buffers, H2D + 11 launches + D2H per call ----
     lat_ms, other_shapes = None, None
     if rank == 0:
         h1 = rpw.Handle(cfg.to_c(), local_rank, POINTS_PER_SCAN + 4096, 1)
@@ -426,7 +426,7 @@ def main():
                        "l2": f"batch is {total * 16 / 1e6:.0f} MB of float4 input per GPU > 126 MB L2 (no flush needed)"},
             "mpoints_per_sec": value * POINTS_PER_SCAN / 1e6,
             "hbm_fraction_whole_path": ALG_BYTES_PER_POINT * (value / world) * POINTS_PER_SCAN / 1e9 / peak,
-            "roofline": {"bound": "hbm", "kernel": "fit phase = rpw_fit_roots_kernel<64|128|256|512> (six size classes on concurrent prioritised streams) + rpw_fit_levels_kernel, timed as one unit", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "fit phase = rpw_fit_roots_kernel<64|128|256|512> (seven size classes on concurrent prioritised streams) + rpw_fit_levels_kernel, timed as one unit", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_point": ALG_BYTES_PER_POINT, "ms_per_launch": fit_ms},
             "kernels": kernels,

@@ -7,7 +7,7 @@
 //   K2  rpw_scatter_kernel  stable counting-sort scatter of (x, y, z, input index) into
 //                           ring/sector patch segments (input order inside every patch, Q1)
 //   K3a rpw_fit_roots_kernel  fitPlaneAndSplit at depth 0 (RP/src/recursive_patchwork.cpp:109-308), one
-//                           block per listed ring/sector patch, six size classes (block shape and shared-
+//                           block per listed ring/sector patch, seven size classes (block shape and shared-
 //                           memory slot per class) launched on concurrent, prioritised streams;
 //                           per node: early-outs, seeds, iterated PCA plane fit with a register
 //                           3x3 eigensolve, residual mask, split (variance axis, exact radix-select

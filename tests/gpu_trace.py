@@ -30,7 +30,7 @@ t0 = tr["t_start_ns"].min()
 s = (tr["t_start_ns"] - t0) / 1e3; e = (tr["t_end_ns"] - t0) / 1e3  # us
 dur = e - s
 print(f"fit makespan {e.max():.1f} us")
-caps = [1024, 2048, 3072, 4096, 5632, 8192]
+caps = [1024, 2048, 3072, 4096, 5632, 8192, 256]
 def kb(c): return caps[c] * 13 / 1024 if c < len(caps) else 0
 print("class  nodes  mean_n  mean_it  mean_us  p99_us  first_start  last_start  last_end  KB*ms")
 for c in sorted(set(tr["size_class"])):
