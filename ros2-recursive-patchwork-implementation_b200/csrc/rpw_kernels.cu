@@ -26,6 +26,18 @@
 #ifndef RPW_LB128
 #define RPW_LB128 5  // resident blocks per SM the 128-thread fit kernels are compiled for (5 x 40 KB slots fill an SM)
 #endif
+#ifndef RPW_NEWTON_TOL_HYBRID
+// Last Newton step of the closed-form solve under the hybrid solver.  The hybrid solver only keeps the closed form
+// where the gap to the second eigenvalue is above 2 % of the matrix scale; there Newton converges quadratically, so
+// a step below 1e-7 leaves an error of ~1e-12 (one step fewer than running to 1e-13; labels unchanged).
+#define RPW_NEWTON_TOL_HYBRID 1e-7
+#endif
+#ifndef RPW_LB64
+#define RPW_LB64 8  // resident blocks per SM the 64-thread fit kernels are compiled for
+#endif
+#ifndef RPW_STREAM_THREADS
+#define RPW_STREAM_THREADS 512  // block size of the class whose patches stream from L2 (no shared-memory slot)
+#endif
 
 namespace rpw {
 
@@ -182,6 +194,8 @@ __global__ void __launch_bounds__(256) rpw_offsets_kernel(const uint64_t* __rest
 // 32-group come from __match_any_sync.  No atomics claim slots, so the result is deterministic
 // and stable regardless of scheduling (SURVEY Q1 needs that).
 // =============================================================================================
+// (64 registers, four blocks per SM.  Forcing five blocks changes nothing, six and more spill the key registers:
+// 0.343 / 0.397 / 0.459 ms per 512 scans for 5 / 6 / 8.)
 template <bool VEC4>
 __global__ void __launch_bounds__(kBinThreads) rpw_scatter_kernel(const float* __restrict__ pts, PointLayout lay, const uint64_t* __restrict__ scan_off,
                                                                  const uint32_t* __restrict__ chunk_base,
@@ -546,11 +560,14 @@ __device__ __forceinline__ void plane_normal(const float (&cv)[6], float cnt, fl
             if (timing && threadIdx.x == 0) atomicAdd(timing + 14, (unsigned long long)(clock64() - t0));
         } else {
             bool small_gap;
-            smallest_eigvec_psd(cv[0], cv[1], cv[2], cv[3], cv[4], cv[5], ax, ay, az, &small_gap);
+            smallest_eigvec_psd(cv[0], cv[1], cv[2], cv[3], cv[4], cv[5], ax, ay, az, &small_gap, hybrid ? RPW_NEWTON_TOL_HYBRID : 1e-13);
             // hybrid solver: where the eigenvector is ill-conditioned only the reference's own operation
             // sequence reproduces the reference's answer
             if (hybrid && small_gap) {
-                plane_normal_exact(cv, cnt - 1.f, ax, ay, az);
+                // out of line: taken by a few percent of the solves, and ~1100 instructions that would otherwise sit in
+                // the middle of the plane-fit loop (fit phase -2 %)
+                const Normal3 r = plane_normal_exact_cold(cv[0], cv[1], cv[2], cv[3], cv[4], cv[5], cnt - 1.f);
+                ax = r.x; ay = r.y; az = r.z;
                 if (timing && threadIdx.x == 0) atomicAdd(timing + 14, 1ull);  // (hybrid: slot 14 counts the QR solves)
             }
         }
@@ -616,22 +633,24 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
         // many independent 16-byte loads in flight per thread (16 where the register budget allows, else
         // 8): the pass is DRAM/L2-latency bound, every trip costs a full memory round trip
         constexpr int kWide = TT <= 256 ? 16 : 8;
+        // (.ca loads for level 0, so that the leaf's label write would find the input indices in L1: no gain)
+        auto ld_rec = [&](const float4* p) { return __ldcg(p); };
         uint32_t i = tid;
         for (; i + (kWide - 1) * TT < n; i += kWide * TT) {
             float4 v[kWide];
 #pragma unroll
-            for (int u = 0; u < kWide; ++u) v[u] = __ldcg(nv.src + i + u * TT);
+            for (int u = 0; u < kWide; ++u) v[u] = ld_rec(nv.src + i + u * TT);
 #pragma unroll
             for (int u = 0; u < kWide; ++u) take(i + u * TT, v[u]);
         }
         for (; i + 3 * TT < n; i += 4 * TT) {
             float4 v[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = __ldcg(nv.src + i + u * TT);
+            for (int u = 0; u < 4; ++u) v[u] = ld_rec(nv.src + i + u * TT);
 #pragma unroll
             for (int u = 0; u < 4; ++u) take(i + u * TT, v[u]);
         }
-        for (; i < n; i += TT) take(i, __ldcg(nv.src + i));
+        for (; i < n; i += TT) take(i, ld_rec(nv.src + i));
         sd[1] = ar.ok() ? 0.f : 1.f;
     }
     tick(12);
@@ -852,22 +871,23 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
         {
             const float4* rec = A.sortedA + nd.start;
             constexpr int kWide = TT <= 256 ? 16 : 8;
+            auto ld_w = [&](const float* p) { return __ldcg(p); };
             uint32_t i = tid;
             for (; i + (kWide - 1) * TT < n; i += kWide * TT) {
                 uint32_t w[kWide];
 #pragma unroll
-                for (int u = 0; u < kWide; ++u) w[u] = __float_as_uint(__ldcg(&rec[i + u * TT].w));
+                for (int u = 0; u < kWide; ++u) w[u] = __float_as_uint(ld_w(&rec[i + u * TT].w));
 #pragma unroll
                 for (int u = 0; u < kWide; ++u) A.labels[w[u]] = nv.mask(i + u * TT);
             }
             for (; i + 3 * TT < n; i += 4 * TT) {
                 uint32_t w[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) w[u] = __float_as_uint(__ldcg(&rec[i + u * TT].w));
+                for (int u = 0; u < 4; ++u) w[u] = __float_as_uint(ld_w(&rec[i + u * TT].w));
 #pragma unroll
                 for (int u = 0; u < 4; ++u) A.labels[w[u]] = nv.mask(i + u * TT);
             }
-            for (; i < n; i += TT) A.labels[__float_as_uint(__ldcg(&rec[i].w))] = nv.mask(i);
+            for (; i < n; i += TT) A.labels[__float_as_uint(ld_w(&rec[i].w))] = nv.mask(i);
         }
         if (tid == 0) dbg_record(A, nd, depth, RPW_NODE_FIT, iters, n_in, -1, cx, cy, cz, nx, ny, nz, residual, 0, mean_dist);
         tick(6);
@@ -988,7 +1008,7 @@ __device__ __forceinline__ FitSmem carve_smem(unsigned char* raw, int cap, int w
 // float solver, which is enough to tip chaotic two-layer patches the other way).
 // ---------------------------------------------------------------------------------------------
 template <int TT, bool EXACT>
-__global__ void __launch_bounds__(TT, (TT <= 64 ? 8 : TT <= 128 ? RPW_LB128 : TT <= 256 ? 3 : 2))
+__global__ void __launch_bounds__(TT, (TT <= 64 ? RPW_LB64 : TT <= 128 ? RPW_LB128 : TT <= 256 ? 3 : 2))
 rpw_fit_roots_kernel(FitArgs A, int cls, int cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // The class's work list and its length are read together (independent addresses, one latency).
@@ -1008,7 +1028,7 @@ rpw_fit_roots_kernel(FitArgs A, int cls, int cap) {
         TraceScope trace(A, nd.n, 0, cls);
         int iters = 0;
         if (nd.n <= (uint32_t)cap) iters = process_node<TT, true, EXACT>(A, nd, 0, S);
-        else if constexpr (TT >= 512) iters = process_node<TT, false, EXACT>(A, nd, 0, S);
+        else if constexpr (TT == RPW_STREAM_THREADS) iters = process_node<TT, false, EXACT>(A, nd, 0, S);
         trace.done(iters);
         if (threadIdx.x == 0) atomicAdd(A.stats + 1, 1u);
         if (next >= count) break;
@@ -1432,7 +1452,7 @@ static cudaError_t set_smem(KernelT k, size_t bytes) {
 struct FitClass { int threads; uint32_t hi; int cap; };
 static const FitClass kFitClasses[kNumFitClasses] = {
     {64, 1024, 1024}, {64, 2048, 2048}, {128, 3072, 3072}, {128, 4096, 4096}, {256, 5632, 5632}, {256, kCapLarge, kCapLarge},
-    {512, 0xFFFFFFFFu, kCapStream},
+    {RPW_STREAM_THREADS, 0xFFFFFFFFu, kCapStream},
 };
 
 template <int TT>

@@ -14,8 +14,8 @@ off = np.zeros(B + 1, np.uint64); off[1:] = np.cumsum([len(s) for s in scans])
 total = int(off[-1])
 d = torch.from_numpy(np.concatenate(scans)).cuda(); lab = torch.empty(total, dtype=torch.uint8, device="cuda")
 st = torch.cuda.Stream(); torch.cuda.set_stream(st)
-for solver in (0, 1):
-    for waves in (1, 2, 4, 8, 16):
+for solver in (2,):
+    for waves in (1, 2, 3, 4, 8):
         os.environ["RPW_WAVES"] = str(waves)
         h = rpw.Handle(rpw.PatchworkConfig(filtering_radius=80.0).to_c(), 0, total, B)
         h.set_stream(st.cuda_stream); h.set_plane_solver(solver)
