@@ -508,10 +508,16 @@ __device__ __forceinline__ void label_const(const FitArgs& A, const NodeRef& nd,
 // CONSECUTIVE points and loads them with three LDS.128 needs a quarter of the load instructions but
 // measured 6 % slower end to end: the passes are bound by the dependent latency of a thread's own
 // instruction stream at the low occupancy shared memory allows, not by issue slots.)
-constexpr int kUnroll = 4;
+#ifndef RPW_UNROLL
+#define RPW_UNROLL 4
+#endif
+#ifndef RPW_WIDE
+#define RPW_WIDE 8
+#endif
+constexpr int kUnroll = RPW_UNROLL;
 template <int TT, bool SMEM, bool WITH_MASK, typename F>
-__device__ __forceinline__ void for_points(const NodeView<SMEM>& nv, uint32_t n, F body) {
-    uint32_t i = threadIdx.x;
+__device__ __forceinline__ void for_points(const NodeView<SMEM>& nv, uint32_t n, uint32_t first, F body) {
+    uint32_t i = first + threadIdx.x;
     for (; i + (kUnroll - 1) * TT < n; i += kUnroll * TT) {
         float x[kUnroll], y[kUnroll], z[kUnroll];
         uint8_t m[kUnroll];
@@ -529,6 +535,69 @@ __device__ __forceinline__ void for_points(const NodeView<SMEM>& nv, uint32_t n,
         body(i, x, y, z, WITH_MASK ? nv.mask(i) : (uint8_t)1);
     }
 }
+template <int TT, bool SMEM, bool WITH_MASK, typename F>
+__device__ __forceinline__ void for_points(const NodeView<SMEM>& nv, uint32_t n, F body) {
+    for_points<TT, SMEM, WITH_MASK>(nv, n, 0u, body);
+}
+
+// The distance / mask / moments pass of the plane-fit loop on Blackwell's packed FP32 instructions (FADD2, FMUL2,
+// FFMA2: two IEEE single-precision operations per instruction, each rounded exactly like the scalar form).  A thread
+// takes its rows two at a time, one row per half of every register pair; the halves keep separate running sums that
+// are added at the end.  Covers the rows [0, 4 * TT * floor(n / (4 * TT))) and returns that bound; the caller's
+// scalar loop finishes the rest and adds into the same totals.  15 floating-point instructions per point instead of
+// 24 -- and measured 0.7 % SLOWER end to end (1.897 against 1.884 ms per 512 scans, labels identical): the packed
+// instructions occupy the FMA pipe for two cycles, so the pass, which is not bound by issue slots, gains nothing.
+// Compiled out by default (RPW_PACKED_PASS=1 builds it).
+#ifndef RPW_PACKED_PASS
+#define RPW_PACKED_PASS 0
+#endif
+#if RPW_PACKED_PASS
+template <int TT, bool SMEM>
+__device__ __forceinline__ uint32_t dist_pass_packed(const NodeView<SMEM>& nv, uint32_t n, float cx, float cy, float cz, float nx, float ny,
+                                                     float nz, float tau, float (&st)[12]) {
+    const float2 ncx = make_float2(-cx, -cx), ncy = make_float2(-cy, -cy), ncz = make_float2(-cz, -cz);
+    const float2 nx2 = make_float2(nx, nx), ny2 = make_float2(ny, ny), nz2 = make_float2(nz, nz);
+    float2 a[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) a[k] = make_float2(0.f, 0.f);
+    bool changed = false;
+    const uint32_t bound = (n / (4u * TT)) * (4u * TT);
+    for (uint32_t i = threadIdx.x; i < bound; i += 4 * TT) {
+        float x[4], y[4], z[4];
+        uint8_t m[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            nv.get(i + u * TT, x[u], y[u], z[u]);
+            m[u] = nv.mask(i + u * TT);
+        }
+#pragma unroll
+        for (int p = 0; p < 4; p += 2) {
+            const float2 dx = __fadd2_rn(make_float2(x[p], x[p + 1]), ncx);
+            const float2 dy = __fadd2_rn(make_float2(y[p], y[p + 1]), ncy);
+            const float2 dz = __fadd2_rn(make_float2(z[p], z[p + 1]), ncz);
+            const float2 p0 = __fmul2_rn(dx, nx2), p1 = __fmul2_rn(dy, ny2), p2 = __fmul2_rn(dz, nz2);
+            // Eigen's dot order p0 + (p1 + p2), see plane_dist.  Scalar additions on purpose: ptxas (12.9) contracts
+            // mul.rn.f32x2 followed by add.rn.f32x2 into FFMA2 even under -fmad=false, which would round the distance
+            // differently from the reference; it leaves packed products feeding scalar additions alone.
+            const float da = fabsf(__fadd_rn(p0.x, __fadd_rn(p1.x, p2.x))), db = fabsf(__fadd_rn(p0.y, __fadd_rn(p1.y, p2.y)));
+            const bool na = da < tau, nb = db < tau;
+            const float2 w = make_float2(na ? 1.f : 0.f, nb ? 1.f : 0.f);
+            a[5] = __fadd2_rn(a[5], make_float2(m[p] ? da : 0.f, m[p + 1] ? db : 0.f));
+            if (na != (m[p] != 0)) { changed = true; nv.set_mask(i + p * TT, na ? 1 : 0); }
+            if (nb != (m[p + 1] != 0)) { changed = true; nv.set_mask(i + (p + 1) * TT, nb ? 1 : 0); }
+            // masked-out rows contribute exact zeros (d * 0)
+            const float2 ex = __fmul2_rn(dx, w), ey = __fmul2_rn(dy, w), ez = __fmul2_rn(dz, w);
+            a[0] = __fadd2_rn(a[0], w); a[1] = __fadd2_rn(a[1], ex); a[2] = __fadd2_rn(a[2], ey); a[3] = __fadd2_rn(a[3], ez);
+            a[6] = __ffma2_rn(ex, ex, a[6]); a[7] = __ffma2_rn(ey, ex, a[7]); a[8] = __ffma2_rn(ey, ey, a[8]);
+            a[9] = __ffma2_rn(ez, ex, a[9]); a[10] = __ffma2_rn(ez, ey, a[10]); a[11] = __ffma2_rn(ez, ez, a[11]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 12; ++k) st[k] = a[k].x + a[k].y;
+    st[4] = changed ? 1.f : 0.f;
+    return bound;
+}
+#endif
 
 // Optional cycle accounting (rpw_debug_fit_timing): thread 0 of every block adds the cycles it spent
 // in each section of process_node to A.timing[section].  Sections: 0 load+bbox, 1 seeds, 2 covariance
@@ -630,11 +699,15 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
             mm[3] = fminf(mm[3], -v.x); mm[4] = fminf(mm[4], -v.y); mm[5] = fminf(mm[5], -v.z);
             if (depth == 0) sd[0] += ar.sqrt(v.x * v.x + v.y * v.y);  // range2d
         };
-        // many independent 16-byte loads in flight per thread (16 where the register budget allows, else
-        // 8): the pass is DRAM/L2-latency bound, every trip costs a full memory round trip
-        constexpr int kWide = TT <= 256 ? 16 : 8;
+        // many independent 16-byte loads in flight per thread: the pass is DRAM/L2-latency bound, every trip costs a
+        // full memory round trip.  Eight per thread: sixteen were better while the QR fallback sat inside the plane-fit
+        // loop, and are 2 % worse since it moved out of line (fit 1.24 -> 1.20 ms per 512 scans with eight; four: 1.22)
+        constexpr int kWide = TT <= 256 ? RPW_WIDE : 8;
         // (.ca loads for level 0, so that the leaf's label write would find the input indices in L1: no gain)
         auto ld_rec = [&](const float4* p) { return __ldcg(p); };
+        // (A bare predicated copy loop followed by a short second loop over shared memory for the bounding box and the
+        // range sum -- 550 instructions less code -- measured the same: 1.846 against 1.838 ms per 512 scans.)
+        {
         uint32_t i = tid;
         for (; i + (kWide - 1) * TT < n; i += kWide * TT) {
             float4 v[kWide];
@@ -651,6 +724,7 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
             for (int u = 0; u < 4; ++u) take(i + u * TT, v[u]);
         }
         for (; i < n; i += TT) take(i, ld_rec(nv.src + i));
+        }
         sd[1] = ar.ok() ? 0.f : 1.f;
     }
     tick(12);
@@ -814,7 +888,12 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
         tick(3);
         // distances, new mask, convergence, residual of the fit just made, moments of the new mask
         float st[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for_points<TT, SMEM, true>(nv, n, [&](uint32_t i, float x, float y, float z, uint8_t om) {
+#if RPW_PACKED_PASS
+        const uint32_t done = dist_pass_packed<TT, SMEM>(nv, n, cx, cy, cz, nx, ny, nz, tau, st);
+#else
+        const uint32_t done = 0;
+#endif
+        for_points<TT, SMEM, true>(nv, n, done, [&](uint32_t i, float x, float y, float z, uint8_t om) {
             const float dx = x - cx, dy = y - cy, dz = z - cz;
             const float p0 = dx * nx, p1 = dy * ny, p2 = dz * nz;
             const float dist = fabsf(p0 + (p1 + p2));  // Eigen's dot order, see plane_dist
@@ -870,7 +949,7 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
         // leaf: slot j labels input point sortedA[start + j].w (positional read-back, Q1)
         {
             const float4* rec = A.sortedA + nd.start;
-            constexpr int kWide = TT <= 256 ? 16 : 8;
+            constexpr int kWide = TT <= 256 ? RPW_WIDE : 8;
             auto ld_w = [&](const float* p) { return __ldcg(p); };
             uint32_t i = tid;
             for (; i + (kWide - 1) * TT < n; i += kWide * TT) {
