@@ -580,6 +580,8 @@ static int run_group(rpw_handle* h, rpw_handle::Lane& L, cudaStream_t st, const 
         RPW_CUDA(h, cudaEventRecord(L.ev_fork, st));
         // side[k] has priority k (0 = highest): strictly by size, largest class first (other orders, e.g. the
         // smallest class ahead of the second smallest so that it is not left alone at the end, measured 2 % slower)
+        // (launching the largest resident class ahead of the streamed one, whose 512-thread blocks take half an SM's
+        // registers each: nothing on C2, 8 % slower on the big-patch shapes C4 and C5)
         for (int k = 0; k < kNumFitClasses; ++k) {
             const int cls = kNumFitClasses - 1 - k;
             RPW_CUDA(h, cudaStreamWaitEvent(L.side[k], L.ev_fork, 0));
