@@ -707,7 +707,6 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
         auto ld_rec = [&](const float4* p) { return __ldcg(p); };
         // (A bare predicated copy loop followed by a short second loop over shared memory for the bounding box and the
         // range sum -- 550 instructions less code -- measured the same: 1.846 against 1.838 ms per 512 scans.)
-        {
         uint32_t i = tid;
         for (; i + (kWide - 1) * TT < n; i += kWide * TT) {
             float4 v[kWide];
@@ -724,7 +723,6 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
             for (int u = 0; u < 4; ++u) take(i + u * TT, v[u]);
         }
         for (; i < n; i += TT) take(i, ld_rec(nv.src + i));
-        }
         sd[1] = ar.ok() ? 0.f : 1.f;
     }
     tick(12);
