@@ -132,6 +132,15 @@ int rpw_create(const rpw_config* cfg, int device, size_t max_total_points, size_
 void rpw_destroy(rpw_handle* h);
 int rpw_set_config(rpw_handle* h, const rpw_config* cfg);
 int rpw_get_config(const rpw_handle* h, rpw_config* out);
+/* Grows the handle's capacity to at least (max_total_points, max_batch) in place: the handle, its
+ * streams, configuration, solver choice and debug switches stay, only the device / pinned buffers
+ * whose size follows the capacity are replaced (waits for the handle's pending work first; results of
+ * earlier calls -- rpw_last_clouds, rpw_debug_keys -- are gone afterwards).  A no-op when the handle
+ * is already large enough; it never shrinks.  The reference's class holds no buffers at all
+ * (RP/include/recursive_patchwork.hpp:70), so its callers never size anything: the C++ drop-in calls
+ * this when a cloud is larger than any it has seen. */
+int rpw_reserve(rpw_handle* h, size_t max_total_points, size_t max_batch);
+int rpw_capacity(const rpw_handle* h, size_t* max_total_points, size_t* max_batch);
 
 /* How the plane normal (smallest-eigenvalue eigenvector of the inlier covariance,
  * RP/src/recursive_patchwork.cpp:89-90) is computed on the device.

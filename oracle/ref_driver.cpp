@@ -7,11 +7,17 @@
 //   recursive_patchwork::RecursivePatchwork::filterGroundPoints
 //       RP/include/recursive_patchwork.hpp:53-54, RP/src/recursive_patchwork.cpp:310-426
 //   recursive_patchwork::PatchworkConfig        RP/include/recursive_patchwork.hpp:25-36
+//   recursive_patchwork::RecursivePatchwork::sampleGroundAndObstacles
+//       RP/include/recursive_patchwork.hpp:56-59, RP/src/recursive_patchwork.cpp:428-465
+//   recursive_patchwork::LidarFusion::fuseLidarPointClouds   RP/src/lidar_fusion.cpp:42-86
+//   recursive_patchwork::Visualization::createBEVImage / createGroundNonGroundImage
+//       RP/include/visualization.hpp:16-27, RP/src/visualization.cpp:18-80
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
 // load the resulting library.
 #include "recursive_patchwork.hpp"
 #include "lidar_fusion.hpp"
+#include "visualization.hpp"  // against tests/ref_build/opencv2/opencv.hpp (cv::Mat stand-in; OpenCV's C++ headers are absent here)
 
 #include <chrono>
 #include <cstdint>
@@ -182,6 +188,37 @@ size_t rpwref_fuse(const rpwref_sensor* sensors, size_t n_sensors, size_t stride
     const std::vector<Point3D> fused = fusion.fuseLidarPointClouds(clouds);
     for (size_t i = 0; i < fused.size(); ++i) { fused_xyz[3 * i] = fused[i].x; fused_xyz[3 * i + 1] = fused[i].y; fused_xyz[3 * i + 2] = fused[i].z; }
     return fused.size();
+}
+
+// The CLI's post-filter, RecursivePatchwork::sampleGroundAndObstacles (RP/src/recursive_patchwork.cpp:428-465):
+// the result is [random ground context sample (min(2000, #ground) points, unseeded std::mt19937) | obstacles].
+// out_xyz: 3 * cap floats.  Returns the number of points (or (size_t)-1 if cap is too small).
+size_t rpwref_sample_ground_and_obstacles(const rpwref_config* c, const float* xyz, size_t n, size_t stride,
+                                          float target_height, float base_tol, float* out_xyz, size_t cap) {
+    std::vector<Point3D> pts(n);
+    for (size_t i = 0; i < n; ++i) { pts[i].x = xyz[i * stride]; pts[i].y = xyz[i * stride + 1]; pts[i].z = xyz[i * stride + 2]; }
+    RecursivePatchwork rp(to_cfg(c));
+    const std::vector<Point3D> res = rp.sampleGroundAndObstacles(pts, target_height, base_tol);
+    if (res.size() > cap) return (size_t)-1;
+    for (size_t i = 0; i < res.size(); ++i) { out_xyz[3 * i] = res[i].x; out_xyz[3 * i + 1] = res[i].y; out_xyz[3 * i + 2] = res[i].z; }
+    return res.size();
+}
+
+// The CLI's rasters (RP/src/visualization.cpp:18-80) through the cv::Mat stand-in.  mode 0:
+// createGroundNonGroundImage(a, b); mode 1: createBEVImage(a) (b ignored).  bgr_out: height * width * 3 bytes.
+int rpwref_bev(int mode, const float* a, size_t na, const float* b, size_t nb, int width, int height,
+               float x_min, float y_min, float x_max, float y_max, uint8_t* bgr_out) {
+    auto cloud = [](const float* p, size_t n) {
+        std::vector<Point3D> v(n);
+        for (size_t i = 0; i < n; ++i) { v[i].x = p[3 * i]; v[i].y = p[3 * i + 1]; v[i].z = p[3 * i + 2]; }
+        return v;
+    };
+    recursive_patchwork::Visualization viz;
+    cv::Mat img = mode == 0 ? viz.createGroundNonGroundImage(cloud(a, na), cloud(b, nb), width, height, x_min, y_min, x_max, y_max)
+                            : viz.createBEVImage(cloud(a, na), width, height, x_min, y_min, x_max, y_max);
+    if (img.rows != height || img.cols != width) return -1;
+    std::memcpy(bgr_out, img.data(), (size_t)width * height * 3);
+    return 0;
 }
 
 // Times `reps` back-to-back calls of filterGroundPoints on one cloud (seconds per call,

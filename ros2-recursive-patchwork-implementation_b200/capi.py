@@ -51,7 +51,7 @@ NODE_DTYPE = np.dtype([("scan", "<i4"), ("root", "<i4"), ("depth", "<i4"), ("sta
                        ("mean_dist", "<f4")])
 
 # Every symbol include/rpw_b200.h declares (tests check that the library exports all of them).
-EXPORTS = ["rpw_default_config", "rpw_zone_model", "rpw_create", "rpw_destroy", "rpw_set_config", "rpw_get_config",
+EXPORTS = ["rpw_default_config", "rpw_zone_model", "rpw_create", "rpw_destroy", "rpw_set_config", "rpw_get_config", "rpw_reserve", "rpw_capacity",
            "rpw_set_plane_solver", "rpw_set_stream", "rpw_last_error", "rpw_segment", "rpw_segment_batch", "rpw_segment_batch_async", "rpw_wait",
            "rpw_segment_pc2", "rpw_segment_fused", "rpw_segment_clouds", "rpw_last_clouds", "rpw_sample_ground_and_obstacles", "rpw_bev_image", "rpw_segment_device", "rpw_debug_keys", "rpw_debug_enable_nodes", "rpw_debug_nodes",
            "rpw_debug_eig3", "rpw_debug_normal", "rpw_debug_atan2", "rpw_debug_fit_timing", "rpw_debug_fit_trace", "rpw_profile_enable", "rpw_profile_read", "rpw_host_alloc", "rpw_host_free", "rpw_kernel_launches", "rpw_abi_version"]
@@ -81,6 +81,8 @@ def load_library() -> C.CDLL:
     lib.rpw_destroy.argtypes = [vp]; lib.rpw_destroy.restype = None
     lib.rpw_set_config.argtypes = [vp, cfgp]; lib.rpw_set_config.restype = C.c_int
     lib.rpw_get_config.argtypes = [vp, cfgp]; lib.rpw_get_config.restype = C.c_int
+    lib.rpw_reserve.argtypes = [vp, sz, sz]; lib.rpw_reserve.restype = C.c_int
+    lib.rpw_capacity.argtypes = [vp, C.POINTER(sz), C.POINTER(sz)]; lib.rpw_capacity.restype = C.c_int
     lib.rpw_set_plane_solver.argtypes = [vp, C.c_int]; lib.rpw_set_plane_solver.restype = C.c_int
     lib.rpw_set_stream.argtypes = [vp, vp]; lib.rpw_set_stream.restype = C.c_int
     lib.rpw_last_error.argtypes = [vp]; lib.rpw_last_error.restype = C.c_char_p
@@ -195,6 +197,16 @@ class Handle:
         c = RpwConfig()
         self._check(self.lib.rpw_get_config(self._h, C.byref(c)))
         return c
+
+    def reserve(self, max_total_points: int, max_batch: int = 1):
+        """Grows the handle in place (never shrinks); results of earlier calls are gone afterwards."""
+        self._check(self.lib.rpw_reserve(self._h, int(max_total_points), int(max_batch)))
+        self.max_total_points, self.max_batch = self.capacity()
+
+    def capacity(self):
+        n, b = C.c_size_t(), C.c_size_t()
+        self._check(self.lib.rpw_capacity(self._h, C.byref(n), C.byref(b)))
+        return int(n.value), int(b.value)
 
     def set_plane_solver(self, solver: int):
         """SOLVER_HYBRID (2, default), SOLVER_EIGEN_QR (0, the reference's own float QR sequence) or SOLVER_CLOSED_FORM (1)."""

@@ -237,24 +237,81 @@ static int alloc_level_buffers(rpw_handle* h) {
     return RPW_OK;
 }
 
+}  // extern "C"
+
+// Everything whose size follows the handle's capacity (max_total_points, max_batch): the per-point
+// buffers, the worklists, the per-scan meta blocks.  rpw_create and rpw_reserve call it.
+static void free_capacity_buffers(rpw_handle* h) {
+    cudaFree(h->d_in); h->d_in = nullptr; h->d_in_bytes = 0;
+    cudaFree(h->d_keys); h->d_keys = nullptr;
+    cudaFree(h->d_labels); h->d_labels = nullptr;
+    cudaFree(h->d_sortedA); h->d_sortedA = nullptr;
+    cudaFree(h->d_bufB); h->d_bufB = nullptr;
+    cudaFree(h->d_bufC); h->d_bufC = nullptr;
+    cudaFree(h->d_gmask); h->d_gmask = nullptr;
+    for (auto& L : h->lane) {
+        cudaFree(L.d_queue[0]); cudaFree(L.d_queue[1]); L.d_queue[0] = L.d_queue[1] = nullptr;
+        cudaFree(L.d_counters); L.d_counters = nullptr;
+    }
+    cudaFree(h->d_scan_off); h->d_scan_off = nullptr;
+    cudaFree(h->d_chunk_base); h->d_chunk_base = nullptr;
+    if (h->h_meta) { cudaFreeHost(h->h_meta); h->h_meta = nullptr; }
+    free_patch_buffers(h);
+    // lazily allocated, sized by the capacity: dropped here, re-created on demand
+    cudaFree(h->d_cmp_cnt); h->d_cmp_cnt = nullptr;
+    cudaFree(h->d_scan_counts); h->d_scan_counts = nullptr;
+    if (h->h_scan_counts) { cudaFreeHost(h->h_scan_counts); h->h_scan_counts = nullptr; }
+    cudaFree(h->d_cloud_g); h->d_cloud_g = nullptr;
+    cudaFree(h->d_cloud_ng); h->d_cloud_ng = nullptr;
+    if (h->h_stage_in) { cudaFreeHost(h->h_stage_in); h->h_stage_in = nullptr; h->h_stage_in_bytes = 0; }
+    if (h->h_stage_labels) { cudaFreeHost(h->h_stage_labels); h->h_stage_labels = nullptr; }
+    cudaFree(h->d_dbg_nodes); h->d_dbg_nodes = nullptr; h->dbg_cap = 0;
+}
+
+static int alloc_capacity_buffers(rpw_handle* h) {
+    const size_t N = h->cap_points, B = h->cap_batch;
+#define RPW_ALLOC(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) RPW_FAIL(h, _e == cudaErrorMemoryAllocation ? RPW_ERR_ALLOC : RPW_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e)); } while (0)
+    RPW_ALLOC(cudaMalloc(&h->d_in, N * 16));
+    h->d_in_bytes = N * 16;
+    RPW_ALLOC(cudaMalloc(&h->d_keys, N * sizeof(uint16_t)));
+    RPW_ALLOC(cudaMalloc(&h->d_labels, N));
+    RPW_ALLOC(cudaMalloc(&h->d_sortedA, N * sizeof(float4)));
+    RPW_ALLOC(cudaMalloc(&h->d_bufB, N * sizeof(float4)));
+    RPW_ALLOC(cudaMalloc(&h->d_bufC, N * sizeof(float4)));
+    RPW_ALLOC(cudaMalloc(&h->d_gmask, N));
+    h->q_cap = (uint32_t)(N / 25 + 64);
+    for (auto& L : h->lane) {
+        RPW_ALLOC(cudaMalloc(&L.d_queue[0], (size_t)h->q_cap * sizeof(NodeRef)));
+        RPW_ALLOC(cudaMalloc(&L.d_queue[1], (size_t)h->q_cap * sizeof(NodeRef)));
+    }
+    RPW_ALLOC(cudaMalloc(&h->d_scan_off, (B + 1) * sizeof(uint64_t)));
+    RPW_ALLOC(cudaMalloc(&h->d_chunk_base, (B + 1) * sizeof(uint32_t)));
+    RPW_ALLOC(cudaMallocHost(&h->h_meta, (B + 1) * (sizeof(uint64_t) + sizeof(uint32_t)) + 64));
+#undef RPW_ALLOC
+    int rc = alloc_patch_buffers(h);
+    if (rc != RPW_OK) return rc;
+    rc = alloc_level_buffers(h);
+    if (rc != RPW_OK) return rc;
+    h->last_off.clear(); h->last_batch = 0; h->last_total = 0;
+    h->last_pts = nullptr; h->last_labels = nullptr;
+    h->pend_labels.clear();
+    return RPW_OK;
+}
+
+extern "C" {
+
 void rpw_destroy(rpw_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->d_in); cudaFree(h->d_keys); cudaFree(h->d_labels); cudaFree(h->d_sortedA); cudaFree(h->d_bufB);
-    cudaFree(h->d_bufC); cudaFree(h->d_gmask); cudaFree(h->d_dbg_count); cudaFree(h->d_trace); cudaFree(h->d_trace_count); cudaFree(h->d_cmp_cnt); cudaFree(h->d_scan_counts); cudaFree(h->d_cloud_g); cudaFree(h->d_cloud_ng); cudaFree(h->d_sample_idx); cudaFree(h->d_bev_owner);
-    if (h->h_scan_counts) cudaFreeHost(h->h_scan_counts);
-    cudaFree(h->d_scan_off); cudaFree(h->d_chunk_base); cudaFree(h->d_dbg_nodes); cudaFree(h->d_timing); cudaFree(h->d_fusion);
+    free_capacity_buffers(h);
+    cudaFree(h->d_dbg_count); cudaFree(h->d_trace); cudaFree(h->d_trace_count); cudaFree(h->d_sample_idx); cudaFree(h->d_bev_owner);
+    cudaFree(h->d_timing); cudaFree(h->d_fusion);
     if (h->h_fusion) cudaFreeHost(h->h_fusion);
-    free_patch_buffers(h);
-    if (h->h_meta) cudaFreeHost(h->h_meta);
-    if (h->h_stage_in) cudaFreeHost(h->h_stage_in);
-    if (h->h_stage_labels) cudaFreeHost(h->h_stage_labels);
     if (h->h_stats) cudaFreeHost(h->h_stats);
     for (auto& L : h->lane) if (L.h_counts) { cudaFreeHost(L.h_counts); L.h_counts = nullptr; }
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     for (auto& L : h->lane) {
-        cudaFree(L.d_queue[0]); cudaFree(L.d_queue[1]); cudaFree(L.d_counters);
         for (int k = 0; k < kNumFitClasses; ++k) { if (L.side[k]) cudaStreamDestroy(L.side[k]); if (L.ev_join[k]) cudaEventDestroy(L.ev_join[k]); }
         if (L.ev_fork) cudaEventDestroy(L.ev_fork);
         if (L.ev_start) cudaEventDestroy(L.ev_start);
@@ -328,28 +385,10 @@ int rpw_create(const rpw_config* cfg, int device, size_t max_total_points, size_
     TRYC(cudaEventCreateWithFlags(&h->ev_call, cudaEventDisableTiming));
     TRYC(cudaMalloc(&h->d_dbg_count, sizeof(uint32_t)));
     TRYC(cudaMemset(h->d_dbg_count, 0, sizeof(uint32_t)));
-    const size_t N = max_total_points;
-    TRYC(cudaMalloc(&h->d_in, N * 16));
-    h->d_in_bytes = N * 16;
-    TRYC(cudaMalloc(&h->d_keys, N * sizeof(uint16_t)));
-    TRYC(cudaMalloc(&h->d_labels, N));
-    TRYC(cudaMalloc(&h->d_sortedA, N * sizeof(float4)));
-    TRYC(cudaMalloc(&h->d_bufB, N * sizeof(float4)));
-    TRYC(cudaMalloc(&h->d_bufC, N * sizeof(float4)));
-    TRYC(cudaMalloc(&h->d_gmask, N));
-    h->q_cap = (uint32_t)(N / 25 + 64);
-    for (auto& L : h->lane) {
-        TRYC(cudaMalloc(&L.d_queue[0], (size_t)h->q_cap * sizeof(NodeRef)));
-        TRYC(cudaMalloc(&L.d_queue[1], (size_t)h->q_cap * sizeof(NodeRef)));
-    }
-    TRYC(cudaMalloc(&h->d_scan_off, (max_batch + 1) * sizeof(uint64_t)));
-    TRYC(cudaMalloc(&h->d_chunk_base, (max_batch + 1) * sizeof(uint32_t)));
-    TRYC(cudaMallocHost(&h->h_meta, (max_batch + 1) * (sizeof(uint64_t) + sizeof(uint32_t)) + 64));
+    TRY(alloc_capacity_buffers(h));
     TRYC(cudaMalloc(&h->d_fusion, sizeof(FusionTable)));
     TRYC(cudaMallocHost(&h->h_fusion, sizeof(FusionTable)));
     TRYC(cudaMallocHost(&h->h_stats, 16 * rpw_handle::kLanes * sizeof(uint32_t)));
-    TRY(alloc_patch_buffers(h));
-    TRY(alloc_level_buffers(h));
     // shared-memory budget of the fit kernel: points a block keeps resident
     // (the levels kernel: kLevelBlocksPerSm persistent blocks per SM share the shared memory; nodes of depth >= 1
     // are mostly small, larger ones stream from L2)
@@ -387,6 +426,29 @@ int rpw_set_config(rpw_handle* h, const rpw_config* cfg) {
         int rc = alloc_level_buffers(h);
         if (rc != RPW_OK) return rc;
     }
+    return RPW_OK;
+}
+
+int rpw_reserve(rpw_handle* h, size_t max_total_points, size_t max_batch) {
+    if (!h) return RPW_ERR_BAD_ARG;
+    if (max_total_points <= h->cap_points && max_batch <= h->cap_batch) return RPW_OK;
+    if (max_total_points >= 0xFFFF0000ull) RPW_FAIL(h, RPW_ERR_BAD_ARG, "max_total_points must be below 2^32 - 65536");
+    RPW_CUDA(h, cudaSetDevice(h->device));
+    RPW_CUDA(h, cudaStreamSynchronize(h->stream));
+    // the handle, its streams, events, configuration and debug switches stay; only the buffers whose
+    // size follows the capacity are replaced
+    free_capacity_buffers(h);
+    if (max_total_points > h->cap_points) h->cap_points = max_total_points;
+    if (max_batch > h->cap_batch) h->cap_batch = max_batch;
+    const int rc = alloc_capacity_buffers(h);
+    if (rc != RPW_OK) return rc;
+    return h->dbg_enabled ? rpw_debug_enable_nodes(h, 1) : RPW_OK;
+}
+
+int rpw_capacity(const rpw_handle* h, size_t* max_total_points, size_t* max_batch) {
+    if (!h) return RPW_ERR_BAD_ARG;
+    if (max_total_points) *max_total_points = h->cap_points;
+    if (max_batch) *max_batch = h->cap_batch;
     return RPW_OK;
 }
 

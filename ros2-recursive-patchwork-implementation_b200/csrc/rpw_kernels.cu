@@ -1239,7 +1239,7 @@ __global__ void __launch_bounds__(kBinThreads) rpw_compact_scatter_kernel(const 
                                                                          uint32_t* __restrict__ scan_counts) {
     constexpr int kWarps = kBinThreads / 32;
     constexpr int kPerWarp = kBinChunk / kWarps;
-    __shared__ uint32_t s_base[4];          // ground, non-ground, beyond bases of this chunk; [3] label-0 total of the scan
+    __shared__ uint32_t s_base[5];          // ground, non-ground, beyond bases of this chunk; [3] label-0, [4] label-1 total of the scan
     __shared__ uint32_t s_warp[kWarps][3];  // per-warp counts, then exclusive offsets
     const int b = blockIdx.y, chunk = blockIdx.x;
     const uint64_t off = scan_off[b];
@@ -1247,7 +1247,7 @@ __global__ void __launch_bounds__(kBinThreads) rpw_compact_scatter_kernel(const 
     const uint32_t base = (uint32_t)chunk * kBinChunk;
     if (base >= n) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x < 4) s_base[threadIdx.x] = 0;
+    if (threadIdx.x < 5) s_base[threadIdx.x] = 0;
     __syncthreads();
     // bases: label counts of the chunks before this one; total label-0 and beyond counts of the scan
     {
@@ -1267,6 +1267,7 @@ __global__ void __launch_bounds__(kBinThreads) rpw_compact_scatter_kernel(const 
         }
         if (lane == 0) {
             atomicAdd(&s_base[0], g); atomicAdd(&s_base[1], ng); atomicAdd(&s_base[2], by); atomicAdd(&s_base[3], ng_all);
+            atomicAdd(&s_base[4], g_all);
             if (chunk == 0) { atomicAdd(&scan_counts[2 * b], g_all); atomicAdd(&scan_counts[2 * b + 1], ng_all + by_all); }
         }
     }
@@ -1286,7 +1287,11 @@ __global__ void __launch_bounds__(kBinThreads) rpw_compact_scatter_kernel(const 
         for (int w = 0; w < kWarps; ++w) { const uint32_t v = s_warp[w][threadIdx.x]; s_warp[w][threadIdx.x] = run; run += v; }
     }
     __syncthreads();
-    uint32_t o_ng = s_base[1] + s_warp[warp][0];
+    // Fewer than three points inside the radius: the reference returns ({}, cleaned points) before it ever separates
+    // the beyond-radius points (RP/src/recursive_patchwork.cpp:339-341), i.e. ONE cloud in plain input order; label-2
+    // points then take their place among the label-0 points instead of following them.
+    const bool degen = s_base[3] + s_base[4] < 3u;
+    uint32_t o_ng = s_base[1] + s_warp[warp][0] + (degen ? s_base[2] + s_warp[warp][2] : 0u);
     uint32_t o_g = s_base[0] + s_warp[warp][1];
     uint32_t o_by = s_base[3] + s_base[2] + s_warp[warp][2];  // beyond-radius points follow ALL label-0 points of the scan
     const unsigned lt = (1u << lane) - 1u;
@@ -1294,14 +1299,15 @@ __global__ void __launch_bounds__(kBinThreads) rpw_compact_scatter_kernel(const 
         const uint32_t i = base + warp * kPerWarp + r * 32 + lane;
         const bool valid = i < n;
         const uint32_t l = valid ? labels[off + i] : 255u;
-        const unsigned m0 = __ballot_sync(0xffffffffu, l == 0), m1 = __ballot_sync(0xffffffffu, l == 1), m2 = __ballot_sync(0xffffffffu, l == 2);
+        const unsigned m1 = __ballot_sync(0xffffffffu, l == 1), m2 = __ballot_sync(0xffffffffu, l == 2);
+        const unsigned m0 = __ballot_sync(0xffffffffu, l == 0) | (degen ? m2 : 0u);
         if (l <= 2u) {
             float x, y, z;
             load_xyz<VEC4>(pts, off + i, lay, x, y, z);
             if (fusion != nullptr) fuse_point(*fusion, i, x, y);
             float* dst;
             if (l == 1u) dst = ground + 3 * (off + o_g + __popc(m1 & lt));
-            else if (l == 0u) dst = nonground + 3 * (off + o_ng + __popc(m0 & lt));
+            else if (l == 0u || degen) dst = nonground + 3 * (off + o_ng + __popc(m0 & lt));
             else dst = nonground + 3 * (off + o_by + __popc(m2 & lt));
             dst[0] = x; dst[1] = y; dst[2] = z;
         }

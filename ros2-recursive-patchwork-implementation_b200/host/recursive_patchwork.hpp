@@ -4,9 +4,17 @@
 // src/recursive_patchwork/include/recursive_patchwork.hpp (namespace, type names, member
 // functions, argument meaning, default values), so the reference's callers — main.cpp:193,268,286,
 // recursive_patchwork_node.cpp:40,91 and test_recursive_patchwork.cpp:65-68,86-89,151-155 — build
-// against it unchanged as far as the segmentation class is concerned.  Differences:
-//   * no Eigen in this header: the class holds an opaque C-ABI handle (include/rpw_b200.h) instead
-//     of running the algorithm on the host; librpw_b200.so must be linked;
+// against it unchanged.  It REPLACES that file in place (the reference's other headers include it by
+// quote, `#include "recursive_patchwork.hpp"`, which resolves to their own directory before any -I
+// path): tests/test_gpu_refbuild.py builds the reference's own
+// test/test_recursive_patchwork.cpp and src/main.cpp, unmodified, against it.  Differences:
+//   * the class holds an opaque C-ABI handle (include/rpw_b200.h) instead of running the algorithm
+//     on the host; librpw_b200.so must be linked.  Nothing here needs Eigen, but the reference's
+//     header includes <Eigen/Dense> and its dependants rely on that (lidar_fusion.hpp:36,50-51 uses
+//     Eigen::Matrix4f without including it), so it is included when the build has it;
+//   * copies of a RecursivePatchwork share nothing: a copy carries the configuration (all the
+//     reference's class holds, recursive_patchwork.hpp:70) and creates its own device handle on
+//     first use;
 //   * failures (no CUDA device, CUDA error, capacity) surface as std::runtime_error — the ROS2
 //     node already wraps its callback in try/catch(std::exception) (recursive_patchwork_node.cpp:66,105);
 //     there is no CPU fallback;
@@ -26,6 +34,12 @@
 #include <string>
 #include <utility>
 #include <vector>
+
+#if defined(__has_include)
+#if __has_include(<Eigen/Dense>)
+#include <Eigen/Dense>  // transitive include the reference's dependants rely on (lidar_fusion.hpp, cuda_interface.hpp)
+#endif
+#endif
 
 #include "rpw_b200.h"
 
@@ -75,11 +89,30 @@ struct LidarConfig {
 
 class RecursivePatchwork {
 public:
-    explicit RecursivePatchwork(const PatchworkConfig& config = PatchworkConfig{}, int device = 0)
+    RecursivePatchwork(const PatchworkConfig& config = PatchworkConfig{}, int device = 0)
         : config_(config), device_(device) {}
     ~RecursivePatchwork() { release(); }
-    RecursivePatchwork(const RecursivePatchwork&) = delete;
-    RecursivePatchwork& operator=(const RecursivePatchwork&) = delete;
+    // Copyable like the reference's class, whose only state is the configuration: a copy gets the
+    // configuration and the device index and builds its own handle when it is first used.
+    RecursivePatchwork(const RecursivePatchwork& o) : config_(o.config_), device_(o.device_) {}
+    RecursivePatchwork& operator=(const RecursivePatchwork& o) {
+        if (this != &o) {
+            if (device_ != o.device_) release();
+            device_ = o.device_;
+            setConfig(o.config_);
+        }
+        return *this;
+    }
+    RecursivePatchwork(RecursivePatchwork&& o) noexcept
+        : config_(o.config_), device_(o.device_), handle_(o.handle_), capacity_(o.capacity_) { o.handle_ = nullptr; o.capacity_ = 0; }
+    RecursivePatchwork& operator=(RecursivePatchwork&& o) noexcept {
+        if (this != &o) {
+            release();
+            config_ = o.config_; device_ = o.device_; handle_ = o.handle_; capacity_ = o.capacity_;
+            o.handle_ = nullptr; o.capacity_ = 0;
+        }
+        return *this;
+    }
 
     // ---- main processing --------------------------------------------------------------------
     // (ground, non-ground) exactly as the reference orders them: ground in input order;
@@ -193,7 +226,8 @@ public:
     }
 
     std::vector<Point3D> rotatePoints2D(const std::vector<Point3D>& points, float angle_degrees) {
-        const float a = angle_degrees * static_cast<float>(M_PI) / 180.0f;
+        // the reference evaluates angle_degrees * M_PI / 180.0f in double and rounds once (recursive_patchwork.cpp:38)
+        const float a = static_cast<float>(static_cast<double>(angle_degrees) * M_PI / static_cast<double>(180.0f));
         const float c = std::cos(a), s = std::sin(a);
         std::vector<Point3D> out;
         out.reserve(points.size());
@@ -224,13 +258,18 @@ private:
     }
     void ensure(std::size_t n) {
         if (handle_ && n <= capacity_) return;
-        std::size_t cap = std::max<std::size_t>(n + n / 4, std::size_t(1) << 18);
-        release();
-        const rpw_config c = config_.toC();
-        const int rc = rpw_create(&c, device_, cap, 1, &handle_);
-        if (rc != RPW_OK) {
-            handle_ = nullptr;
-            throw std::runtime_error(std::string("RecursivePatchwork (B200): ") + rpw_last_error(nullptr));
+        const std::size_t cap = std::max<std::size_t>(n + n / 4, std::size_t(1) << 18);
+        if (handle_) {
+            // a larger cloud than any before: the handle grows in place (streams, configuration and
+            // solver choice stay; only the capacity-sized buffers are replaced)
+            check(rpw_reserve(handle_, cap, 1));
+        } else {
+            const rpw_config c = config_.toC();
+            const int rc = rpw_create(&c, device_, cap, 1, &handle_);
+            if (rc != RPW_OK) {
+                handle_ = nullptr;
+                throw std::runtime_error(std::string("RecursivePatchwork (B200): ") + rpw_last_error(nullptr));
+            }
         }
         capacity_ = cap;
     }

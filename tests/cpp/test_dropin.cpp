@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <iterator>
+#include <limits>
 #include <fstream>
 #include <iostream>
 #include <random>
@@ -74,6 +75,14 @@ int main(int argc, char** argv) {
         std::vector<Point3D> two = {Point3D(3, 4, 0), Point3D(5, 1, 0.1f)};
         auto few = patchwork.filterGroundPoints(two);
         REQUIRE(few.first.empty() && few.second.size() == 2);
+        // fewer than three points inside the radius: ({}, cleaned points) in plain input order, beyond-radius points
+        // interleaved where they stood (RP/src/recursive_patchwork.cpp:339-341)
+        const float inf = std::numeric_limits<float>::infinity();
+        std::vector<Point3D> mixed = {Point3D(900, 0, 1), Point3D(3, 4, 0), Point3D(0, -700, 2), Point3D(inf, 0, 0), Point3D(5, 1, 0.1f), Point3D(400, 400, 3)};
+        auto deg = patchwork.filterGroundPoints(mixed);
+        REQUIRE(deg.first.empty() && deg.second.size() == 5);
+        const int order[5] = {0, 1, 2, 4, 5};
+        for (int k = 0; k < 5; ++k) REQUIRE(std::memcmp(&deg.second[k], &mixed[order[k]], 12) == 0);
         // setConfig / getConfig
         PatchworkConfig c2 = patchwork.getConfig();
         c2.num_sectors = 16;
@@ -81,6 +90,32 @@ int main(int argc, char** argv) {
         REQUIRE(patchwork.getConfig().num_sectors == 16);
         auto again = patchwork.filterGroundPoints(points);
         REQUIRE(again.first.size() + again.second.size() == points.size());
+    }
+    {   // the class is copyable and movable like the reference's (its only state there is the configuration); a cloud
+        // larger than any before grows the handle in place
+        auto small = synthetic_cloud(2000, 5), large = synthetic_cloud(400000, 6);
+        PatchworkConfig cfg;
+        cfg.num_sectors = 12;
+        RecursivePatchwork a(cfg);
+        auto ra = a.filterGroundPoints(small);
+        RecursivePatchwork b = a;             // copy: same configuration, own handle on first use
+        REQUIRE(b.getConfig().num_sectors == 12);
+        auto rb = b.filterGroundPoints(small);
+        REQUIRE(ra.first.size() == rb.first.size() && ra.second.size() == rb.second.size());
+        REQUIRE(std::memcmp(ra.first.data(), rb.first.data(), ra.first.size() * 12) == 0);
+        RecursivePatchwork c;
+        c = a;                                // copy assignment
+        REQUIRE(c.getConfig().num_sectors == 12);
+        RecursivePatchwork d = std::move(b);  // move keeps the handle
+        auto rd = d.filterGroundPoints(small);
+        REQUIRE(rd.first.size() == ra.first.size());
+        std::vector<RecursivePatchwork> pool(2, a);  // containers of the class work as with the reference's
+        REQUIRE(pool[1].filterGroundPoints(small).first.size() == ra.first.size());
+        auto big = a.filterGroundPoints(large);      // 400,000 points > the initial 262,144-point capacity
+        REQUIRE(big.first.size() + big.second.size() == large.size());
+        auto after = a.filterGroundPoints(small);    // and the grown handle still answers the small cloud identically
+        REQUIRE(after.first.size() == ra.first.size() && std::memcmp(after.first.data(), ra.first.data(), ra.first.size() * 12) == 0);
+        std::printf("copy/move/grow: ground=%zu, large cloud ground=%zu\n", ra.first.size(), big.first.size());
     }
     {   // fused multi-LiDAR frame: three sensors, default 0 / +120 / -120 degree yaws, ego radius 2.5
         std::vector<std::vector<Point3D>> clouds = {synthetic_cloud(4000, 7), synthetic_cloud(3000, 8), synthetic_cloud(3000, 9)};

@@ -183,6 +183,34 @@ class Reference:
         k = self.lib.rpwref_fuse(sens, C.c_size_t(len(arrs)), C.c_size_t(arrs[0].shape[1]), C.c_void_p(fused.ctypes.data))
         return fused[:k]
 
+    def sample_ground_and_obstacles(self, cfg, points, target_height=1.1, base_tol=0.5):
+        """RecursivePatchwork::sampleGroundAndObstacles (RP/src/recursive_patchwork.cpp:428-465): (k, 3) float32,
+        [unseeded random ground sample | obstacles in non-ground order]."""
+        cfg = cfg if isinstance(cfg, Cfg) else to_cfg(cfg)
+        a = _pts(points)
+        cap = len(a) + 2000
+        out = np.zeros((cap, 3), np.float32)
+        self.lib.rpwref_sample_ground_and_obstacles.restype = C.c_size_t
+        k = self.lib.rpwref_sample_ground_and_obstacles(C.byref(cfg), C.c_void_p(a.ctypes.data), C.c_size_t(len(a)), C.c_size_t(a.shape[1]),
+                                                        C.c_float(target_height), C.c_float(base_tol), C.c_void_p(out.ctypes.data), C.c_size_t(cap))
+        if k == C.c_size_t(-1).value:
+            raise RuntimeError("reference sample larger than the buffer")
+        return out[:k]
+
+    def bev(self, mode, a, b, width, height, x_min, y_min, x_max, y_max):
+        """Visualization::createGroundNonGroundImage(a, b) (mode 0) or createBEVImage(a) (mode 1),
+        RP/src/visualization.cpp:18-80, through the cv::Mat stand-in: (height, width, 3) uint8 BGR."""
+        a = np.ascontiguousarray(a, np.float32).reshape(-1, 3)
+        b = np.ascontiguousarray(b if b is not None else np.zeros((0, 3)), np.float32).reshape(-1, 3)
+        img = np.zeros((int(height), int(width), 3), np.uint8)
+        self.lib.rpwref_bev.restype = C.c_int
+        rc = self.lib.rpwref_bev(C.c_int(mode), C.c_void_p(a.ctypes.data), C.c_size_t(len(a)), C.c_void_p(b.ctypes.data), C.c_size_t(len(b)),
+                                 C.c_int(width), C.c_int(height), C.c_float(x_min), C.c_float(y_min), C.c_float(x_max), C.c_float(y_max),
+                                 C.c_void_p(img.ctypes.data))
+        if rc != 0:
+            raise RuntimeError("rpwref_bev failed")
+        return img
+
     def time_scan(self, cfg, points, reps=1) -> float:
         cfg = cfg if isinstance(cfg, Cfg) else to_cfg(cfg)
         a = _pts(points)

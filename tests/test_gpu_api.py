@@ -191,6 +191,109 @@ def test_sample_ground_and_obstacles_on_device(rpw, h, oracle):
     assert np.array_equal(sg, flat) and len(so) == 0
 
 
+def test_degenerate_cloud_order_is_the_reference(rpw, h, ref):
+    """Fewer than three points inside the radius: the reference returns ({}, cleaned points) in plain input order, the
+    beyond-radius points where they stood (RP/src/recursive_patchwork.cpp:339-341); K4 must not move them to the tail."""
+    if ref is None:
+        pytest.skip("oracle/_ref/libref_strict.so not built")
+    cfg = rpw.PatchworkConfig(filtering_radius=50.0)
+    h.set_config(cfg.to_c())
+    rng = np.random.default_rng(5)
+    for n_in in (0, 1, 2, 3):
+        far = rng.uniform(60.0, 300.0, (9000, 3)).astype(np.float32) * rng.choice([-1.0, 1.0], (9000, 3)).astype(np.float32)
+        pts = far.copy()
+        pts[rng.choice(9000, 40, replace=False), 0] = np.nan
+        where = np.sort(rng.choice(9000, n_in, replace=False))
+        pts[where] = rng.uniform(2.0, 20.0, (n_in, 3)).astype(np.float32)
+        r = ref.run(cfg, pts)
+        g, ng, labels = h.segment_clouds(pts)
+        assert np.array_equal(labels, r["labels"]), n_in
+        assert np.array_equal(g.view(np.uint32), r["ground"].view(np.uint32)), n_in
+        assert np.array_equal(ng.view(np.uint32), r["non_ground"].view(np.uint32)), n_in
+
+
+def test_reserve_grows_the_handle_in_place(rpw, gpu_handle_factory, oracle):
+    cfg = rpw.PatchworkConfig(filtering_radius=80.0)
+    hd = gpu_handle_factory(cfg, 1 << 14, 1)
+    hd.set_plane_solver(rpw.capi.SOLVER_EIGEN_QR)
+    small = rpw.synth.testsuite_cloud(9, 9000)
+    big = rpw.synth.spinning_scan(1234, 64, 900)
+    want_small, want_big = oracle.run(cfg, small)["labels"], oracle.run(cfg, big)["labels"]
+    assert np.array_equal(hd.segment(small), want_small)
+    with pytest.raises(rpw.RpwError) as e:
+        hd.segment(big)
+    assert e.value.code == rpw.capi.RPW_ERR_CAPACITY
+    hd.reserve(len(big) + 2 * len(small), 4)
+    assert hd.capacity() == (len(big) + 2 * len(small), 4)
+    hd.reserve(100, 1)  # never shrinks
+    assert hd.capacity() == (len(big) + 2 * len(small), 4)
+    assert (hd.segment(big) == want_big).mean() >= 0.9999
+    got = hd.segment_batch([small, big, small])
+    assert np.array_equal(got[0], want_small) and np.array_equal(got[2], want_small)
+    hd.close()
+
+
+def test_sample_ground_and_obstacles_is_the_reference(rpw, h, ref):
+    """f2 pinned to the reference itself: RecursivePatchwork::sampleGroundAndObstacles as compiled from
+    RP/src/recursive_patchwork.cpp:428-465 (oracle/_ref/libref_strict.so) against rpw_sample_ground_and_obstacles on
+    the same scans.  The obstacle list is compared bit for bit, in order; the ground context sample (unseeded
+    std::mt19937 in the reference) by count, distinctness and membership in the reference's own ground cloud."""
+    if ref is None:
+        pytest.skip("oracle/_ref/libref_strict.so not built")
+    as_rows = lambda a: {r.tobytes() for r in np.ascontiguousarray(a)}
+    cases = [(rpw.PatchworkConfig(filtering_radius=60.0), rpw.synth.spinning_scan(1500, 64, 600), (1.1, 0.5)),
+             (rpw.PatchworkConfig(filtering_radius=60.0), rpw.synth.spinning_scan(1501, 64, 600), (0.3, 0.25)),
+             (rpw.PatchworkConfig(), rpw.synth.testsuite_cloud(42, 10000), (1.1, 0.5)),   # the CLI's demo cloud shape, its defaults
+             (rpw.PatchworkConfig(), rpw.synth.testsuite_cloud(61, 900), (1.1, 0.5)),     # fewer ground points than the sample size
+             (rpw.PatchworkConfig(filtering_radius=150.0), rpw.synth.solidstate_merged(2500, 120, 100), (1.1, 0.5))]
+    for cfg, pts, (target, tol) in cases:
+        h.set_config(cfg.to_c())
+        r = ref.run(cfg, pts)
+        want = ref.sample_ground_and_obstacles(cfg, pts, target, tol)
+        labels = h.segment(pts)
+        assert np.array_equal(labels, r["labels"])
+        sample, obstacles = h.sample_ground_and_obstacles(len(pts), target, tol, 2.5, 2000, seed=0)
+        k = min(2000, len(r["ground"]))
+        assert len(want) >= k
+        want_sample, want_obstacles = want[:k], want[k:]
+        assert np.array_equal(obstacles.view(np.uint32), want_obstacles.view(np.uint32)), (len(obstacles), len(want_obstacles))
+        assert len(sample) == len(want_sample)
+        ground_rows = as_rows(r["ground"])
+        assert as_rows(sample) <= ground_rows and as_rows(want_sample) <= ground_rows
+        if len(ground_rows) == len(r["ground"]):
+            assert len(as_rows(sample)) == len(sample)
+        if len(r["ground"]) <= 2000:  # no draw: the whole ground cloud in order, in both
+            assert np.array_equal(sample, want_sample)
+
+
+def test_bev_rasters_are_the_reference(rpw, h, ref):
+    """f4 pinned to the reference itself: Visualization::createGroundNonGroundImage / createBEVImage as compiled from
+    RP/src/visualization.cpp:18-80 (against the cv::Mat stand-in of tests/ref_build) fed with the reference's own
+    clouds, against rpw_bev_image, pixel for pixel -- the CLI's three rasters (RP/src/main.cpp:268-300), at the CLI's
+    default geometry and two others."""
+    if ref is None:
+        pytest.skip("oracle/_ref/libref_strict.so not built")
+    cases = [(rpw.PatchworkConfig(), rpw.synth.testsuite_cloud(42, 10000)),
+             (rpw.PatchworkConfig(filtering_radius=60.0), rpw.synth.spinning_scan(1600, 32, 500)),
+             (rpw.PatchworkConfig(filtering_radius=80.0), rpw.synth.spinning_scan(1601, 64, 900))]
+    views = [(300, 150, -150.0, -75.0, 150.0, 75.0),   # main.cpp defaults: x_min + bev_width, y_min + bev_height
+             (200, 160, -40.0, -32.0, 40.0, 32.0), (64, 48, -10.0, 0.0, 30.0, 30.0)]
+    painted = 0
+    for cfg, pts in cases:
+        h.set_config(cfg.to_c())
+        r = ref.run(cfg, pts)
+        labels = h.segment(pts)
+        assert np.array_equal(labels, r["labels"])
+        g, ng = r["ground"], r["non_ground"]
+        for (w, hh, x0, y0, x1, y1) in views:
+            assert np.array_equal(h.bev_image(h.BEV_CLASSES, w, hh, x0, y0, x1, y1), ref.bev(0, g, ng, w, hh, x0, y0, x1, y1))
+            assert np.array_equal(h.bev_image(h.BEV_HEIGHT_NONGROUND, w, hh, x0, y0, x1, y1), ref.bev(1, ng, None, w, hh, x0, y0, x1, y1))
+            got = h.bev_image(h.BEV_HEIGHT_ALL, w, hh, x0, y0, x1, y1)
+            assert np.array_equal(got, ref.bev(1, np.concatenate([g, ng]), None, w, hh, x0, y0, x1, y1))
+            painted += int(got.any())
+    assert painted == len(cases) * len(views)
+
+
 def _bev_reference(clouds_colours, width, height, x_min, y_min, x_max, y_max):
     """Sequential drawing of RP/src/visualization.cpp (createBEVImage / createGroundNonGroundImage): float scale
     factors, int truncation, later points overwrite earlier ones."""

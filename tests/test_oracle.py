@@ -160,3 +160,32 @@ def test_fusion_restatement_is_the_reference(rpw, oracle, ref):
     f1 = ref.fuse(clouds[:1], [2e-6], [0.0])
     f2, _ = oracle.fuse(clouds[:1], [2e-6], [0.0])
     assert np.array_equal(f1.view(np.uint32), f2.view(np.uint32)) and len(f0) == len(f2)
+
+
+def test_reference_exports_for_the_post_steps(rpw, ref):
+    """The reference's sampleGroundAndObstacles and BEV writers, as exported from oracle/_ref/libref_strict.so
+    (RP/src/recursive_patchwork.cpp:428-465, RP/src/visualization.cpp:18-80 against the cv::Mat stand-in), agree with
+    the numpy restatements the GPU tests used before they were pinned: the stand-in draws what OpenCV would."""
+    if ref is None:
+        pytest.skip("reference build not available")
+    from test_gpu_api import _bev_reference, _expected_clouds
+    cfg = rpw.PatchworkConfig(filtering_radius=60.0)
+    pts = rpw.synth.spinning_scan(1500, 32, 400)
+    r = ref.run(cfg, pts)
+    eg, eng = _expected_clouds(pts[:, :3], r["labels"])
+    assert np.array_equal(eg, r["ground"]) and np.array_equal(eng, r["non_ground"])
+    out = ref.sample_ground_and_obstacles(cfg, pts, 1.1, 0.5)
+    k = min(2000, len(eg))
+    d = np.sqrt(eng[:, 0] * eng[:, 0] + eng[:, 1] * eng[:, 1], dtype=np.float32)
+    want = eng[(d > np.float32(2.5)) & (np.abs(eng[:, 2] - np.float32(1.1)) <= np.float32(0.5))]
+    assert len(want) > 0 and np.array_equal(out[k:], want)
+    rows = {x.tobytes() for x in eg}
+    assert all(x.tobytes() in rows for x in out[:k])
+
+    def height_colour(p):
+        i = np.minimum(np.float32(255.0), np.maximum(np.float32(0.0), (p[:, 2] + np.float32(2.0)) * np.float32(50.0))).astype(np.int32)
+        return np.stack([i, i, np.full_like(i, 255)], 1).astype(np.uint8)
+
+    for (w, hh, x0, y0, x1, y1) in ((300, 150, -150.0, -75.0, 150.0, 75.0), (64, 48, -10.0, 0.0, 30.0, 30.0)):
+        assert np.array_equal(ref.bev(0, eg, eng, w, hh, x0, y0, x1, y1), _bev_reference([(eg, (0, 255, 0)), (eng, (0, 0, 255))], w, hh, x0, y0, x1, y1))
+        assert np.array_equal(ref.bev(1, eng, None, w, hh, x0, y0, x1, y1), _bev_reference([(eng, height_colour)], w, hh, x0, y0, x1, y1))
