@@ -432,7 +432,7 @@ def main():
             "kernels": kernels,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": total * 12, "d2h_bytes_per_step": total,
                     "api": f"rpw_segment_batch_async + rpw_wait (C-ABI) rolling over {len(chunks)} handles, pinned host xyz stride 12 in, labels out",
-                    "pcie_note": "host->device copies alone run at 54.4 GB/s on this box (tests/gpu_pcie.py): 37.8 k scans/s of 1.44 MB is the ceiling",
+                    "pcie_note": "host->device copies alone run at 54.4 GB/s on this box (tools/gpu_pcie.py): 37.8 k scans/s of 1.44 MB is the ceiling",
                     "steps": e2e_steps},
             "single_scan_latency_ms": lat_ms,
             "other_shapes_single_scan": other_shapes,

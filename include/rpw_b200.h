@@ -155,7 +155,7 @@ int rpw_capacity(const rpw_handle* h, size_t* max_total_points, size_t* max_batc
  *     smallest eigenvalues further apart than 2 % of the matrix scale: both solvers then agree to
  *     ~1e-6 rad), the QR sequence for the rest (a few percent of the solves).  Measured against
  *     RPW_SOLVER_EIGEN_QR: 1 label of 61.4 M differs over 512 ordinary scans, at most 31 of 262 k on the
- *     two-layer stress scans (tests/gpu_solver_agreement.py); every parity test runs with both.
+ *     two-layer stress scans (tools/gpu_solver_agreement.py); every parity test runs with both.
  * Environment override at rpw_create: RPW_PLANE_SOLVER=0|1|2. */
 #define RPW_SOLVER_EIGEN_QR 0
 #define RPW_SOLVER_CLOSED_FORM 1

@@ -32,6 +32,15 @@
 // a step below 1e-7 leaves an error of ~1e-12 (one step fewer than running to 1e-13; labels unchanged).
 #define RPW_NEWTON_TOL_HYBRID 1e-7
 #endif
+#ifndef RPW_LB32
+#define RPW_LB32 16  // resident blocks per SM the one-warp fit kernel (smallest patches) is compiled for
+#endif
+#ifndef RPW_T0
+#define RPW_T0 64    // threads of the <= 1024-point class
+#endif
+#ifndef RPW_T1
+#define RPW_T1 64    // threads of the <= 2048-point class
+#endif
 #ifndef RPW_LB64
 #define RPW_LB64 8  // resident blocks per SM the 64-thread fit kernels are compiled for
 #endif
@@ -304,6 +313,54 @@ template <int TT, int K>
 __device__ __forceinline__ void block_sum(float (&v)[K], float* red, int& phase) {
     static_assert(K <= 16, "block_sum handles at most 16 values");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if constexpr (TT == 32 && K <= 2) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], d);
+        }
+        __syncwarp();
+        return;
+    } else if constexpr (TT == 32) {
+        // a block of one warp (the small-patch classes): the same reduce-scatter butterfly, then every lane fetches
+        // the totals from the lanes that hold them; no shared memory, no barrier
+        float w[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) w[k] = k < K ? v[k] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool up = lane & 16;
+            const float send = up ? w[j] : w[j + 8];
+            const float keep = up ? w[j + 8] : w[j];
+            w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool up = lane & 8;
+            const float send = up ? w[j] : w[j + 4];
+            const float keep = up ? w[j + 4] : w[j];
+            w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const bool up = lane & 4;
+            const float send = up ? w[j] : w[j + 2];
+            const float keep = up ? w[j + 2] : w[j];
+            w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        {
+            const bool up = lane & 2;
+            const float send = up ? w[0] : w[1];
+            const float keep = up ? w[1] : w[0];
+            w[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+        w[0] += __shfl_xor_sync(0xffffffffu, w[0], 1);
+        // value k sits in the lanes whose bits 4..1 spell k (bit4 -> 8, bit3 -> 4, bit2 -> 2, bit1 -> 1)
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] = __shfl_sync(0xffffffffu, w[0], ((k >> 3) & 1) * 16 + ((k >> 2) & 1) * 8 + ((k >> 1) & 1) * 4 + (k & 1) * 2);
+        __syncwarp();
+        return;
+    } else {
     float* r = red + phase * ((TT / 32) * 16);
     phase ^= 1;
     if (K <= 2) {
@@ -362,6 +419,7 @@ __device__ __forceinline__ void block_sum(float (&v)[K], float* red, int& phase)
     t += __shfl_xor_sync(0xffffffffu, t, 16);
 #pragma unroll
     for (int k = 0; k < K; ++k) v[k] = __shfl_sync(0xffffffffu, t, k);
+    }
 }
 
 template <int TT, int K>
@@ -372,6 +430,7 @@ __device__ __forceinline__ void block_min(float (&v)[K], float* red, int& phase)
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) v[k] = fminf(v[k], __shfl_xor_sync(0xffffffffu, v[k], d));
     }
+    if (TT == 32) { __syncwarp(); return; }  // the xor butterfly left the minima in every lane
     float* r = red + phase * ((TT / 32) * kRedMax);
     phase ^= 1;
     if (lane == 0) {
@@ -397,6 +456,7 @@ __device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v
         const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, d);
         v = o < v ? o : v;
     }
+    if (TT == 32) return v;
     unsigned long long* r = reinterpret_cast<unsigned long long*>(red + phase * ((TT / 32) * kRedMax));
     phase ^= 1;
     if (lane == 0) r[warp] = v;
@@ -617,10 +677,10 @@ struct Tick {
 // eigenvalue eigenvector, flipped to z >= 0.  Computed by warp 0, broadcast through shared memory.
 // (Which warp runs the solve makes no measurable difference: first, last, or spread round-robin over
 // the SM's sub-partitions all give the same throughput.)
-template <bool EXACT>
+template <bool EXACT, int TT>
 __device__ __forceinline__ void plane_normal(const float (&cv)[6], float cnt, float* bc, float& nx, float& ny, float& nz,
                                              bool hybrid, unsigned long long* timing = nullptr) {
-    if (threadIdx.x < 32) {
+    if (TT == 32 || threadIdx.x < 32) {
         float ax, ay, az;
         if (EXACT) {
             long long t0 = 0;
@@ -641,6 +701,7 @@ __device__ __forceinline__ void plane_normal(const float (&cv)[6], float cnt, fl
             }
         }
         if (az < 0.f) { ax = -ax; ay = -ay; az = -az; }  // :93-95
+        if (TT == 32) { nx = ax; ny = ay; nz = az; return; }  // a block of one warp: every lane holds the result
         if (threadIdx.x == 0) { bc[0] = ax; bc[1] = ay; bc[2] = az; }
     }
     __syncthreads();
@@ -881,7 +942,7 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
         if (cnt < 3.f) break;  // :196 — collapsed mask is kept (Q3)
         if (!have_cv) covariance_pass();
         tick(2);
-        plane_normal<EXACT>(cv, cnt, bc, nx, ny, nz, fp.hybrid != 0, A.timing);
+        plane_normal<EXACT, TT>(cv, cnt, bc, nx, ny, nz, fp.hybrid != 0, A.timing);
         iters++;
         tick(3);
         // distances, new mask, convergence, residual of the fit just made, moments of the new mask
@@ -902,6 +963,8 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
             st[0] += nm ? 1.f : 0.f; st[1] += ex; st[2] += ey; st[3] += ez;
             st[6] = fmaf(ex, ex, st[6]); st[7] = fmaf(ey, ex, st[7]); st[8] = fmaf(ey, ey, st[8]);
             st[9] = fmaf(ez, ex, st[9]); st[10] = fmaf(ez, ey, st[10]); st[11] = fmaf(ez, ez, st[11]);
+            // (predicated accumulation, "if (nm) { st[..] += .. }", instead of adding selected zeros: 6 % slower, 1.276
+            // against 1.202 ms per 512 scans -- ptxas turns the block into a branch)
         });
         tick(4);
         block_sum<TT, 12>(st, S.red, phase);
@@ -924,7 +987,7 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
     if (!have_final) {
         if (cnt >= 3.f) {
             if (!have_cv) covariance_pass();
-            plane_normal<EXACT>(cv, cnt, bc, nx, ny, nz, fp.hybrid != 0, A.timing);
+            plane_normal<EXACT, TT>(cv, cnt, bc, nx, ny, nz, fp.hybrid != 0, A.timing);
             float rs[1] = {0.f};
             for_points<TT, SMEM, true>(nv, n, [&](uint32_t, float x, float y, float z, uint8_t m) {
                 rs[0] += m ? plane_dist(x, y, z, cx, cy, cz, nx, ny, nz) : 0.f;
@@ -1085,7 +1148,7 @@ __device__ __forceinline__ FitSmem carve_smem(unsigned char* raw, int cap, int w
 // float solver, which is enough to tip chaotic two-layer patches the other way).
 // ---------------------------------------------------------------------------------------------
 template <int TT, bool EXACT>
-__global__ void __launch_bounds__(TT, (TT <= 64 ? RPW_LB64 : TT <= 128 ? RPW_LB128 : TT <= 256 ? 3 : 2))
+__global__ void __launch_bounds__(TT, (TT <= 32 ? RPW_LB32 : TT <= 64 ? RPW_LB64 : TT <= 128 ? RPW_LB128 : TT <= 256 ? 3 : 2))
 rpw_fit_roots_kernel(FitArgs A, int cls, int cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // The class's work list and its length are read together (independent addresses, one latency).
@@ -1534,7 +1597,7 @@ static cudaError_t set_smem(KernelT k, size_t bytes) {
 // blocks twice the memory it needs for its whole 40 us life), which is what bounds the fit phase.
 struct FitClass { int threads; uint32_t hi; int cap; };
 static const FitClass kFitClasses[kNumFitClasses] = {
-    {64, 1024, 1024}, {64, 2048, 2048}, {128, 3072, 3072}, {128, 4096, 4096}, {256, 5632, 5632}, {256, kCapLarge, kCapLarge},
+    {RPW_T0, 1024, 1024}, {RPW_T1, 2048, 2048}, {128, 3072, 3072}, {128, 4096, 4096}, {256, 5632, 5632}, {256, kCapLarge, kCapLarge},
     {RPW_STREAM_THREADS, 0xFFFFFFFFu, kCapStream},
 };
 
@@ -1549,6 +1612,7 @@ static cudaError_t configure_roots() {
 
 cudaError_t fit_configure(int smem_cap, int* blocks_per_sm) {
     cudaError_t e;
+    if ((e = configure_roots<32>()) != cudaSuccess) return e;
     if ((e = configure_roots<64>()) != cudaSuccess) return e;
     if ((e = configure_roots<128>()) != cudaSuccess) return e;
     if ((e = configure_roots<256>()) != cudaSuccess) return e;
@@ -1621,6 +1685,7 @@ cudaError_t launch_fit_roots(cudaStream_t st, const FitArgs& args, int cls, unsi
     const FitClass& c = kFitClasses[cls];
     if (grid == 0) grid = 1;
     switch (c.threads) {
+        case 32: launch_roots_tt<32>(st, args, cls, c.cap, grid); break;
         case 64: launch_roots_tt<64>(st, args, cls, c.cap, grid); break;
         case 128: launch_roots_tt<128>(st, args, cls, c.cap, grid); break;
         case 256: launch_roots_tt<256>(st, args, cls, c.cap, grid); break;

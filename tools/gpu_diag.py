@@ -1,5 +1,5 @@
 """Diagnostic run on a GPU box: every named shape through the CUDA path next to the oracle, with
-the parity report printed rather than asserted.  `python tests/gpu_diag.py [quick]`."""
+the parity report printed rather than asserted.  `python tools/gpu_diag.py [quick]`."""
 import importlib
 import json
 import sys

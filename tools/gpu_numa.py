@@ -2,7 +2,7 @@
 GPU's CPU affinity as NVML reports it, and the H2D bandwidth of pinned memory first touched by a thread bound to
 each NUMA node in turn (bench.py's e2e arm is bound by exactly this copy).
 
-    python tests/gpu_numa.py [device]
+    python tools/gpu_numa.py [device]
 """
 import glob, os, subprocess, sys, time
 import torch

@@ -18,7 +18,7 @@ SHAPES = [
     ("C1 test-suite cloud 10k, defaults", rpw.PatchworkConfig(), lambda s: rpw.synth.testsuite_cloud(s, 10000), range(100, 100 + int(128 * scale))),
     ("C1 10k, 10th-percentile seeds (adaptive off), 37 sectors", rpw.PatchworkConfig(adaptive_seed_height=False, num_sectors=37), lambda s: rpw.synth.testsuite_cloud(s, 10000), range(300, 300 + int(64 * scale))),
 ]
-print("# Parity soak, round 1 (tests/gpu_soak.py): GPU labels and keys against the CPU oracle\n")
+print("# Parity soak, round 1 (tools/gpu_soak.py): GPU labels and keys against the CPU oracle\n")
 print("| shape | scans | points | key mismatches | labels differing, hybrid (default) | labels differing, eigen_qr | worst scan agreement (hybrid / eigen_qr) |")
 print("|---|---|---|---|---|---|---|")
 tot = dict(n=0, k=0, h=0, q=0, scans=0)

@@ -1,4 +1,4 @@
-"""Cycle accounting of the fit kernel on a batch of C2 scans: python tests/gpu_timing.py [scans]"""
+"""Cycle accounting of the fit kernel on a batch of C2 scans: python tools/gpu_timing.py [scans]"""
 import importlib, sys, time
 from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path

@@ -2,7 +2,7 @@
 (built into ros2-recursive-patchwork-implementation_b200/_variants/ with different -D flags) and prints a checksum
 of the labels, which must not depend on the variant.
 
-    python tests/gpu_variants.py [scans] name1 name2 ...      (names of _variants/*.so; 'default' = the shipped library)
+    python tools/gpu_variants.py [scans] name1 name2 ...      (names of _variants/*.so; 'default' = the shipped library)
 """
 import hashlib, importlib, os, subprocess, sys, tempfile
 from concurrent.futures import ThreadPoolExecutor
