@@ -156,11 +156,26 @@ int rpw_capacity(const rpw_handle* h, size_t* max_total_points, size_t* max_batc
  *     ~1e-6 rad), the QR sequence for the rest (a few percent of the solves).  Measured against
  *     RPW_SOLVER_EIGEN_QR: 1 label of 61.4 M differs over 512 ordinary scans, at most 31 of 262 k on the
  *     two-layer stress scans (tools/gpu_solver_agreement.py); every parity test runs with both.
- * Environment override at rpw_create: RPW_PLANE_SOLVER=0|1|2. */
+ *   RPW_SOLVER_REFERENCE: RPW_SOLVER_EIGEN_QR plus every float reduction of fitPlaneAndSplit in the reference's
+ *     ORDER -- computeCentroid / computeCovariance (RP/src/point_cloud_processor.cpp:58-86), the residual
+ *     (RP/src/recursive_patchwork.cpp:98-104), the root patch's mean range (:383-387) and the split statistics
+ *     (:240-249) are sequential float sums there, and the other solvers add in trees.  With it every decision
+ *     is taken on the reference's bits: labels, node records (centroid, normal, residual, iteration counts) and
+ *     clouds are IDENTICAL to the reference's strict-IEEE build, including the bistable and never-converging
+ *     patches that amplify last-bit differences (tests/test_gpu_parity.py).  The sums are dependent chains
+ *     (one lane per sum), so this mode is several times slower; it is the verification mode.
+ * Environment override at rpw_create: RPW_PLANE_SOLVER=0|1|2|3. */
 #define RPW_SOLVER_EIGEN_QR 0
 #define RPW_SOLVER_CLOSED_FORM 1
 #define RPW_SOLVER_HYBRID 2
+#define RPW_SOLVER_REFERENCE 3
 int rpw_set_plane_solver(rpw_handle* h, int solver);
+/* Selective form of the reference-order arithmetic, for any solver: a plane fit that needed more than
+ * max_fast_iterations iterations is run again from its seeds with the reference's sequential sums and the QR solver
+ * (long fits are the ones that amplify the moments' last bits); the root mean range and the split statistics are
+ * always taken in the reference's order then.  0 = every fit (what RPW_SOLVER_REFERENCE selects), negative = off
+ * (default).  Environment override at rpw_create: RPW_EXACT_REPLAY=K. */
+int rpw_set_exact_replay(rpw_handle* h, int max_fast_iterations);
 
 /* Use a caller-owned CUDA stream (cudaStream_t passed as void*; NULL = the handle's own stream).
  * All copies and kernels of later calls are enqueued on it. */

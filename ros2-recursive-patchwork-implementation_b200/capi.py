@@ -16,7 +16,7 @@ LIB_PATH = Path(os.environ["RPW_B200_LIB"]) if os.environ.get("RPW_B200_LIB") el
 RPW_OK, RPW_ERR_BAD_ARG, RPW_ERR_NO_DEVICE, RPW_ERR_CUDA, RPW_ERR_CAPACITY, RPW_ERR_ALLOC = range(6)
 LABEL_NONGROUND, LABEL_GROUND, LABEL_BEYOND, LABEL_DROPPED, LABEL_EGO = 0, 1, 2, 3, 4
 KEY_DROPPED, KEY_BEYOND, KEY_UNBINNED, KEY_EGO = 0xFFFF, 0xFFFE, 0xFFFD, 0xFFFC
-SOLVER_EIGEN_QR, SOLVER_CLOSED_FORM, SOLVER_HYBRID = 0, 1, 2
+SOLVER_EIGEN_QR, SOLVER_CLOSED_FORM, SOLVER_HYBRID, SOLVER_REFERENCE = 0, 1, 2, 3
 NODE_SMALL, NODE_AREA, NODE_FLAT, NODE_FIT, NODE_SPLIT = 1, 2, 3, 4, 5
 
 
@@ -52,7 +52,7 @@ NODE_DTYPE = np.dtype([("scan", "<i4"), ("root", "<i4"), ("depth", "<i4"), ("sta
 
 # Every symbol include/rpw_b200.h declares (tests check that the library exports all of them).
 EXPORTS = ["rpw_default_config", "rpw_zone_model", "rpw_create", "rpw_destroy", "rpw_set_config", "rpw_get_config", "rpw_reserve", "rpw_capacity",
-           "rpw_set_plane_solver", "rpw_set_stream", "rpw_last_error", "rpw_segment", "rpw_segment_batch", "rpw_segment_batch_async", "rpw_wait",
+           "rpw_set_plane_solver", "rpw_set_exact_replay", "rpw_set_stream", "rpw_last_error", "rpw_segment", "rpw_segment_batch", "rpw_segment_batch_async", "rpw_wait",
            "rpw_segment_pc2", "rpw_segment_fused", "rpw_segment_clouds", "rpw_last_clouds", "rpw_sample_ground_and_obstacles", "rpw_bev_image", "rpw_segment_device", "rpw_debug_keys", "rpw_debug_enable_nodes", "rpw_debug_nodes",
            "rpw_debug_eig3", "rpw_debug_normal", "rpw_debug_atan2", "rpw_debug_fit_timing", "rpw_debug_fit_trace", "rpw_profile_enable", "rpw_profile_read", "rpw_host_alloc", "rpw_host_free", "rpw_kernel_launches", "rpw_abi_version"]
 
@@ -84,6 +84,7 @@ def load_library() -> C.CDLL:
     lib.rpw_reserve.argtypes = [vp, sz, sz]; lib.rpw_reserve.restype = C.c_int
     lib.rpw_capacity.argtypes = [vp, C.POINTER(sz), C.POINTER(sz)]; lib.rpw_capacity.restype = C.c_int
     lib.rpw_set_plane_solver.argtypes = [vp, C.c_int]; lib.rpw_set_plane_solver.restype = C.c_int
+    lib.rpw_set_exact_replay.argtypes = [vp, C.c_int]; lib.rpw_set_exact_replay.restype = C.c_int
     lib.rpw_set_stream.argtypes = [vp, vp]; lib.rpw_set_stream.restype = C.c_int
     lib.rpw_last_error.argtypes = [vp]; lib.rpw_last_error.restype = C.c_char_p
     lib.rpw_segment.argtypes = [vp, vp, sz, sz, vp, C.POINTER(RpwStats)]; lib.rpw_segment.restype = C.c_int
@@ -211,6 +212,10 @@ class Handle:
     def set_plane_solver(self, solver: int):
         """SOLVER_HYBRID (2, default), SOLVER_EIGEN_QR (0, the reference's own float QR sequence) or SOLVER_CLOSED_FORM (1)."""
         self._check(self.lib.rpw_set_plane_solver(self._h, int(solver)))
+
+    def set_exact_replay(self, max_fast_iterations: int):
+        """Fits of more than this many iterations are redone in the reference's arithmetic order (0: all, < 0: off)."""
+        self._check(self.lib.rpw_set_exact_replay(self._h, int(max_fast_iterations)))
 
     def set_stream(self, cuda_stream: int | None):
         self._check(self.lib.rpw_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
@@ -372,7 +377,7 @@ class Handle:
         """Reads+clears the fit kernel's cycle counters, then switches the accounting on/off."""
         out = (C.c_uint64 * 16)()
         self._check(self.lib.rpw_debug_fit_timing(self._h, 1 if enable else 0, out))
-        names = ["load", "seeds", "cov", "eig", "dist", "final", "label", "split", "fetch", "gridsync", "nodes", "iters", "load_loop", "dist_reduce", "qr_only"]
+        names = ["load", "seeds", "cov", "eig", "dist", "final", "label", "split", "fetch", "gridsync", "nodes", "iters", "load_loop", "dist_reduce", "qr_only", "replays"]
         return {k: int(out[i]) for i, k in enumerate(names)}
 
     TRACE_DTYPE = np.dtype([("t_start_ns", "<u8"), ("t_end_ns", "<u8"), ("sm", "<u4"), ("n", "<u4"), ("depth", "<u2"),

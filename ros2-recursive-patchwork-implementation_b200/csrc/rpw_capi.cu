@@ -53,6 +53,7 @@ struct rpw_handle {
     int smem_cap = 0;
     int fit_blocks = 0;
     int solver = RPW_SOLVER_HYBRID;
+    int exact_replay = -1;  // rpw_set_exact_replay
 
     // device buffers
     float* d_in = nullptr;       // staged input records of host-path calls
@@ -170,6 +171,12 @@ static int check_config(const rpw_config* c, std::string& why) {
     return RPW_OK;
 }
 
+static void apply_solver(rpw_handle* h) {
+    h->fp.exact_eig = (h->solver == RPW_SOLVER_EIGEN_QR || h->solver == RPW_SOLVER_REFERENCE) ? 1 : 0;
+    h->fp.hybrid = h->solver == RPW_SOLVER_HYBRID ? 1 : 0;
+    h->fp.exact_replay = h->solver == RPW_SOLVER_REFERENCE ? 0 : h->exact_replay;
+}
+
 static void apply_config(rpw_handle* h, const rpw_config* c) {
     h->cfg = *c;
     rpw_zone_model(c, h->zm.ring_edges, &h->zm.sector_angle);
@@ -186,8 +193,7 @@ static void apply_config(rpw_handle* h, const rpw_config* c) {
     h->fp.max_iter = c->max_iter;
     h->fp.adaptive_seed_height = c->adaptive_seed_height;
     h->fp.max_split_depth = c->max_split_depth;
-    h->fp.exact_eig = h->solver == RPW_SOLVER_EIGEN_QR ? 1 : 0;
-    h->fp.hybrid = h->solver == RPW_SOLVER_HYBRID ? 1 : 0;
+    apply_solver(h);
 }
 
 static void free_patch_buffers(rpw_handle* h) {
@@ -353,8 +359,9 @@ int rpw_create(const rpw_config* cfg, int device, size_t max_total_points, size_
     h->cap_batch = max_batch;
     if (const char* s = getenv("RPW_PLANE_SOLVER")) {
         const int v = atoi(s);
-        h->solver = v == RPW_SOLVER_CLOSED_FORM || v == RPW_SOLVER_EIGEN_QR ? v : RPW_SOLVER_HYBRID;
+        h->solver = v == RPW_SOLVER_CLOSED_FORM || v == RPW_SOLVER_EIGEN_QR || v == RPW_SOLVER_REFERENCE ? v : RPW_SOLVER_HYBRID;
     }
+    if (const char* s = getenv("RPW_EXACT_REPLAY")) h->exact_replay = atoi(s) < 0 ? -1 : atoi(s);
     apply_config(h, &c);
     int rc = RPW_OK;
     auto fail = [&](int code) { g_create_error = h->err; rpw_destroy(h); return code; };
@@ -454,11 +461,17 @@ int rpw_capacity(const rpw_handle* h, size_t* max_total_points, size_t* max_batc
 
 int rpw_set_plane_solver(rpw_handle* h, int solver) {
     if (!h) return RPW_ERR_BAD_ARG;
-    if (solver != RPW_SOLVER_EIGEN_QR && solver != RPW_SOLVER_CLOSED_FORM && solver != RPW_SOLVER_HYBRID)
+    if (solver != RPW_SOLVER_EIGEN_QR && solver != RPW_SOLVER_CLOSED_FORM && solver != RPW_SOLVER_HYBRID && solver != RPW_SOLVER_REFERENCE)
         RPW_FAIL(h, RPW_ERR_BAD_ARG, "unknown plane solver %d", solver);
     h->solver = solver;
-    h->fp.exact_eig = solver == RPW_SOLVER_EIGEN_QR ? 1 : 0;
-    h->fp.hybrid = solver == RPW_SOLVER_HYBRID ? 1 : 0;
+    apply_solver(h);
+    return RPW_OK;
+}
+
+int rpw_set_exact_replay(rpw_handle* h, int max_fast_iterations) {
+    if (!h) return RPW_ERR_BAD_ARG;
+    h->exact_replay = max_fast_iterations < 0 ? -1 : max_fast_iterations;
+    apply_solver(h);
     return RPW_OK;
 }
 

@@ -296,8 +296,8 @@ struct FitSmem {
 };
 
 constexpr int kRedMax = 16;
-// FitSmem::misc, in words: [0, 1] radix select, [2..4] heap-select replay, [8..10] plane normal
-constexpr int kMiscWords = 16;
+// FitSmem::misc, in words: [0, 1] radix select, [2..4] heap-select replay, [8..10] plane normal, [16..24] sequential sums
+constexpr int kMiscWords = 32;
 constexpr int kCapTiny = 1024;   // points a 64-thread block keeps in shared memory
 constexpr int kCapSmall = 4096;  // points a 128-thread block keeps in shared memory
 constexpr int kCapLarge = 8192;  // largest shared-memory slot (256-thread block); larger patches stream from L2 ...
@@ -729,6 +729,149 @@ struct TraceScope {
     }
 };
 
+// =============================================================================================
+// Reference-order arithmetic (rpw_set_exact_replay / RPW_SOLVER_REFERENCE).
+//
+// The reference adds floats one after the other -- computeCentroid and computeCovariance
+// (RP/src/point_cloud_processor.cpp:58-86), the residual (RP/src/recursive_patchwork.cpp:98-104), the root patch's
+// mean range (:383-387), the split statistics (:240-249) -- and a float sum depends on its order.  The fast path
+// above sums in trees; the two differ in the last bits of every moment, which a patch whose fit sits between two
+// fixed points (or creeps until max_iter) amplifies into different masks.  Here the sums are taken in the
+// reference's order: NV running sums are NV dependent chains of FADDs, one lane each; the warp's 32 lanes first
+// compute the addends of 32 consecutive points side by side and hand them over through shared memory, so the chain
+// lanes only load and add (about six cycles per point, against ~0.5 for the tree).  Masked-out points contribute
+// +0.0f, which leaves a sum's bits unchanged (a sum that starts at +0 never becomes -0).  Everything else of a plane
+// fit is element-wise and already the reference's operations.  With these sums, the QR eigensolver and the exact
+// medians / percentiles, every decision of fitPlaneAndSplit is taken on the reference's bits.
+// =============================================================================================
+constexpr int kSeqStride = 36;  // floats between the addend rows of two sums (36: the chain lanes' 16-byte loads spread over the banks)
+
+// Sequential sums over the node's points i = 0 .. n-1, in order.  produce(i, x, y, z, m, v) fills the NV addends of
+// point i.  scratch: NV * kSeqStride floats (FitSmem::hist).  Every thread of the block receives the sums.
+template <int TT, bool SMEM, int NV, typename F>
+__device__ __forceinline__ void seq_sums(const NodeView<SMEM>& nv, uint32_t n, float* scratch, float* bc, float (&out)[NV], F produce) {
+    static_assert(NV * kSeqStride <= 256, "the addend rows live in the 256-word histogram area");
+    const int lane = threadIdx.x & 31;
+    if (TT > 32) __syncthreads();  // scratch and bc may still be read by the previous user
+    if (TT == 32 || threadIdx.x < 32) {
+        float acc = 0.f;  // lane k < NV owns sum k
+        for (uint32_t base = 0; base < n; base += 32) {
+            const uint32_t i = base + lane;
+            float v[NV];
+#pragma unroll
+            for (int k = 0; k < NV; ++k) v[k] = 0.f;
+            if (i < n) {
+                float x, y, z;
+                nv.get(i, x, y, z);
+                produce(i, x, y, z, nv.mask(i), v);
+            }
+#pragma unroll
+            for (int k = 0; k < NV; ++k) scratch[k * kSeqStride + lane] = v[k];
+            __syncwarp();
+            if (lane < NV) {
+                const float4* p = reinterpret_cast<const float4*>(scratch + lane * kSeqStride);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 t = p[q];
+                    acc = __fadd_rn(acc, t.x); acc = __fadd_rn(acc, t.y); acc = __fadd_rn(acc, t.z); acc = __fadd_rn(acc, t.w);
+                }
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int k = 0; k < NV; ++k) out[k] = __shfl_sync(0xffffffffu, acc, k);
+        if (TT > 32 && lane == 0) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) bc[k] = out[k];
+        }
+    }
+    if (TT > 32) {
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < NV; ++k) out[k] = bc[k];
+    }
+}
+
+struct FitState {
+    float cx, cy, cz, nx, ny, nz, residual, cnt;
+    int iters;
+};
+
+// fitPlanePCA (RP/src/recursive_patchwork.cpp:77-95) of the points whose mask byte is set, reference order.
+template <int TT, bool SMEM>
+__device__ __forceinline__ void plane_of_mask_seq(const NodeView<SMEM>& nv, uint32_t n, float cnt, FitSmem S, float& cx, float& cy, float& cz,
+                                                  float& nx, float& ny, float& nz) {
+    float* bc = reinterpret_cast<float*>(S.misc + 8);
+    float* sbc = reinterpret_cast<float*>(S.misc + 16);
+    float s3[3];
+    seq_sums<TT, SMEM, 3>(nv, n, reinterpret_cast<float*>(S.hist), sbc, s3, [](uint32_t, float x, float y, float z, uint8_t m, float (&v)[3]) {
+        v[0] = m ? x : 0.f; v[1] = m ? y : 0.f; v[2] = m ? z : 0.f;
+    });
+    cx = s3[0] / cnt; cy = s3[1] / cnt; cz = s3[2] / cnt;  // centroid /= points.size()
+    const float ccx = cx, ccy = cy, ccz = cz;
+    float cv[6];  // xx yx yy zx zy zz (diff * diff^T is symmetric bit for bit: float products commute)
+    seq_sums<TT, SMEM, 6>(nv, n, reinterpret_cast<float*>(S.hist), sbc, cv, [=](uint32_t, float x, float y, float z, uint8_t m, float (&v)[6]) {
+        const float d0 = x - ccx, d1 = y - ccy, d2 = z - ccz;
+        v[0] = m ? d0 * d0 : 0.f; v[1] = m ? d1 * d0 : 0.f; v[2] = m ? d1 * d1 : 0.f;
+        v[3] = m ? d2 * d0 : 0.f; v[4] = m ? d2 * d1 : 0.f; v[5] = m ? d2 * d2 : 0.f;
+    });
+    plane_normal<true, TT>(cv, cnt, bc, nx, ny, nz, false);  // cov /= (size - 1), Eigen's QR sequence, z-up flip
+}
+
+// The iterated fit of fitPlaneAndSplit (:185-228) from the seed mask, in the reference's arithmetic order.
+// c0..c2: the three lowest points when fewer than three seeds lie below z_th (ascending index), else unused.
+template <int TT, bool SMEM>
+static __device__ __noinline__ void exact_refit(const NodeView<SMEM> nv, const uint32_t n, const float z_th, const float tau, const int max_iter,
+                                                const bool seeds_by_height, const uint32_t c0, const uint32_t c1, const uint32_t c2,
+                                                FitSmem S, FitState* out) {
+    const int tid = threadIdx.x;
+    int phase = 0;
+    float cntv[1] = {0.f};
+    for (uint32_t i = tid; i < n; i += TT) {
+        const bool m = seeds_by_height ? nv.coord(i, 2) < z_th : (i == c0 || i == c1 || i == c2);
+        nv.set_mask(i, m ? 1 : 0);
+        cntv[0] += m ? 1.f : 0.f;
+    }
+    block_sum<TT, 1>(cntv, S.red, phase);
+    float cnt = cntv[0];
+    float cx = 0.f, cy = 0.f, cz = 0.f, nx = 0.f, ny = 0.f, nz = 1.f;
+    bool plane_is_final = false;
+    int iters = 0;
+    for (int iter = 0; iter < max_iter; ++iter) {
+        if (cnt < 3.f) break;  // :196
+        plane_of_mask_seq<TT, SMEM>(nv, n, cnt, S, cx, cy, cz, nx, ny, nz);
+        iters++;
+        float st[2] = {0.f, 0.f};  // new count, changed
+        for (uint32_t i = tid; i < n; i += TT) {
+            float x, y, z;
+            nv.get(i, x, y, z);
+            const bool nm = plane_dist(x, y, z, cx, cy, cz, nx, ny, nz) < tau;
+            const bool om = nv.mask(i) != 0;
+            if (nm != om) { st[1] = 1.f; nv.set_mask(i, nm ? 1 : 0); }  // in place: a point's test does not read other masks
+            st[0] += nm ? 1.f : 0.f;
+        }
+        block_sum<TT, 2>(st, S.red, phase);
+        if (st[1] == 0.f) { plane_is_final = true; break; }  // :215
+        cnt = st[0];
+    }
+    float residual = FLT_MAX;
+    if (cnt >= 3.f) {  // :220-228, fitPlanePCA on the final mask
+        if (!plane_is_final) plane_of_mask_seq<TT, SMEM>(nv, n, cnt, S, cx, cy, cz, nx, ny, nz);
+        float rs[1];
+        const float fcx = cx, fcy = cy, fcz = cz, fnx = nx, fny = ny, fnz = nz;
+        seq_sums<TT, SMEM, 1>(nv, n, reinterpret_cast<float*>(S.hist), reinterpret_cast<float*>(S.misc + 16), rs,
+                              [=](uint32_t, float x, float y, float z, uint8_t m, float (&v)[1]) {
+                                  v[0] = m ? plane_dist(x, y, z, fcx, fcy, fcz, fnx, fny, fnz) : 0.f;
+                              });
+        residual = rs[0] / cnt;
+    } else {
+        cx = cy = cz = 0.f; nx = ny = 0.f; nz = 1.f;  // :78-80
+    }
+    if (TT > 32) __syncthreads();
+    out->cx = cx; out->cy = cy; out->cz = cz; out->nx = nx; out->ny = ny; out->nz = nz;
+    out->residual = residual; out->cnt = cnt; out->iters = iters;
+}
+
 template <int TT, bool SMEM, bool EXACT>
 __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth, FitSmem S) {
     const FitParams& fp = A.fp;
@@ -789,12 +932,19 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
     tick(12);
     block_min<TT, 6>(mm, S.red, phase);
     float mean_dist;
+    const int replay = fp.exact_replay;  // < 0: off; 0: every fit in the reference's arithmetic order; K > 0: fits of more than K iterations
     if (depth == 0) {
         block_sum<TT, 2>(sd, S.red, phase);
         if (sd[1] != 0.f) {  // (never for patch points, whose range is at least 1 m: kept for safety)
             sd[0] = 0.f;
             for (uint32_t i = tid; i < n; i += TT) sd[0] += range2d(nv.coord(i, 0), nv.coord(i, 1));
             block_sum<TT, 2>(sd, S.red, phase);
+        }
+        if (replay >= 0) {  // the reference's running sum (:383-387), so that z_th and the distance threshold carry its bits
+            float sr[1];
+            seq_sums<TT, SMEM, 1>(nv, n, reinterpret_cast<float*>(S.hist), reinterpret_cast<float*>(S.misc + 16), sr,
+                                  [](uint32_t, float x, float y, float, uint8_t, float (&v)[1]) { v[0] = range2d(x, y); });
+            sd[0] = sr[0];
         }
         mean_dist = sd[0] / (float)n;  // :383-387
         if (tid == 0) A.root_mean[nd.root] = mean_dist;
@@ -845,11 +995,11 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
     });
     block_sum<TT, 10>(acc, S.red, phase);
     bool seeds_by_height = true;
+    uint32_t chosen[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
     if (acc[0] < 3.f) {
         // the three lowest-z points (std::partial_sort over indices, :173-181).  Parallel pick by
         // (z, index); if z ties reach across the cut the SET libstdc++'s heap-select keeps depends on
         // its heap history, so in that (rare) case one thread replays the heap exactly.
-        uint32_t chosen[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
         for (int r = 0; r < 3; ++r) {
             unsigned long long best = ~0ull;
             for (uint32_t i = tid; i < n; i += TT) {
@@ -926,6 +1076,7 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
     int iters = 0;
     bool have_final = false;  // final plane (:220-228) already known
     float* bc = reinterpret_cast<float*>(S.misc + 8);
+    if (replay != 0) {  // (replay == 0: every fit runs in the reference's order below, the tree-sum fit is skipped)
     auto covariance_pass = [&]() {  // computeCovariance about the centroid (point_cloud_processor.cpp:72-86)
 #pragma unroll
         for (int k = 0; k < 6; ++k) cv[k] = 0.f;
@@ -998,6 +1149,16 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
             cx = cy = cz = 0.f; nx = ny = 0.f; nz = 1.f; residual = FLT_MAX;  // :78-80
         }
     }
+    }  // replay != 0
+    if (replay >= 0 && (replay == 0 || iters > replay)) {
+        // Reference-order refit: this node's fit again from its seeds with the reference's sequential sums and the QR
+        // solver; the fast fit above only decided that the node is worth it (long runs are the ones that amplify the
+        // last bits of the moments: bistable or creeping masks).
+        FitState fs;
+        exact_refit<TT, SMEM>(nv, n, z_th, tau, fp.max_iter, seeds_by_height, chosen[0], chosen[1], chosen[2], S, &fs);
+        cx = fs.cx; cy = fs.cy; cz = fs.cz; nx = fs.nx; ny = fs.ny; nz = fs.nz; residual = fs.residual; cnt = fs.cnt; iters = fs.iters;
+        tick.count(15, 1);
+    }
     const int n_in = (int)cnt;
     tick(5);
     tick.count(10, 1);
@@ -1035,15 +1196,27 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
     }
 
     // ---- split (:238-283) --------------------------------------------------------------------
-    float sxy[2] = {0.f, 0.f};
+    float sxy[2] = {0.f, 0.f}, var[2] = {0.f, 0.f};
+    float ccx, ccy;
+    if (replay >= 0) {  // :240-249 in the reference's order
+        seq_sums<TT, SMEM, 2>(nv, n, reinterpret_cast<float*>(S.hist), reinterpret_cast<float*>(S.misc + 16), sxy,
+                              [](uint32_t, float x, float y, float, uint8_t, float (&v)[2]) { v[0] = x; v[1] = y; });
+        ccx = sxy[0] / (float)n; ccy = sxy[1] / (float)n;
+        const float qx = ccx, qy = ccy;
+        seq_sums<TT, SMEM, 2>(nv, n, reinterpret_cast<float*>(S.hist), reinterpret_cast<float*>(S.misc + 16), var,
+                              [=](uint32_t, float x, float y, float, uint8_t, float (&v)[2]) {
+                                  const float dx = x - qx, dy = y - qy;
+                                  v[0] = dx * dx; v[1] = dy * dy;
+                              });
+        if (TT > 32) __syncthreads();  // the histogram area goes back to the radix select
+    } else {
     for (uint32_t i = tid; i < n; i += TT) {
         float x, y, z;
         nv.get(i, x, y, z);
         sxy[0] += x; sxy[1] += y;
     }
     block_sum<TT, 2>(sxy, S.red, phase);
-    const float ccx = sxy[0] / (float)n, ccy = sxy[1] / (float)n;
-    float var[2] = {0.f, 0.f};
+    ccx = sxy[0] / (float)n; ccy = sxy[1] / (float)n;
     for (uint32_t i = tid; i < n; i += TT) {
         float x, y, z;
         nv.get(i, x, y, z);
@@ -1051,6 +1224,7 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
         var[0] = fmaf(dx, dx, var[0]); var[1] = fmaf(dy, dy, var[1]);
     }
     block_sum<TT, 2>(var, S.red, phase);
+    }
     const int axis = (var[0] / (float)n > var[1] / (float)n) ? 0 : 1;  // :250
     const float median = radix_select<TT, SMEM>(nv, n, axis, n / 2);       // upper median (Q7)
 
