@@ -6,15 +6,8 @@
 //                           work lists of the non-empty root patches
 //   K2  rpw_scatter_kernel  stable counting-sort scatter of (x, y, z, input index) into
 //                           ring/sector patch segments (input order inside every patch, Q1)
-//   K3a rpw_fit_roots_kernel  fitPlaneAndSplit at depth 0 (RP/src/recursive_patchwork.cpp:109-308), one
-//                           block per listed ring/sector patch, seven size classes (block shape and shared-
-//                           memory slot per class) launched on concurrent, prioritised streams;
-//                           per node: early-outs, seeds, iterated PCA plane fit with a register
-//                           3x3 eigensolve, residual mask, split (variance axis, exact radix-select
-//                           median, stable partition), child enqueue, label scatter
-//   K3b rpw_fit_levels_kernel persistent cooperative kernel (one block per SM, grid barrier in global memory):
-//                           level-synchronous device worklist over the children of split nodes
-//                           (depth >= 1), no host round trips
+//   K3  the plane fit (fitPlaneAndSplit) lives in rpw_fit.cuh and is instantiated by rpw_fit_fast.cu and
+//       rpw_fit_replay.cu; this file only dispatches to them
 //   K4  rpw_compact_count_kernel / rpw_compact_scatter_kernel   result assembly (:402-419): the ground and
 //                           non-ground clouds in the reference's order, a stable compaction by label
 //   dbg rpw_eig3_kernel / rpw_normal_kernel / rpw_atan2_kernel   unit-test entry points for the device math
@@ -22,31 +15,6 @@
 // All of it is HBM/L2/shared-memory bound integer-and-float SIMT work; there is no dense
 // contraction, so no tensor-core path.  Compiled with -fmad=false (see rpw_device.cuh).
 #include "rpw_kernels.h"
-
-#ifndef RPW_LB128
-#define RPW_LB128 5  // resident blocks per SM the 128-thread fit kernels are compiled for (5 x 40 KB slots fill an SM)
-#endif
-#ifndef RPW_NEWTON_TOL_HYBRID
-// Last Newton step of the closed-form solve under the hybrid solver.  The hybrid solver only keeps the closed form
-// where the gap to the second eigenvalue is above 2 % of the matrix scale; there Newton converges quadratically, so
-// a step below 1e-7 leaves an error of ~1e-12 (one step fewer than running to 1e-13; labels unchanged).
-#define RPW_NEWTON_TOL_HYBRID 1e-7
-#endif
-#ifndef RPW_LB32
-#define RPW_LB32 16  // resident blocks per SM the one-warp fit kernel (smallest patches) is compiled for
-#endif
-#ifndef RPW_T0
-#define RPW_T0 64    // threads of the <= 1024-point class
-#endif
-#ifndef RPW_T1
-#define RPW_T1 64    // threads of the <= 2048-point class
-#endif
-#ifndef RPW_LB64
-#define RPW_LB64 8  // resident blocks per SM the 64-thread fit kernels are compiled for
-#endif
-#ifndef RPW_STREAM_THREADS
-#define RPW_STREAM_THREADS 512  // block size of the class whose patches stream from L2 (no shared-memory slot)
-#endif
 
 namespace rpw {
 
@@ -281,1151 +249,6 @@ __global__ void __launch_bounds__(kBinThreads) rpw_scatter_kernel(const float* _
             __syncwarp();
             if (kk != 0xFFFFFFFFu && lane == __ffs(peers) - 1) my[kk] += __popc(peers);
             __syncwarp();
-        }
-    }
-}
-
-// =============================================================================================
-// K3: fit
-// =============================================================================================
-struct FitSmem {
-    float* x; float* y; float* z; uint8_t* m;
-    float* red;        // 2 * (TT / 32) * kRedMax floats (ping-pong)
-    uint32_t* hist;    // 256
-    uint32_t* misc;    // small broadcast area
-};
-
-constexpr int kRedMax = 16;
-// FitSmem::misc, in words: [0, 1] radix select, [2..4] heap-select replay, [8..10] plane normal, [16..24] sequential sums
-constexpr int kMiscWords = 32;
-constexpr int kCapTiny = 1024;   // points a 64-thread block keeps in shared memory
-constexpr int kCapSmall = 4096;  // points a 128-thread block keeps in shared memory
-constexpr int kCapLarge = 8192;  // largest shared-memory slot (256-thread block); larger patches stream from L2 ...
-constexpr int kCapStream = 256;  // ... in 512-thread blocks that keep nothing resident
-
-// Sum of K floats over the block; every thread receives the totals (bitwise identical in all
-// threads).  One __syncthreads per call; the scratch area alternates so that back-to-back calls do
-// not race.  Inside a warp the K running sums are reduce-scattered (at every butterfly step a lane
-// hands half of its values to its partner and keeps the other half), so K values cost about K + 4
-// shuffles instead of 5 K; after the barrier every warp folds the 8 per-warp partials and
-// broadcasts the totals with one shuffle each.
-template <int TT, int K>
-__device__ __forceinline__ void block_sum(float (&v)[K], float* red, int& phase) {
-    static_assert(K <= 16, "block_sum handles at most 16 values");
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if constexpr (TT == 32 && K <= 2) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], d);
-        }
-        __syncwarp();
-        return;
-    } else if constexpr (TT == 32) {
-        // a block of one warp (the small-patch classes): the same reduce-scatter butterfly, then every lane fetches
-        // the totals from the lanes that hold them; no shared memory, no barrier
-        float w[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) w[k] = k < K ? v[k] : 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const bool up = lane & 16;
-            const float send = up ? w[j] : w[j + 8];
-            const float keep = up ? w[j + 8] : w[j];
-            w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const bool up = lane & 8;
-            const float send = up ? w[j] : w[j + 4];
-            const float keep = up ? w[j + 4] : w[j];
-            w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const bool up = lane & 4;
-            const float send = up ? w[j] : w[j + 2];
-            const float keep = up ? w[j + 2] : w[j];
-            w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
-        {
-            const bool up = lane & 2;
-            const float send = up ? w[0] : w[1];
-            const float keep = up ? w[1] : w[0];
-            w[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-        }
-        w[0] += __shfl_xor_sync(0xffffffffu, w[0], 1);
-        // value k sits in the lanes whose bits 4..1 spell k (bit4 -> 8, bit3 -> 4, bit2 -> 2, bit1 -> 1)
-#pragma unroll
-        for (int k = 0; k < K; ++k) v[k] = __shfl_sync(0xffffffffu, w[0], ((k >> 3) & 1) * 16 + ((k >> 2) & 1) * 8 + ((k >> 1) & 1) * 4 + (k & 1) * 2);
-        __syncwarp();
-        return;
-    } else {
-    float* r = red + phase * ((TT / 32) * 16);
-    phase ^= 1;
-    if (K <= 2) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], d);
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < K; ++k) r[warp * 16 + k] = v[k];
-        }
-    } else {
-        float w[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) w[k] = k < K ? v[k] : 0.f;
-        // 16 -> 8 -> 4 -> 2 -> 1 values per lane; lane bit (4,3,2,1) selects the half that is kept
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const bool up = lane & 16;
-            const float send = up ? w[j] : w[j + 8];
-            const float keep = up ? w[j + 8] : w[j];
-            w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const bool up = lane & 8;
-            const float send = up ? w[j] : w[j + 4];
-            const float keep = up ? w[j + 4] : w[j];
-            w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const bool up = lane & 4;
-            const float send = up ? w[j] : w[j + 2];
-            const float keep = up ? w[j + 2] : w[j];
-            w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
-        {
-            const bool up = lane & 2;
-            const float send = up ? w[0] : w[1];
-            const float keep = up ? w[1] : w[0];
-            w[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-        }
-        w[0] += __shfl_xor_sync(0xffffffffu, w[0], 1);
-        // the value index this lane ended up with: bit4 -> 8, bit3 -> 4, bit2 -> 2, bit1 -> 1
-        const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-        if ((lane & 1) == 0) r[warp * 16 + idx] = w[0];
-    }
-    __syncthreads();
-    // fold the per-warp partials: lane l sums value (l & 15) over warps (l >> 4) * 4 .. + 3
-    const int val = lane & 15, half = lane >> 4;
-    float t = 0.f;
-#pragma unroll
-    for (int q = 0; q < (TT / 32) / 2; ++q) t += r[(half * ((TT / 32) / 2) + q) * 16 + val];
-    t += __shfl_xor_sync(0xffffffffu, t, 16);
-#pragma unroll
-    for (int k = 0; k < K; ++k) v[k] = __shfl_sync(0xffffffffu, t, k);
-    }
-}
-
-template <int TT, int K>
-__device__ __forceinline__ void block_min(float (&v)[K], float* red, int& phase) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) v[k] = fminf(v[k], __shfl_xor_sync(0xffffffffu, v[k], d));
-    }
-    if (TT == 32) { __syncwarp(); return; }  // the xor butterfly left the minima in every lane
-    float* r = red + phase * ((TT / 32) * kRedMax);
-    phase ^= 1;
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) r[warp * kRedMax + k] = v[k];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        float t = r[(lane & ((TT / 32) - 1)) * kRedMax + k];
-#pragma unroll
-        for (int d = (TT / 32) / 2; d > 0; d >>= 1) t = fminf(t, __shfl_xor_sync(0xffffffffu, t, d));
-        v[k] = t;
-    }
-}
-
-// min over the block of a 64-bit key; all threads get the result.
-template <int TT>
-__device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v, float* red, int& phase) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, d);
-        v = o < v ? o : v;
-    }
-    if (TT == 32) return v;
-    unsigned long long* r = reinterpret_cast<unsigned long long*>(red + phase * ((TT / 32) * kRedMax));
-    phase ^= 1;
-    if (lane == 0) r[warp] = v;
-    __syncthreads();
-    unsigned long long t = r[lane & ((TT / 32) - 1)];
-#pragma unroll
-    for (int d = (TT / 32) / 2; d > 0; d >>= 1) {
-        const unsigned long long o = __shfl_xor_sync(0xffffffffu, t, d);
-        t = o < t ? o : t;
-    }
-    return t;
-}
-
-// Point access: shared-memory resident (node fits) or streamed from the L2-resident segment.
-template <bool SMEM>
-struct NodeView {
-    const float4* src;  // node's first record in its level buffer
-    uint8_t* gmask;     // node's first byte of the streaming mask scratch
-    FitSmem s;
-    __device__ __forceinline__ void get(uint32_t i, float& x, float& y, float& z) const {
-        if (SMEM) { x = s.x[i]; y = s.y[i]; z = s.z[i]; }
-        else { const float4 v = __ldcg(src + i); x = v.x; y = v.y; z = v.z; }
-    }
-    __device__ __forceinline__ float coord(uint32_t i, int axis) const {
-        if (SMEM) return axis == 0 ? s.x[i] : (axis == 1 ? s.y[i] : s.z[i]);
-        const float4 v = __ldcg(src + i);
-        return axis == 0 ? v.x : (axis == 1 ? v.y : v.z);
-    }
-    __device__ __forceinline__ uint8_t mask(uint32_t i) const { return SMEM ? s.m[i] : gmask[i]; }
-    __device__ __forceinline__ void set_mask(uint32_t i, uint8_t v) const { if (SMEM) s.m[i] = v; else gmask[i] = v; }
-};
-
-// k-th smallest (0-based) of one coordinate over the node: exact 4x8-bit radix select.
-// Reference: std::sort + index (RP/src/recursive_patchwork.cpp:156-159, :259-260, :267-268).
-template <int TT, bool SMEM>
-__device__ float radix_select(const NodeView<SMEM>& nv, uint32_t n, int axis, uint32_t k) {
-    uint32_t* hist = nv.s.hist;
-    uint32_t* misc = nv.s.misc;
-    uint32_t prefix = 0, pmask = 0;
-    for (int shift = 24; shift >= 0; shift -= 8) {
-        for (int i = threadIdx.x; i < 256; i += TT) hist[i] = 0;
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < n; i += TT) {
-            const uint32_t u = f2ord(nv.coord(i, axis));
-            if ((u & pmask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
-        }
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            // lane l owns bins [8l, 8l+8)
-            uint32_t c[8], tot = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { c[j] = hist[threadIdx.x * 8 + j]; tot += c[j]; }
-            uint32_t inc = tot;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-                if ((int)threadIdx.x >= d) inc += t;
-            }
-            uint32_t before = inc - tot;
-            if (k >= before && k < inc) {
-                uint32_t kk = k - before;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (kk < c[j]) { misc[0] = threadIdx.x * 8 + j; misc[1] = kk; kk = 0xFFFFFFFFu; }
-                    else if (kk != 0xFFFFFFFFu) kk -= c[j];
-                }
-            }
-        }
-        __syncthreads();
-        prefix |= misc[0] << shift;
-        pmask |= 255u << shift;
-        k = misc[1];
-        __syncthreads();
-    }
-    return ord2f(prefix);
-}
-
-__device__ __forceinline__ void dbg_record(const FitArgs& A, const NodeRef& nd, int depth, int outcome, int iters, int n_in,
-                                           int axis, float cx, float cy, float cz, float nx, float ny, float nz, float res,
-                                           float median, float mean_dist) {
-    if (A.dbg_nodes == nullptr) return;
-    const uint32_t slot = atomicAdd(A.dbg_count, 1u);
-    if (slot >= A.dbg_cap) return;
-    rpw_node_rec& r = A.dbg_nodes[slot];
-    const uint32_t lscan = nd.root / (uint32_t)A.P;
-    r.scan = (int32_t)(A.scan_base + lscan);
-    r.root = (int32_t)(nd.root % (uint32_t)A.P);
-    r.depth = depth;
-    r.start = (int32_t)(nd.start - A.patch_start[(size_t)lscan * (A.P + 1) + r.root]);
-    r.n = (int32_t)nd.n;
-    r.outcome = outcome; r.iters = iters; r.n_inliers = n_in; r.split_axis = axis;
-    r.centroid[0] = cx; r.centroid[1] = cy; r.centroid[2] = cz;
-    r.normal[0] = nx; r.normal[1] = ny; r.normal[2] = nz;
-    r.residual = res; r.median = median; r.mean_dist = mean_dist;
-}
-
-// Labels of a whole node set to one value (early-outs; RP/src/recursive_patchwork.cpp:111-113,
-// :126-129, :138-140).  Slot j of the node labels input point sortedA[start + j].w — the
-// positional read-back of SURVEY Q1.
-template <int TT>
-__device__ __forceinline__ void label_const(const FitArgs& A, const NodeRef& nd, uint8_t v) {
-    for (uint32_t i = threadIdx.x; i < nd.n; i += TT)
-        A.labels[__float_as_uint(A.sortedA[nd.start + i].w)] = v;
-}
-
-// Strided loop over a node's points, four rows per trip: the loads of a trip are issued together
-// before any of its arithmetic (memory-level parallelism instead of one dependent chain per row).
-// body(i, x, y, z, m) sees point i with its current mask byte.  (A layout where a thread owns four
-// CONSECUTIVE points and loads them with three LDS.128 needs a quarter of the load instructions but
-// measured 6 % slower end to end: the passes are bound by the dependent latency of a thread's own
-// instruction stream at the low occupancy shared memory allows, not by issue slots.)
-#ifndef RPW_UNROLL
-#define RPW_UNROLL 4
-#endif
-#ifndef RPW_WIDE
-#define RPW_WIDE 8
-#endif
-constexpr int kUnroll = RPW_UNROLL;
-template <int TT, bool SMEM, bool WITH_MASK, typename F>
-__device__ __forceinline__ void for_points(const NodeView<SMEM>& nv, uint32_t n, uint32_t first, F body) {
-    uint32_t i = first + threadIdx.x;
-    for (; i + (kUnroll - 1) * TT < n; i += kUnroll * TT) {
-        float x[kUnroll], y[kUnroll], z[kUnroll];
-        uint8_t m[kUnroll];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            nv.get(i + u * TT, x[u], y[u], z[u]);
-            m[u] = WITH_MASK ? nv.mask(i + u * TT) : (uint8_t)1;
-        }
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) body(i + u * TT, x[u], y[u], z[u], m[u]);
-    }
-    for (; i < n; i += TT) {
-        float x, y, z;
-        nv.get(i, x, y, z);
-        body(i, x, y, z, WITH_MASK ? nv.mask(i) : (uint8_t)1);
-    }
-}
-template <int TT, bool SMEM, bool WITH_MASK, typename F>
-__device__ __forceinline__ void for_points(const NodeView<SMEM>& nv, uint32_t n, F body) {
-    for_points<TT, SMEM, WITH_MASK>(nv, n, 0u, body);
-}
-
-// The distance / mask / moments pass of the plane-fit loop on Blackwell's packed FP32 instructions (FADD2, FMUL2,
-// FFMA2: two IEEE single-precision operations per instruction, each rounded exactly like the scalar form).  A thread
-// takes its rows two at a time, one row per half of every register pair; the halves keep separate running sums that
-// are added at the end.  Covers the rows [0, 4 * TT * floor(n / (4 * TT))) and returns that bound; the caller's
-// scalar loop finishes the rest and adds into the same totals.  15 floating-point instructions per point instead of
-// 24 -- and measured 0.7 % SLOWER end to end (1.897 against 1.884 ms per 512 scans, labels identical): the packed
-// instructions occupy the FMA pipe for two cycles, so the pass, which is not bound by issue slots, gains nothing.
-// Compiled out by default (RPW_PACKED_PASS=1 builds it).
-#ifndef RPW_PACKED_PASS
-#define RPW_PACKED_PASS 0
-#endif
-#if RPW_PACKED_PASS
-template <int TT, bool SMEM>
-__device__ __forceinline__ uint32_t dist_pass_packed(const NodeView<SMEM>& nv, uint32_t n, float cx, float cy, float cz, float nx, float ny,
-                                                     float nz, float tau, float (&st)[12]) {
-    const float2 ncx = make_float2(-cx, -cx), ncy = make_float2(-cy, -cy), ncz = make_float2(-cz, -cz);
-    const float2 nx2 = make_float2(nx, nx), ny2 = make_float2(ny, ny), nz2 = make_float2(nz, nz);
-    float2 a[12];
-#pragma unroll
-    for (int k = 0; k < 12; ++k) a[k] = make_float2(0.f, 0.f);
-    bool changed = false;
-    const uint32_t bound = (n / (4u * TT)) * (4u * TT);
-    for (uint32_t i = threadIdx.x; i < bound; i += 4 * TT) {
-        float x[4], y[4], z[4];
-        uint8_t m[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            nv.get(i + u * TT, x[u], y[u], z[u]);
-            m[u] = nv.mask(i + u * TT);
-        }
-#pragma unroll
-        for (int p = 0; p < 4; p += 2) {
-            const float2 dx = __fadd2_rn(make_float2(x[p], x[p + 1]), ncx);
-            const float2 dy = __fadd2_rn(make_float2(y[p], y[p + 1]), ncy);
-            const float2 dz = __fadd2_rn(make_float2(z[p], z[p + 1]), ncz);
-            const float2 p0 = __fmul2_rn(dx, nx2), p1 = __fmul2_rn(dy, ny2), p2 = __fmul2_rn(dz, nz2);
-            // Eigen's dot order p0 + (p1 + p2), see plane_dist.  Scalar additions on purpose: ptxas (12.9) contracts
-            // mul.rn.f32x2 followed by add.rn.f32x2 into FFMA2 even under -fmad=false, which would round the distance
-            // differently from the reference; it leaves packed products feeding scalar additions alone.
-            const float da = fabsf(__fadd_rn(p0.x, __fadd_rn(p1.x, p2.x))), db = fabsf(__fadd_rn(p0.y, __fadd_rn(p1.y, p2.y)));
-            const bool na = da < tau, nb = db < tau;
-            const float2 w = make_float2(na ? 1.f : 0.f, nb ? 1.f : 0.f);
-            a[5] = __fadd2_rn(a[5], make_float2(m[p] ? da : 0.f, m[p + 1] ? db : 0.f));
-            if (na != (m[p] != 0)) { changed = true; nv.set_mask(i + p * TT, na ? 1 : 0); }
-            if (nb != (m[p + 1] != 0)) { changed = true; nv.set_mask(i + (p + 1) * TT, nb ? 1 : 0); }
-            // masked-out rows contribute exact zeros (d * 0)
-            const float2 ex = __fmul2_rn(dx, w), ey = __fmul2_rn(dy, w), ez = __fmul2_rn(dz, w);
-            a[0] = __fadd2_rn(a[0], w); a[1] = __fadd2_rn(a[1], ex); a[2] = __fadd2_rn(a[2], ey); a[3] = __fadd2_rn(a[3], ez);
-            a[6] = __ffma2_rn(ex, ex, a[6]); a[7] = __ffma2_rn(ey, ex, a[7]); a[8] = __ffma2_rn(ey, ey, a[8]);
-            a[9] = __ffma2_rn(ez, ex, a[9]); a[10] = __ffma2_rn(ez, ey, a[10]); a[11] = __ffma2_rn(ez, ez, a[11]);
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 12; ++k) st[k] = a[k].x + a[k].y;
-    st[4] = changed ? 1.f : 0.f;
-    return bound;
-}
-#endif
-
-// Optional cycle accounting (rpw_debug_fit_timing): thread 0 of every block adds the cycles it spent
-// in each section of process_node to A.timing[section].  Sections: 0 load+bbox, 1 seeds, 2 covariance
-// pass + reduce, 3 eigensolve + broadcast, 4 distance/mask pass + reduce, 5 final fit, 6 leaf label
-// write, 7 split, 8 fetch / between nodes, 9 grid barrier, 10 nodes, 11 plane-fit iterations.
-struct Tick {
-    unsigned long long* t;
-    long long last;
-    __device__ __forceinline__ Tick(unsigned long long* timing) : t(timing), last(0) { if (t && threadIdx.x == 0) last = clock64(); }
-    __device__ __forceinline__ void operator()(int slot) {
-        if (t && threadIdx.x == 0) { const long long now = clock64(); atomicAdd(t + slot, (unsigned long long)(now - last)); last = now; }
-    }
-    __device__ __forceinline__ void count(int slot, unsigned v) { if (t && threadIdx.x == 0) atomicAdd(t + slot, (unsigned long long)v); }
-};
-
-// Plane normal from the scatter sums of the current inliers (fitPlanePCA, :86-95): smallest-
-// eigenvalue eigenvector, flipped to z >= 0.  Computed by warp 0, broadcast through shared memory.
-// (Which warp runs the solve makes no measurable difference: first, last, or spread round-robin over
-// the SM's sub-partitions all give the same throughput.)
-template <bool EXACT, int TT>
-__device__ __forceinline__ void plane_normal(const float (&cv)[6], float cnt, float* bc, float& nx, float& ny, float& nz,
-                                             bool hybrid, unsigned long long* timing = nullptr) {
-    if (TT == 32 || threadIdx.x < 32) {
-        float ax, ay, az;
-        if (EXACT) {
-            long long t0 = 0;
-            if (timing && threadIdx.x == 0) t0 = clock64();
-            plane_normal_exact(cv, cnt - 1.f, ax, ay, az);  // computeCovariance divides by n-1 (point_cloud_processor.cpp:84)
-            if (timing && threadIdx.x == 0) atomicAdd(timing + 14, (unsigned long long)(clock64() - t0));
-        } else {
-            bool small_gap;
-            smallest_eigvec_psd(cv[0], cv[1], cv[2], cv[3], cv[4], cv[5], ax, ay, az, &small_gap, hybrid ? RPW_NEWTON_TOL_HYBRID : 1e-13);
-            // hybrid solver: where the eigenvector is ill-conditioned only the reference's own operation
-            // sequence reproduces the reference's answer
-            if (hybrid && small_gap) {
-                // out of line: taken by a few percent of the solves, and ~1100 instructions that would otherwise sit in
-                // the middle of the plane-fit loop (fit phase -2 %)
-                const Normal3 r = plane_normal_exact_cold(cv[0], cv[1], cv[2], cv[3], cv[4], cv[5], cnt - 1.f);
-                ax = r.x; ay = r.y; az = r.z;
-                if (timing && threadIdx.x == 0) atomicAdd(timing + 14, 1ull);  // (hybrid: slot 14 counts the QR solves)
-            }
-        }
-        if (az < 0.f) { ax = -ax; ay = -ay; az = -az; }  // :93-95
-        if (TT == 32) { nx = ax; ny = ay; nz = az; return; }  // a block of one warp: every lane holds the result
-        if (threadIdx.x == 0) { bc[0] = ax; bc[1] = ay; bc[2] = az; }
-    }
-    __syncthreads();
-    nx = bc[0]; ny = bc[1]; nz = bc[2];
-}
-
-// Timeline record of one node (thread 0; debugging aid, off unless rpw_debug_fit_trace armed it).
-struct TraceScope {
-    const FitArgs& A; uint64_t t0; uint32_t n; uint16_t depth, cls;
-    __device__ __forceinline__ static uint64_t now() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-    __device__ __forceinline__ TraceScope(const FitArgs& a, uint32_t n_, int depth_, int cls_) : A(a), t0(0), n(n_), depth((uint16_t)depth_), cls((uint16_t)cls_) {
-        if (A.trace && threadIdx.x == 0) t0 = now();
-    }
-    __device__ __forceinline__ void done(int iters) {
-        if (A.trace && threadIdx.x == 0) {
-            const uint32_t slot = atomicAdd(A.trace_count, 1u);
-            if (slot < A.trace_cap) {
-                uint32_t smid;
-                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-                rpw_trace_rec r;
-                r.t_start_ns = t0; r.t_end_ns = now(); r.sm = smid; r.n = n; r.depth = depth; r.size_class = cls; r.iters = (uint32_t)iters;
-                A.trace[slot] = r;
-            }
-        }
-    }
-};
-
-// =============================================================================================
-// Reference-order arithmetic (rpw_set_exact_replay / RPW_SOLVER_REFERENCE).
-//
-// The reference adds floats one after the other -- computeCentroid and computeCovariance
-// (RP/src/point_cloud_processor.cpp:58-86), the residual (RP/src/recursive_patchwork.cpp:98-104), the root patch's
-// mean range (:383-387), the split statistics (:240-249) -- and a float sum depends on its order.  The fast path
-// above sums in trees; the two differ in the last bits of every moment, which a patch whose fit sits between two
-// fixed points (or creeps until max_iter) amplifies into different masks.  Here the sums are taken in the
-// reference's order: NV running sums are NV dependent chains of FADDs, one lane each; the warp's 32 lanes first
-// compute the addends of 32 consecutive points side by side and hand them over through shared memory, so the chain
-// lanes only load and add (about six cycles per point, against ~0.5 for the tree).  Masked-out points contribute
-// +0.0f, which leaves a sum's bits unchanged (a sum that starts at +0 never becomes -0).  Everything else of a plane
-// fit is element-wise and already the reference's operations.  With these sums, the QR eigensolver and the exact
-// medians / percentiles, every decision of fitPlaneAndSplit is taken on the reference's bits.
-// =============================================================================================
-constexpr int kSeqStride = 36;  // floats between the addend rows of two sums (36: the chain lanes' 16-byte loads spread over the banks)
-
-// Sequential sums over the node's points i = 0 .. n-1, in order.  produce(i, x, y, z, m, v) fills the NV addends of
-// point i.  scratch: NV * kSeqStride floats (FitSmem::hist).  Every thread of the block receives the sums.
-template <int TT, bool SMEM, int NV, typename F>
-__device__ __forceinline__ void seq_sums(const NodeView<SMEM>& nv, uint32_t n, float* scratch, float* bc, float (&out)[NV], F produce) {
-    static_assert(NV * kSeqStride <= 256, "the addend rows live in the 256-word histogram area");
-    const int lane = threadIdx.x & 31;
-    if (TT > 32) __syncthreads();  // scratch and bc may still be read by the previous user
-    if (TT == 32 || threadIdx.x < 32) {
-        float acc = 0.f;  // lane k < NV owns sum k
-        for (uint32_t base = 0; base < n; base += 32) {
-            const uint32_t i = base + lane;
-            float v[NV];
-#pragma unroll
-            for (int k = 0; k < NV; ++k) v[k] = 0.f;
-            if (i < n) {
-                float x, y, z;
-                nv.get(i, x, y, z);
-                produce(i, x, y, z, nv.mask(i), v);
-            }
-#pragma unroll
-            for (int k = 0; k < NV; ++k) scratch[k * kSeqStride + lane] = v[k];
-            __syncwarp();
-            if (lane < NV) {
-                const float4* p = reinterpret_cast<const float4*>(scratch + lane * kSeqStride);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 t = p[q];
-                    acc = __fadd_rn(acc, t.x); acc = __fadd_rn(acc, t.y); acc = __fadd_rn(acc, t.z); acc = __fadd_rn(acc, t.w);
-                }
-            }
-            __syncwarp();
-        }
-#pragma unroll
-        for (int k = 0; k < NV; ++k) out[k] = __shfl_sync(0xffffffffu, acc, k);
-        if (TT > 32 && lane == 0) {
-#pragma unroll
-            for (int k = 0; k < NV; ++k) bc[k] = out[k];
-        }
-    }
-    if (TT > 32) {
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < NV; ++k) out[k] = bc[k];
-    }
-}
-
-struct FitState {
-    float cx, cy, cz, nx, ny, nz, residual, cnt;
-    int iters;
-};
-
-// fitPlanePCA (RP/src/recursive_patchwork.cpp:77-95) of the points whose mask byte is set, reference order.
-template <int TT, bool SMEM>
-__device__ __forceinline__ void plane_of_mask_seq(const NodeView<SMEM>& nv, uint32_t n, float cnt, FitSmem S, float& cx, float& cy, float& cz,
-                                                  float& nx, float& ny, float& nz) {
-    float* bc = reinterpret_cast<float*>(S.misc + 8);
-    float* sbc = reinterpret_cast<float*>(S.misc + 16);
-    float s3[3];
-    seq_sums<TT, SMEM, 3>(nv, n, reinterpret_cast<float*>(S.hist), sbc, s3, [](uint32_t, float x, float y, float z, uint8_t m, float (&v)[3]) {
-        v[0] = m ? x : 0.f; v[1] = m ? y : 0.f; v[2] = m ? z : 0.f;
-    });
-    cx = s3[0] / cnt; cy = s3[1] / cnt; cz = s3[2] / cnt;  // centroid /= points.size()
-    const float ccx = cx, ccy = cy, ccz = cz;
-    float cv[6];  // xx yx yy zx zy zz (diff * diff^T is symmetric bit for bit: float products commute)
-    seq_sums<TT, SMEM, 6>(nv, n, reinterpret_cast<float*>(S.hist), sbc, cv, [=](uint32_t, float x, float y, float z, uint8_t m, float (&v)[6]) {
-        const float d0 = x - ccx, d1 = y - ccy, d2 = z - ccz;
-        v[0] = m ? d0 * d0 : 0.f; v[1] = m ? d1 * d0 : 0.f; v[2] = m ? d1 * d1 : 0.f;
-        v[3] = m ? d2 * d0 : 0.f; v[4] = m ? d2 * d1 : 0.f; v[5] = m ? d2 * d2 : 0.f;
-    });
-    plane_normal<true, TT>(cv, cnt, bc, nx, ny, nz, false);  // cov /= (size - 1), Eigen's QR sequence, z-up flip
-}
-
-// The iterated fit of fitPlaneAndSplit (:185-228) from the seed mask, in the reference's arithmetic order.
-// c0..c2: the three lowest points when fewer than three seeds lie below z_th (ascending index), else unused.
-template <int TT, bool SMEM>
-static __device__ __noinline__ void exact_refit(const NodeView<SMEM> nv, const uint32_t n, const float z_th, const float tau, const int max_iter,
-                                                const bool seeds_by_height, const uint32_t c0, const uint32_t c1, const uint32_t c2,
-                                                FitSmem S, FitState* out) {
-    const int tid = threadIdx.x;
-    int phase = 0;
-    float cntv[1] = {0.f};
-    for (uint32_t i = tid; i < n; i += TT) {
-        const bool m = seeds_by_height ? nv.coord(i, 2) < z_th : (i == c0 || i == c1 || i == c2);
-        nv.set_mask(i, m ? 1 : 0);
-        cntv[0] += m ? 1.f : 0.f;
-    }
-    block_sum<TT, 1>(cntv, S.red, phase);
-    float cnt = cntv[0];
-    float cx = 0.f, cy = 0.f, cz = 0.f, nx = 0.f, ny = 0.f, nz = 1.f;
-    bool plane_is_final = false;
-    int iters = 0;
-    for (int iter = 0; iter < max_iter; ++iter) {
-        if (cnt < 3.f) break;  // :196
-        plane_of_mask_seq<TT, SMEM>(nv, n, cnt, S, cx, cy, cz, nx, ny, nz);
-        iters++;
-        float st[2] = {0.f, 0.f};  // new count, changed
-        for (uint32_t i = tid; i < n; i += TT) {
-            float x, y, z;
-            nv.get(i, x, y, z);
-            const bool nm = plane_dist(x, y, z, cx, cy, cz, nx, ny, nz) < tau;
-            const bool om = nv.mask(i) != 0;
-            if (nm != om) { st[1] = 1.f; nv.set_mask(i, nm ? 1 : 0); }  // in place: a point's test does not read other masks
-            st[0] += nm ? 1.f : 0.f;
-        }
-        block_sum<TT, 2>(st, S.red, phase);
-        if (st[1] == 0.f) { plane_is_final = true; break; }  // :215
-        cnt = st[0];
-    }
-    float residual = FLT_MAX;
-    if (cnt >= 3.f) {  // :220-228, fitPlanePCA on the final mask
-        if (!plane_is_final) plane_of_mask_seq<TT, SMEM>(nv, n, cnt, S, cx, cy, cz, nx, ny, nz);
-        float rs[1];
-        const float fcx = cx, fcy = cy, fcz = cz, fnx = nx, fny = ny, fnz = nz;
-        seq_sums<TT, SMEM, 1>(nv, n, reinterpret_cast<float*>(S.hist), reinterpret_cast<float*>(S.misc + 16), rs,
-                              [=](uint32_t, float x, float y, float z, uint8_t m, float (&v)[1]) {
-                                  v[0] = m ? plane_dist(x, y, z, fcx, fcy, fcz, fnx, fny, fnz) : 0.f;
-                              });
-        residual = rs[0] / cnt;
-    } else {
-        cx = cy = cz = 0.f; nx = ny = 0.f; nz = 1.f;  // :78-80
-    }
-    if (TT > 32) __syncthreads();
-    out->cx = cx; out->cy = cy; out->cz = cz; out->nx = nx; out->ny = ny; out->nz = nz;
-    out->residual = residual; out->cnt = cnt; out->iters = iters;
-}
-
-template <int TT, bool SMEM, bool EXACT>
-__device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth, FitSmem S) {
-    const FitParams& fp = A.fp;
-    const uint32_t n = nd.n;
-    const int tid = threadIdx.x;
-    int phase = 0;
-    Tick tick(A.timing);
-
-    if (n < 3 || depth > fp.max_split_depth) {  // :111-113
-        label_const<TT>(A, nd, 0);
-        if (tid == 0) dbg_record(A, nd, depth, RPW_NODE_SMALL, 0, 0, -1, 0, 0, 0, 0, 0, 1, FLT_MAX, 0, 0);
-        return 0;
-    }
-    NodeView<SMEM> nv;
-    nv.s = S;
-    nv.src = (depth == 0 ? A.sortedA : ((depth & 1) ? A.bufB : A.bufC)) + nd.start;
-    nv.gmask = A.gmask + nd.start;
-
-    // ---- pass 1: load, bounding box, (root only) mean range ------------------------------
-    float mm[6] = {FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX};  // min x,y,z, min -x,-y,-z
-    float sd[2] = {0.f, 0.f};  // sum of ranges; [1]: a square root left the branch-free sequence's range
-    {
-        // sqrtf carries a branch to its slow path, which would keep the rows' 40-cycle chains from
-        // overlapping; the branch-free copy (ArithSpec, bit-identical in range) is checked once at the end
-        ArithSpec ar;
-        auto take = [&](uint32_t i, const float4 v) {
-            if (SMEM) { S.x[i] = v.x; S.y[i] = v.y; S.z[i] = v.z; }
-            mm[0] = fminf(mm[0], v.x); mm[1] = fminf(mm[1], v.y); mm[2] = fminf(mm[2], v.z);
-            mm[3] = fminf(mm[3], -v.x); mm[4] = fminf(mm[4], -v.y); mm[5] = fminf(mm[5], -v.z);
-            if (depth == 0) sd[0] += ar.sqrt(v.x * v.x + v.y * v.y);  // range2d
-        };
-        // many independent 16-byte loads in flight per thread: the pass is DRAM/L2-latency bound, every trip costs a
-        // full memory round trip.  Eight per thread: sixteen were better while the QR fallback sat inside the plane-fit
-        // loop, and are 2 % worse since it moved out of line (fit 1.24 -> 1.20 ms per 512 scans with eight; four: 1.22)
-        constexpr int kWide = TT <= 256 ? RPW_WIDE : 8;
-        // (.ca loads for level 0, so that the leaf's label write would find the input indices in L1: no gain)
-        auto ld_rec = [&](const float4* p) { return __ldcg(p); };
-        // (A bare predicated copy loop followed by a short second loop over shared memory for the bounding box and the
-        // range sum -- 550 instructions less code -- measured the same: 1.846 against 1.838 ms per 512 scans.)
-        uint32_t i = tid;
-        for (; i + (kWide - 1) * TT < n; i += kWide * TT) {
-            float4 v[kWide];
-#pragma unroll
-            for (int u = 0; u < kWide; ++u) v[u] = ld_rec(nv.src + i + u * TT);
-#pragma unroll
-            for (int u = 0; u < kWide; ++u) take(i + u * TT, v[u]);
-        }
-        for (; i + 3 * TT < n; i += 4 * TT) {
-            float4 v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = ld_rec(nv.src + i + u * TT);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) take(i + u * TT, v[u]);
-        }
-        for (; i < n; i += TT) take(i, ld_rec(nv.src + i));
-        sd[1] = ar.ok() ? 0.f : 1.f;
-    }
-    tick(12);
-    block_min<TT, 6>(mm, S.red, phase);
-    float mean_dist;
-    const int replay = fp.exact_replay;  // < 0: off; 0: every fit in the reference's arithmetic order; K > 0: fits of more than K iterations
-    if (depth == 0) {
-        block_sum<TT, 2>(sd, S.red, phase);
-        if (sd[1] != 0.f) {  // (never for patch points, whose range is at least 1 m: kept for safety)
-            sd[0] = 0.f;
-            for (uint32_t i = tid; i < n; i += TT) sd[0] += range2d(nv.coord(i, 0), nv.coord(i, 1));
-            block_sum<TT, 2>(sd, S.red, phase);
-        }
-        if (replay >= 0) {  // the reference's running sum (:383-387), so that z_th and the distance threshold carry its bits
-            float sr[1];
-            seq_sums<TT, SMEM, 1>(nv, n, reinterpret_cast<float*>(S.hist), reinterpret_cast<float*>(S.misc + 16), sr,
-                                  [](uint32_t, float x, float y, float, uint8_t, float (&v)[1]) { v[0] = range2d(x, y); });
-            sd[0] = sr[0];
-        }
-        mean_dist = sd[0] / (float)n;  // :383-387
-        if (tid == 0) A.root_mean[nd.root] = mean_dist;
-    } else {
-        mean_dist = __ldcg(A.root_mean + nd.root);  // Q4: inherited unchanged
-    }
-    tick(0);
-    const float x_min = mm[0], x_max = -mm[3], y_min = mm[1], y_max = -mm[4], z_min = mm[2], z_max = -mm[5];
-    const float area = (x_max - x_min) * (y_max - y_min);
-    if (area < 25.0f && depth > 0) {  // :126-129
-        label_const<TT>(A, nd, 1);
-        if (tid == 0) dbg_record(A, nd, depth, RPW_NODE_AREA, 0, 0, -1, 0, 0, 0, 0, 0, 1, FLT_MAX, 0, mean_dist);
-        return 0;
-    }
-    if ((z_max - z_min) < 0.05f && n > 10) {  // :138-140
-        label_const<TT>(A, nd, 1);
-        if (tid == 0) dbg_record(A, nd, depth, RPW_NODE_FLAT, 0, 0, -1, 0, 0, 0, 0, 0, 1, FLT_MAX, 0, mean_dist);
-        return 0;
-    }
-    // (the barrier inside block_min already made every thread's shared-memory stores visible)
-
-    // ---- seed threshold (:149-160) ----------------------------------------------------------
-    const float rel_dist = mean_dist / fp.radius;
-    float z_th;
-    if (fp.adaptive_seed_height) {
-        z_th = fp.sensor_height + 0.2f * rel_dist;
-    } else {
-        const uint32_t idx = (uint32_t)(0.1f * (float)n);
-        z_th = radix_select<TT, SMEM>(nv, n, 2, idx) + fp.th_seeds;
-    }
-    const float tau = fp.th_dist * (1.0f + 0.2f * rel_dist);  // :203
-
-    // ---- seeds (:163-182) -------------------------------------------------------------------
-    // One pass builds the seed mask AND its first/second moments about a fixed pivot (bounding-box
-    // centre, lowest z): the seed centroid is pivot + s/n and its scatter S' - s s^T / n, so the first
-    // plane fit needs no separate covariance pass.  The subtraction is harmless while the pivot sits
-    // inside the seed cloud; a compact seed set far from the pivot (S' >> scatter) falls back to the
-    // covariance pass about the centroid.
-    const float px = 0.5f * (x_min + x_max), py = 0.5f * (y_min + y_max), pz = z_min;
-    float acc[10] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // count, s, S' (xx yx yy zx zy zz)
-    for_points<TT, SMEM, false>(nv, n, [&](uint32_t i, float x, float y, float z, uint8_t) {
-        const bool m = z < z_th;
-        nv.set_mask(i, m ? 1 : 0);
-        const float dx = m ? x - px : 0.f, dy = m ? y - py : 0.f, dz = m ? z - pz : 0.f;
-        acc[0] += m ? 1.f : 0.f; acc[1] += dx; acc[2] += dy; acc[3] += dz;
-        acc[4] = fmaf(dx, dx, acc[4]); acc[5] = fmaf(dy, dx, acc[5]); acc[6] = fmaf(dy, dy, acc[6]);
-        acc[7] = fmaf(dz, dx, acc[7]); acc[8] = fmaf(dz, dy, acc[8]); acc[9] = fmaf(dz, dz, acc[9]);
-    });
-    block_sum<TT, 10>(acc, S.red, phase);
-    bool seeds_by_height = true;
-    uint32_t chosen[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-    if (acc[0] < 3.f) {
-        // the three lowest-z points (std::partial_sort over indices, :173-181).  Parallel pick by
-        // (z, index); if z ties reach across the cut the SET libstdc++'s heap-select keeps depends on
-        // its heap history, so in that (rare) case one thread replays the heap exactly.
-        for (int r = 0; r < 3; ++r) {
-            unsigned long long best = ~0ull;
-            for (uint32_t i = tid; i < n; i += TT) {
-                if (i == chosen[0] || i == chosen[1]) continue;
-                const unsigned long long key = ((unsigned long long)f2ord(nv.coord(i, 2)) << 32) | i;
-                best = key < best ? key : best;
-            }
-            best = block_min_u64<TT>(best, S.red, phase);
-            chosen[r] = (uint32_t)(best & 0xFFFFFFFFu);
-        }
-        {
-            const float v3 = nv.coord(chosen[2], 2);
-            float ties[1] = {0.f};
-            for (uint32_t i = tid; i < n; i += TT) ties[0] += (nv.coord(i, 2) <= v3) ? 1.f : 0.f;
-            block_sum<TT, 1>(ties, S.red, phase);
-            if (ties[0] > 3.f) {
-                // replay of std::__heap_select(first, first + 3, last, z[a] < z[b]) on a 3-element heap
-                // (make_heap with one __adjust_heap, then __pop_heap for every later element that is
-                // strictly below the root); same code as oracle/rpw_oracle.c:lowest3
-                if (tid == 0) {
-                    uint32_t hp[3] = {0, 1, 2};
-                    auto zz = [&](uint32_t i) { return nv.coord(i, 2); };
-                    auto adjust = [&](uint32_t value) {
-                        uint32_t hole = 0;
-                        uint32_t second = 2;
-                        if (zz(hp[2]) < zz(hp[1])) second = 1;
-                        hp[0] = hp[second];
-                        hole = second;
-                        if (zz(hp[0]) < zz(value)) { hp[hole] = hp[0]; hole = 0; }  // __push_heap: parent is the root
-                        hp[hole] = value;
-                    };
-                    adjust(hp[0]);
-                    for (uint32_t i = 3; i < n; ++i)
-                        if (zz(i) < zz(hp[0])) adjust(i);
-                    S.misc[2] = hp[0]; S.misc[3] = hp[1]; S.misc[4] = hp[2];
-                }
-                __syncthreads();
-                chosen[0] = S.misc[2]; chosen[1] = S.misc[3]; chosen[2] = S.misc[4];
-                __syncthreads();
-            }
-        }
-        // ascending index so that the 3-term sums follow the reference's order
-        if (chosen[0] > chosen[1]) { const uint32_t t = chosen[0]; chosen[0] = chosen[1]; chosen[1] = t; }
-        if (chosen[1] > chosen[2]) { const uint32_t t = chosen[1]; chosen[1] = chosen[2]; chosen[2] = t; }
-        if (chosen[0] > chosen[1]) { const uint32_t t = chosen[0]; chosen[0] = chosen[1]; chosen[1] = t; }
-        for (uint32_t i = tid; i < n; i += TT) nv.set_mask(i, (i == chosen[0] || i == chosen[1] || i == chosen[2]) ? 1 : 0);
-        acc[0] = 3.f; acc[1] = acc[2] = acc[3] = 0.f;
-        for (int r = 0; r < 3; ++r) {
-            float x, y, z;
-            nv.get(chosen[r], x, y, z);
-            acc[1] += x; acc[2] += y; acc[3] += z;
-        }
-        seeds_by_height = false;
-    }
-
-    tick(1);
-    // ---- iterated plane fit (:185-217) -------------------------------------------------------
-    // One pass per iteration: the distance pass that builds the next mask also accumulates that
-    // mask's first and second moments about the CURRENT centroid; the next centroid is mu + s/n and
-    // the next scatter matrix is S' - s s^T / n (the shift s/n is small, so nothing cancels badly).
-    // Only the very first fit (seeds) needs a separate covariance pass.
-    float cnt = acc[0];
-    float cx = acc[1] / cnt, cy = acc[2] / cnt, cz = acc[3] / cnt;  // computeCentroid (seeds by height: relative to the pivot)
-    float nx = 0.f, ny = 0.f, nz = 1.f, residual = FLT_MAX;
-    float cv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // scatter of the current mask about (cx, cy, cz): xx yx yy zx zy zz
-    bool have_cv = false;
-    if (seeds_by_height) {
-        cv[0] = fmaf(-acc[1], cx, acc[4]); cv[1] = fmaf(-acc[2], cx, acc[5]); cv[2] = fmaf(-acc[2], cy, acc[6]);
-        cv[3] = fmaf(-acc[3], cx, acc[7]); cv[4] = fmaf(-acc[3], cy, acc[8]); cv[5] = fmaf(-acc[3], cz, acc[9]);
-        cx += px; cy += py; cz += pz;
-        // more than four bits lost to the pivot offset: take the covariance pass about the centroid instead
-        have_cv = !((acc[4] + acc[6] + acc[9]) > 16.f * (cv[0] + cv[2] + cv[5]));
-    }
-    int iters = 0;
-    bool have_final = false;  // final plane (:220-228) already known
-    float* bc = reinterpret_cast<float*>(S.misc + 8);
-    if (replay != 0) {  // (replay == 0: every fit runs in the reference's order below, the tree-sum fit is skipped)
-    auto covariance_pass = [&]() {  // computeCovariance about the centroid (point_cloud_processor.cpp:72-86)
-#pragma unroll
-        for (int k = 0; k < 6; ++k) cv[k] = 0.f;
-        for_points<TT, SMEM, true>(nv, n, [&](uint32_t, float x, float y, float z, uint8_t m) {
-            // masked-out points contribute exact zeros
-            const float dx = m ? x - cx : 0.f, dy = m ? y - cy : 0.f, dz = m ? z - cz : 0.f;
-            cv[0] = fmaf(dx, dx, cv[0]); cv[1] = fmaf(dy, dx, cv[1]); cv[2] = fmaf(dy, dy, cv[2]);
-            cv[3] = fmaf(dz, dx, cv[3]); cv[4] = fmaf(dz, dy, cv[4]); cv[5] = fmaf(dz, dz, cv[5]);
-        });
-        block_sum<TT, 6>(cv, S.red, phase);
-        have_cv = true;
-    };
-    for (int iter = 0; iter < fp.max_iter; ++iter) {
-        if (cnt < 3.f) break;  // :196 — collapsed mask is kept (Q3)
-        if (!have_cv) covariance_pass();
-        tick(2);
-        plane_normal<EXACT, TT>(cv, cnt, bc, nx, ny, nz, fp.hybrid != 0, A.timing);
-        iters++;
-        tick(3);
-        // distances, new mask, convergence, residual of the fit just made, moments of the new mask
-        float st[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#if RPW_PACKED_PASS
-        const uint32_t done = dist_pass_packed<TT, SMEM>(nv, n, cx, cy, cz, nx, ny, nz, tau, st);
-#else
-        const uint32_t done = 0;
-#endif
-        for_points<TT, SMEM, true>(nv, n, done, [&](uint32_t i, float x, float y, float z, uint8_t om) {
-            const float dx = x - cx, dy = y - cy, dz = z - cz;
-            const float p0 = dx * nx, p1 = dy * ny, p2 = dz * nz;
-            const float dist = fabsf(p0 + (p1 + p2));  // Eigen's dot order, see plane_dist
-            const bool nm = dist < tau;
-            st[5] += om ? dist : 0.f;
-            if (nm != (om != 0)) { st[4] = 1.f; nv.set_mask(i, nm ? 1 : 0); }
-            const float ex = nm ? dx : 0.f, ey = nm ? dy : 0.f, ez = nm ? dz : 0.f;
-            st[0] += nm ? 1.f : 0.f; st[1] += ex; st[2] += ey; st[3] += ez;
-            st[6] = fmaf(ex, ex, st[6]); st[7] = fmaf(ey, ex, st[7]); st[8] = fmaf(ey, ey, st[8]);
-            st[9] = fmaf(ez, ex, st[9]); st[10] = fmaf(ez, ey, st[10]); st[11] = fmaf(ez, ez, st[11]);
-            // (predicated accumulation, "if (nm) { st[..] += .. }", instead of adding selected zeros: 6 % slower, 1.276
-            // against 1.202 ms per 512 scans -- ptxas turns the block into a branch)
-        });
-        tick(4);
-        block_sum<TT, 12>(st, S.red, phase);
-        tick(13);
-        if (st[4] == 0.f) {  // :215 converged: the final fit repeats this one
-            residual = st[5] / cnt;
-            have_final = true;
-            break;
-        }
-        cnt = st[0];
-        if (cnt >= 3.f) {
-            const float mx = st[1] / cnt, my = st[2] / cnt, mz = st[3] / cnt;  // centroid shift
-            cv[0] = fmaf(-st[1], mx, st[6]); cv[1] = fmaf(-st[2], mx, st[7]); cv[2] = fmaf(-st[2], my, st[8]);
-            cv[3] = fmaf(-st[3], mx, st[9]); cv[4] = fmaf(-st[3], my, st[10]); cv[5] = fmaf(-st[3], mz, st[11]);
-            cx += mx; cy += my; cz += mz;
-            have_cv = true;
-        }
-    }
-    // ---- final fit (:220-228) ----------------------------------------------------------------
-    if (!have_final) {
-        if (cnt >= 3.f) {
-            if (!have_cv) covariance_pass();
-            plane_normal<EXACT, TT>(cv, cnt, bc, nx, ny, nz, fp.hybrid != 0, A.timing);
-            float rs[1] = {0.f};
-            for_points<TT, SMEM, true>(nv, n, [&](uint32_t, float x, float y, float z, uint8_t m) {
-                rs[0] += m ? plane_dist(x, y, z, cx, cy, cz, nx, ny, nz) : 0.f;
-            });
-            block_sum<TT, 1>(rs, S.red, phase);
-            residual = rs[0] / cnt;
-        } else {
-            cx = cy = cz = 0.f; nx = ny = 0.f; nz = 1.f; residual = FLT_MAX;  // :78-80
-        }
-    }
-    }  // replay != 0
-    if (replay >= 0 && (replay == 0 || iters > replay)) {
-        // Reference-order refit: this node's fit again from its seeds with the reference's sequential sums and the QR
-        // solver; the fast fit above only decided that the node is worth it (long runs are the ones that amplify the
-        // last bits of the moments: bistable or creeping masks).
-        FitState fs;
-        exact_refit<TT, SMEM>(nv, n, z_th, tau, fp.max_iter, seeds_by_height, chosen[0], chosen[1], chosen[2], S, &fs);
-        cx = fs.cx; cy = fs.cy; cz = fs.cz; nx = fs.nx; ny = fs.ny; nz = fs.nz; residual = fs.residual; cnt = fs.cnt; iters = fs.iters;
-        tick.count(15, 1);
-    }
-    const int n_in = (int)cnt;
-    tick(5);
-    tick.count(10, 1);
-    tick.count(11, (unsigned)iters);
-
-    // ---- split decision (:231-235) -----------------------------------------------------------
-    const float split_threshold = fp.th_dist * (1.0f + 1.5f * (float)depth);
-    const uint32_t min_patch = (uint32_t)(50 + 10 * depth);
-    if (!(residual > split_threshold && depth < fp.max_split_depth && n >= min_patch)) {
-        // leaf: slot j labels input point sortedA[start + j].w (positional read-back, Q1)
-        {
-            const float4* rec = A.sortedA + nd.start;
-            constexpr int kWide = TT <= 256 ? RPW_WIDE : 8;
-            auto ld_w = [&](const float* p) { return __ldcg(p); };
-            uint32_t i = tid;
-            for (; i + (kWide - 1) * TT < n; i += kWide * TT) {
-                uint32_t w[kWide];
-#pragma unroll
-                for (int u = 0; u < kWide; ++u) w[u] = __float_as_uint(ld_w(&rec[i + u * TT].w));
-#pragma unroll
-                for (int u = 0; u < kWide; ++u) A.labels[w[u]] = nv.mask(i + u * TT);
-            }
-            for (; i + 3 * TT < n; i += 4 * TT) {
-                uint32_t w[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) w[u] = __float_as_uint(ld_w(&rec[i + u * TT].w));
-#pragma unroll
-                for (int u = 0; u < 4; ++u) A.labels[w[u]] = nv.mask(i + u * TT);
-            }
-            for (; i < n; i += TT) A.labels[__float_as_uint(ld_w(&rec[i].w))] = nv.mask(i);
-        }
-        if (tid == 0) dbg_record(A, nd, depth, RPW_NODE_FIT, iters, n_in, -1, cx, cy, cz, nx, ny, nz, residual, 0, mean_dist);
-        tick(6);
-        return iters;
-    }
-
-    // ---- split (:238-283) --------------------------------------------------------------------
-    float sxy[2] = {0.f, 0.f}, var[2] = {0.f, 0.f};
-    float ccx, ccy;
-    if (replay >= 0) {  // :240-249 in the reference's order
-        seq_sums<TT, SMEM, 2>(nv, n, reinterpret_cast<float*>(S.hist), reinterpret_cast<float*>(S.misc + 16), sxy,
-                              [](uint32_t, float x, float y, float, uint8_t, float (&v)[2]) { v[0] = x; v[1] = y; });
-        ccx = sxy[0] / (float)n; ccy = sxy[1] / (float)n;
-        const float qx = ccx, qy = ccy;
-        seq_sums<TT, SMEM, 2>(nv, n, reinterpret_cast<float*>(S.hist), reinterpret_cast<float*>(S.misc + 16), var,
-                              [=](uint32_t, float x, float y, float, uint8_t, float (&v)[2]) {
-                                  const float dx = x - qx, dy = y - qy;
-                                  v[0] = dx * dx; v[1] = dy * dy;
-                              });
-        if (TT > 32) __syncthreads();  // the histogram area goes back to the radix select
-    } else {
-    for (uint32_t i = tid; i < n; i += TT) {
-        float x, y, z;
-        nv.get(i, x, y, z);
-        sxy[0] += x; sxy[1] += y;
-    }
-    block_sum<TT, 2>(sxy, S.red, phase);
-    ccx = sxy[0] / (float)n; ccy = sxy[1] / (float)n;
-    for (uint32_t i = tid; i < n; i += TT) {
-        float x, y, z;
-        nv.get(i, x, y, z);
-        const float dx = x - ccx, dy = y - ccy;
-        var[0] = fmaf(dx, dx, var[0]); var[1] = fmaf(dy, dy, var[1]);
-    }
-    block_sum<TT, 2>(var, S.red, phase);
-    }
-    const int axis = (var[0] / (float)n > var[1] / (float)n) ? 0 : 1;  // :250
-    const float median = radix_select<TT, SMEM>(nv, n, axis, n / 2);       // upper median (Q7)
-
-    // stable partition: thread t owns the contiguous run [t*per, (t+1)*per)
-    const uint32_t per = (n + TT - 1) / TT;
-    const uint32_t lo = min(n, (uint32_t)tid * per), hi = min(n, lo + per);
-    uint32_t nleft = 0;
-    for (uint32_t i = lo; i < hi; ++i) nleft += nv.coord(i, axis) <= median;
-    // block exclusive scan of nleft
-    uint32_t* wsum = S.hist;  // reuse (256 words)
-    const int lane = tid & 31, warp = tid >> 5;
-    uint32_t inc = nleft;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += t;
-    }
-    __syncthreads();
-    if (lane == 31) wsum[warp] = inc;
-    __syncthreads();
-    uint32_t wbase = 0, total_left = 0;
-#pragma unroll
-    for (int w = 0; w < (TT / 32); ++w) {
-        const uint32_t v = wsum[w];
-        if (w < warp) wbase += v;
-        total_left += v;
-    }
-    uint32_t lpos = wbase + inc - nleft;  // lefts before my run
-    uint32_t rpos = total_left + (lo - lpos);
-    float4* dst = (((depth + 1) & 1) ? A.bufB : A.bufC) + nd.start;
-    for (uint32_t i = lo; i < hi; ++i) {
-        float x, y, z;
-        nv.get(i, x, y, z);
-        const float v = axis == 0 ? x : y;
-        if (v <= median) dst[lpos++] = make_float4(x, y, z, 0.f);
-        else dst[rpos++] = make_float4(x, y, z, 0.f);
-    }
-    // children (:286-287) go to the next level's queue; the parent range [start, start+n) is
-    // simply cut in two, which IS the reference's concatenated return order (Q1).
-    NodeRef L, R;
-    L.start = nd.start; L.n = total_left; L.root = nd.root; L.pad = 0;
-    R.start = nd.start + total_left; R.n = n - total_left; R.root = nd.root; R.pad = 0;
-    if (L.n < 3) {
-        label_const<TT>(A, L, 0);
-        if (tid == 0) dbg_record(A, L, depth + 1, RPW_NODE_SMALL, 0, 0, -1, 0, 0, 0, 0, 0, 1, FLT_MAX, 0, 0);
-    }
-    if (R.n < 3) {
-        label_const<TT>(A, R, 0);
-        if (tid == 0) dbg_record(A, R, depth + 1, RPW_NODE_SMALL, 0, 0, -1, 0, 0, 0, 0, 0, 1, FLT_MAX, 0, 0);
-    }
-    if (tid == 0) {
-        const uint32_t k = (L.n >= 3) + (R.n >= 3);
-        if (k) {
-            uint32_t slot = atomicAdd(A.q_count + depth + 1, k);
-            NodeRef* q = A.queue[(depth + 1) & 1];
-            if (slot + k <= A.q_cap) {
-                if (L.n >= 3) q[slot++] = L;
-                if (R.n >= 3) q[slot] = R;
-            } else {
-                atomicExch(A.overflow, 1u);
-            }
-        }
-        dbg_record(A, nd, depth, RPW_NODE_SPLIT, iters, n_in, axis, cx, cy, cz, nx, ny, nz, residual, median, mean_dist);
-    }
-    tick(7);
-    return iters;
-}
-
-__device__ __forceinline__ FitSmem carve_smem(unsigned char* raw, int cap, int warps) {
-    FitSmem S;
-    S.x = reinterpret_cast<float*>(raw);
-    S.y = S.x + cap;
-    S.z = S.y + cap;
-    S.red = S.z + cap;
-    S.hist = reinterpret_cast<uint32_t*>(S.red + 2 * warps * kRedMax);
-    S.misc = S.hist + 256;
-    S.m = reinterpret_cast<uint8_t*>(S.misc + kMiscWords);
-    return S;
-}
-
-// ---------------------------------------------------------------------------------------------
-// K3a: level 0 — the ring/sector patches themselves, one block per patch, no grid-wide barrier.
-// Patches come in very different sizes (a few points near the sensor, >10k in the far rings), so
-// the launch is split into size classes, each with its own block size and shared-memory carve-out:
-//   64 threads: <= 1024 points (15 KB) and <= 2048 (28 KB) : many resident blocks, their eigensolves overlap
-//   128 threads: <= 3072 (41 KB) and <= 4096 (55 KB)
-//   256 threads: <= 5632 (74 KB, three per SM)
-//   512 threads: everything larger: <= 8192 points shared-memory resident (108 KB), beyond that
-//                streamed from L2; the far-ring patches that iterate longest get the most threads
-// The class kernels run concurrently on separate streams and the hardware block scheduler packs
-// whatever mix fits an SM.  blockIdx.x walks (patch rank, scan) largest patch first; a block whose
-// patch belongs to another class exits at once.
-// EXACT = true: plane normals from Eigen's QR sequence (bit-comparable with the CPU reference);
-// EXACT = false: closed-form FP64 smallest eigenvector (faster, ~1e-6 rad away from the reference's
-// float solver, which is enough to tip chaotic two-layer patches the other way).
-// ---------------------------------------------------------------------------------------------
-template <int TT, bool EXACT>
-__global__ void __launch_bounds__(TT, (TT <= 32 ? RPW_LB32 : TT <= 64 ? RPW_LB64 : TT <= 128 ? RPW_LB128 : TT <= 256 ? 3 : 2))
-rpw_fit_roots_kernel(FitArgs A, int cls, int cap) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    // The class's work list and its length are read together (independent addresses, one latency).
-    // The host sizes the grid from the previous launch group's counts; a block whose index is past
-    // the list leaves at once, and a grid shorter than the list strides over it.
-    const uint4* list = A.cls_list + (size_t)cls * A.cls_cap;
-    uint32_t i = blockIdx.x;
-    uint4 item = __ldcg(list + (i < A.cls_cap ? i : 0));
-    const uint32_t count = min(__ldcg(A.cls_count + cls), A.cls_cap);
-    if (i >= count) return;
-    FitSmem S = carve_smem(smem_raw, cap, TT / 32);
-    for (;;) {
-        NodeRef nd;
-        nd.start = item.x; nd.n = item.y; nd.root = item.z; nd.pad = 0;
-        const uint32_t next = i + gridDim.x;
-        if (next < count) item = __ldcg(list + next);  // in flight while this node is processed
-        TraceScope trace(A, nd.n, 0, cls);
-        int iters = 0;
-        if (nd.n <= (uint32_t)cap) iters = process_node<TT, true, EXACT>(A, nd, 0, S);
-        else if constexpr (TT == RPW_STREAM_THREADS) iters = process_node<TT, false, EXACT>(A, nd, 0, S);
-        trace.done(iters);
-        if (threadIdx.x == 0) atomicAdd(A.stats + 1, 1u);
-        if (next >= count) break;
-        i = next;
-        __syncthreads();  // the next node reuses the shared-memory arrays
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K3b: levels >= 1 — persistent kernel, level-synchronous device worklist with no host round trip:
-// every split at level l pushed its children to the queue of level l+1; a grid-wide barrier
-// separates levels; the kernel ends when a level enqueued nothing.  Typical scans never split: every
-// block then reads an empty queue and leaves without touching the barrier.
-//
-// The grid is one block per SM, launched cooperatively (all blocks resident, so the barrier cannot
-// deadlock), and the barrier itself is a counter in global memory (arrive + spin with nanosleep).
-// All cross-block data (children, queues, counters) is read with ld.global.cg, so no stale L1 lines
-// are involved.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void grid_barrier(uint32_t* ctr, uint32_t target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(ctr, 1u);
-        while (*reinterpret_cast<volatile uint32_t*>(ctr) < target) __nanosleep(64);
-        __threadfence();
-    }
-    __syncthreads();
-}
-
-template <bool EXACT>
-__global__ void __launch_bounds__(kFitThreads, kLevelBlocksPerSm) rpw_fit_levels_kernel(FitArgs A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int TT = kFitThreads;
-    FitSmem S = carve_smem(smem_raw, A.smem_cap, TT / 32);
-    __shared__ uint32_t s_fetch;
-    uint32_t n_done = 0, pre = 0, bar_target = 0;
-    if (blockIdx.x == 0 && threadIdx.x < kClsWords && A.host_counts)  // grid estimate for the next launch group (zero-copy store)
-        A.host_counts[threadIdx.x] = threadIdx.x < kNumFitClasses ? __ldcg(A.cls_count + threadIdx.x) : (uint32_t)A.n_scans;
-    Tick ktick(A.timing);
-    int level = 0;
-    for (;;) {
-        const uint32_t cnt = min(__ldcg(A.q_count + level + 1), A.q_cap);
-        if (cnt == 0) break;
-        level++;
-        const NodeRef* q = A.queue[level & 1];
-        // the cursor of the NEXT node is fetched while the current one is processed
-        if (threadIdx.x == 0) pre = atomicAdd(A.fetch_ctr + level, 1u);
-        for (;;) {
-            __syncthreads();
-            if (threadIdx.x == 0) s_fetch = pre;
-            __syncthreads();
-            const uint32_t id = s_fetch;
-            ktick(8);
-            if (id >= cnt) break;
-            if (threadIdx.x == 0) pre = atomicAdd(A.fetch_ctr + level, 1u);
-            NodeRef nd;
-            const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(q + id));
-            nd.start = raw.x; nd.n = raw.y; nd.root = raw.z; nd.pad = 0;
-            TraceScope trace(A, nd.n, level, 0xFFFF);
-            int iters;
-            if (nd.n <= (uint32_t)A.smem_cap) iters = process_node<TT, true, EXACT>(A, nd, level, S);
-            else iters = process_node<TT, false, EXACT>(A, nd, level, S);
-            trace.done(iters);
-            n_done++;
-            if (A.timing && threadIdx.x == 0) ktick.last = clock64();
-        }
-        bar_target += gridDim.x;
-        grid_barrier(A.stats + 4, bar_target);
-        ktick(9);
-    }
-    // bookkeeping + self-cleaning: the last block to arrive publishes the totals and zeroes the
-    // per-level counters, so the next call needs no memset
-    if (threadIdx.x == 0) {
-        if (n_done) atomicAdd(A.stats + 1, n_done);
-        __threadfence();
-        const uint32_t arrived = atomicAdd(A.stats + 2, 1u);
-        if (arrived == gridDim.x - 1) {
-            A.stats[0] = max(A.stats[0], (uint32_t)level + 1);
-            A.stats[3] += atomicExch(A.stats + 1, 0u);
-            A.stats[2] = 0;
-            A.stats[4] = 0;
-            for (int l = 0; l <= level + 1; ++l) { A.fetch_ctr[l] = 0; A.q_count[l] = 0; }
         }
     }
 }
@@ -1730,10 +553,6 @@ __global__ void rpw_atan2_kernel(const float* __restrict__ y, const float* __res
 // =============================================================================================
 // host-side launchers
 // =============================================================================================
-size_t fit_smem_bytes(int smem_cap, int threads) {
-    return (size_t)smem_cap * 13 + (2 * (threads / 32) * kRedMax + 256 + kMiscWords) * 4 + 16;
-}
-
 cudaError_t launch_bin(cudaStream_t st, const PointLayout& lay, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
                        const ZoneModel& zm, uint16_t* keys, uint8_t* labels, uint32_t* blk_hist, uint32_t* cls_count,
                        const FusionTable* fusion, int max_chunks, int batch) {
@@ -1761,60 +580,6 @@ cudaError_t launch_scatter(cudaStream_t st, const PointLayout& lay, const float*
     return cudaGetLastError();
 }
 
-template <typename KernelT>
-static cudaError_t set_smem(KernelT k, size_t bytes) {
-    return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-}
-
-// Size classes of the level-0 kernel: (threads, largest patch, shared-memory capacity in points).
-// Finer steps waste less shared memory per resident patch (a 2100-point patch in a 4096-point slot
-// blocks twice the memory it needs for its whole 40 us life), which is what bounds the fit phase.
-struct FitClass { int threads; uint32_t hi; int cap; };
-static const FitClass kFitClasses[kNumFitClasses] = {
-    {RPW_T0, 1024, 1024}, {RPW_T1, 2048, 2048}, {128, 3072, 3072}, {128, 4096, 4096}, {256, 5632, 5632}, {256, kCapLarge, kCapLarge},
-    {RPW_STREAM_THREADS, 0xFFFFFFFFu, kCapStream},
-};
-
-template <int TT>
-static cudaError_t configure_roots() {
-    size_t need = 0;
-    for (const FitClass& c : kFitClasses) if (c.threads == TT) need = fit_smem_bytes(c.cap, TT) > need ? fit_smem_bytes(c.cap, TT) : need;
-    cudaError_t e = set_smem(rpw_fit_roots_kernel<TT, true>, need);
-    if (e != cudaSuccess) return e;
-    return set_smem(rpw_fit_roots_kernel<TT, false>, need);
-}
-
-cudaError_t fit_configure(int smem_cap, int* blocks_per_sm) {
-    cudaError_t e;
-    if ((e = configure_roots<32>()) != cudaSuccess) return e;
-    if ((e = configure_roots<64>()) != cudaSuccess) return e;
-    if ((e = configure_roots<128>()) != cudaSuccess) return e;
-    if ((e = configure_roots<256>()) != cudaSuccess) return e;
-    if ((e = configure_roots<512>()) != cudaSuccess) return e;
-    const size_t smem = fit_smem_bytes(smem_cap, kFitThreads);
-    if ((e = set_smem(rpw_fit_levels_kernel<true>, smem)) != cudaSuccess) return e;
-    if ((e = set_smem(rpw_fit_levels_kernel<false>, smem)) != cudaSuccess) return e;
-    int a = 0, b = 0;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, rpw_fit_levels_kernel<true>, kFitThreads, smem)) != cudaSuccess) return e;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, rpw_fit_levels_kernel<false>, kFitThreads, smem)) != cudaSuccess) return e;
-    *blocks_per_sm = a < b ? a : b;
-    return cudaSuccess;
-}
-
-ClassBounds fit_class_bounds() {
-    ClassBounds cb;
-    for (int c = 0; c < kNumFitClasses; ++c) cb.hi[c] = kFitClasses[c].hi;
-    return cb;
-}
-
-template <int TT>
-static void launch_roots_tt(cudaStream_t st, const FitArgs& args, int cls, int cap, unsigned grid) {
-    const size_t sm = fit_smem_bytes(cap, TT);
-    if (args.fp.exact_eig) rpw_fit_roots_kernel<TT, true><<<grid, TT, sm, st>>>(args, cls, cap);
-    else rpw_fit_roots_kernel<TT, false><<<grid, TT, sm, st>>>(args, cls, cap);
-}
-
-// size class cls in [0, kNumFitClasses): patches with kFitClasses[cls-1].hi < n <= kFitClasses[cls].hi
 cudaError_t launch_compact(cudaStream_t st, const PointLayout& lay, const float* pts, const uint8_t* labels, const uint64_t* scan_off,
                            const uint32_t* chunk_base, uint32_t* cnt, const FusionTable* fusion, float* ground, float* nonground,
                            uint32_t* scan_counts, int max_chunks, int batch) {
@@ -1855,28 +620,30 @@ cudaError_t launch_gather_xyz(cudaStream_t st, const float* xyz, const uint32_t*
     return cudaGetLastError();
 }
 
-cudaError_t launch_fit_roots(cudaStream_t st, const FitArgs& args, int cls, unsigned grid) {
-    const FitClass& c = kFitClasses[cls];
-    if (grid == 0) grid = 1;
-    switch (c.threads) {
-        case 32: launch_roots_tt<32>(st, args, cls, c.cap, grid); break;
-        case 64: launch_roots_tt<64>(st, args, cls, c.cap, grid); break;
-        case 128: launch_roots_tt<128>(st, args, cls, c.cap, grid); break;
-        case 256: launch_roots_tt<256>(st, args, cls, c.cap, grid); break;
-        default: launch_roots_tt<512>(st, args, cls, c.cap, grid); break;
-    }
-    return cudaGetLastError();
+// The fit kernels live in two translation units (rpw_fit.cuh): the default ones and the ones that carry the
+// reference-order arithmetic; the latter run whenever it is switched on.
+cudaError_t fit_configure_fast(int smem_cap, int* blocks_per_sm);
+cudaError_t fit_configure_replay(int smem_cap, int* blocks_per_sm);
+cudaError_t launch_fit_roots_fast(cudaStream_t st, const FitArgs& args, int cls, unsigned grid);
+cudaError_t launch_fit_roots_replay(cudaStream_t st, const FitArgs& args, int cls, unsigned grid);
+cudaError_t launch_fit_levels_fast(cudaStream_t st, const FitArgs& args, int grid_blocks);
+cudaError_t launch_fit_levels_replay(cudaStream_t st, const FitArgs& args, int grid_blocks);
+
+cudaError_t fit_configure(int smem_cap, int* blocks_per_sm) {
+    int a = 0, b = 0;
+    cudaError_t e = fit_configure_fast(smem_cap, &a);
+    if (e != cudaSuccess) return e;
+    if ((e = fit_configure_replay(smem_cap, &b)) != cudaSuccess) return e;
+    *blocks_per_sm = a < b ? a : b;
+    return cudaSuccess;
 }
 
-// Launched with cudaLaunchCooperativeKernel: the driver only starts the grid when every block can be
-// resident, which is what makes the spin barrier safe however many handles share the device (two
-// plain launches from different handles could otherwise each hold half of the SMs and wait for the
-// other half forever).
+cudaError_t launch_fit_roots(cudaStream_t st, const FitArgs& args, int cls, unsigned grid) {
+    return args.fp.exact_replay >= 0 ? launch_fit_roots_replay(st, args, cls, grid) : launch_fit_roots_fast(st, args, cls, grid);
+}
+
 cudaError_t launch_fit_levels(cudaStream_t st, const FitArgs& args, int grid_blocks) {
-    FitArgs a = args;
-    void* params[] = {&a};
-    void* fn = args.fp.exact_eig ? (void*)rpw_fit_levels_kernel<true> : (void*)rpw_fit_levels_kernel<false>;
-    return cudaLaunchCooperativeKernel(fn, dim3(grid_blocks), dim3(kFitThreads), params, fit_smem_bytes(args.smem_cap, kFitThreads), st);
+    return args.fp.exact_replay >= 0 ? launch_fit_levels_replay(st, args, grid_blocks) : launch_fit_levels_fast(st, args, grid_blocks);
 }
 
 cudaError_t launch_eig3(cudaStream_t st, const float* mats, size_t count, float* evals, float* evecs) {

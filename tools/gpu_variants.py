@@ -43,7 +43,7 @@ def child(path, B):
         ndiff = int((np.load(first) != labels).sum())
     else:
         np.save(first, labels); ndiff = 0
-    print(f"{os.environ.get('RPW_B200_LIB', 'default').split('/')[-1]:16s} step ms {min(best):.3f} (runs {' '.join('%.3f' % b for b in best)})  "
+    print(f"{os.environ.get('RPW_VARIANT_LABEL', 'default'):32s} step ms {min(best):.3f} (runs {' '.join('%.3f' % b for b in best)})  "
           f"{B / min(best):.1f} k scans/s  bin {p['bin']['ms']/R:.3f} scatter {p['scatter']['ms']/R:.3f} fit {p['fit']['ms']/R:.3f}  labels {digest} ({ndiff} differ from the first variant)", flush=True)
 
 
@@ -61,8 +61,14 @@ if __name__ == "__main__":
     path = os.path.join(tempfile.gettempdir(), "rpw_variant_batch.npz")
     np.savez(path, pts=np.concatenate(scans), off=off)
     if os.path.exists(path + ".labels.npy"): os.remove(path + ".labels.npy")
-    for name in args:
+    for spec in args:
+        # "name" or "name:VAR=value,VAR=value" (environment of the child: RPW_PLANE_SOLVER, RPW_EXACT_REPLAY, ...)
+        name, _, envs = spec.partition(":")
         env = dict(os.environ)
+        for kv in filter(None, envs.split(",")):
+            k, _, v = kv.partition("=")
+            env[k] = v
+        env["RPW_VARIANT_LABEL"] = spec
         if name != "default":
             env["RPW_B200_LIB"] = str(ROOT / "ros2-recursive-patchwork-implementation_b200" / "_variants" / f"{name}.so")
         subprocess.run([sys.executable, __file__, "--child", path, str(B)], env=env, check=False)
