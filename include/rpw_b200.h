@@ -332,6 +332,11 @@ void* rpw_host_alloc(size_t bytes); /* pinned host memory (NULL on failure) */
 void rpw_host_free(void* p);
 /* Kernels launched through this handle since creation (bench.py's gpu_launches). */
 uint64_t rpw_kernel_launches(const rpw_handle* h);
+/* Single host-path scans (rpw_segment and what calls it) run as one captured CUDA graph per handle -- eleven kernels
+ * with fixed parameters, re-captured when the configuration, solver, record layout, stream or capacity changes or a
+ * scan outgrows the captured grids.  launches / captures so far; enable = 0 / 1 switches the graph path off / on,
+ * negative leaves it as it is (environment: RPW_NO_GRAPH=1). */
+int rpw_scan_graph(rpw_handle* h, int enable, uint64_t* launches, uint64_t* captures);
 int rpw_abi_version(void);
 
 #ifdef __cplusplus

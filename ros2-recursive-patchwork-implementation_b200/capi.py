@@ -54,7 +54,7 @@ NODE_DTYPE = np.dtype([("scan", "<i4"), ("root", "<i4"), ("depth", "<i4"), ("sta
 EXPORTS = ["rpw_default_config", "rpw_zone_model", "rpw_create", "rpw_destroy", "rpw_set_config", "rpw_get_config", "rpw_reserve", "rpw_capacity",
            "rpw_set_plane_solver", "rpw_set_exact_replay", "rpw_set_stream", "rpw_last_error", "rpw_segment", "rpw_segment_batch", "rpw_segment_batch_async", "rpw_wait",
            "rpw_segment_pc2", "rpw_segment_fused", "rpw_segment_clouds", "rpw_last_clouds", "rpw_sample_ground_and_obstacles", "rpw_bev_image", "rpw_segment_device", "rpw_debug_keys", "rpw_debug_enable_nodes", "rpw_debug_nodes",
-           "rpw_debug_eig3", "rpw_debug_normal", "rpw_debug_atan2", "rpw_debug_fit_timing", "rpw_debug_fit_trace", "rpw_profile_enable", "rpw_profile_read", "rpw_host_alloc", "rpw_host_free", "rpw_kernel_launches", "rpw_abi_version"]
+           "rpw_debug_eig3", "rpw_debug_normal", "rpw_debug_atan2", "rpw_debug_fit_timing", "rpw_debug_fit_trace", "rpw_profile_enable", "rpw_profile_read", "rpw_host_alloc", "rpw_host_free", "rpw_kernel_launches", "rpw_scan_graph", "rpw_abi_version"]
 
 _lib = None
 
@@ -118,6 +118,7 @@ def load_library() -> C.CDLL:
     lib.rpw_host_alloc.argtypes = [sz]; lib.rpw_host_alloc.restype = vp
     lib.rpw_host_free.argtypes = [vp]; lib.rpw_host_free.restype = None
     lib.rpw_kernel_launches.argtypes = [vp]; lib.rpw_kernel_launches.restype = C.c_uint64
+    lib.rpw_scan_graph.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]; lib.rpw_scan_graph.restype = C.c_int
     lib.rpw_abi_version.argtypes = []; lib.rpw_abi_version.restype = C.c_int
     _lib = lib
     return lib
@@ -404,6 +405,12 @@ class Handle:
         out["fit_grid_blocks"] = int(p.fit_grid_blocks)
         out["fit_smem_points"] = int(p.fit_smem_points)
         return out
+
+    def scan_graph(self, enable: int = -1):
+        """(graph launches, graph captures) of the single-scan path; enable = 0 / 1 switches it off / on."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._check(self.lib.rpw_scan_graph(self._h, int(enable), C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def kernel_launches(self) -> int:
         return int(self.lib.rpw_kernel_launches(self._h))

@@ -97,8 +97,27 @@ struct rpw_handle {
     uint32_t dbg_cap = 0;
     bool dbg_enabled = false;
 
+    // The pipeline of a single host-path scan as a CUDA graph (the reference's real use: one scan per ROS2 callback):
+    // kernels with fixed parameters and grids sized for `chunks` 4096-point chunks; a call only copies its points and
+    // its 24-byte meta block in, launches the graph and copies the labels out.  Re-captured when the configuration,
+    // the solver, the record layout, the stream or the capacity changes (cfg_epoch) or a scan needs more chunks.
+    struct ScanGraph {
+        cudaGraphExec_t exec = nullptr;
+        int chunks = 0;
+        uint64_t epoch = 0;
+        PointLayout lay{};
+        cudaStream_t stream = nullptr;
+    } graph1;
+    uint64_t cfg_epoch = 1;
+    bool graphs_enabled = true;
+    uint64_t graph_launches = 0, graph_captures = 0;
+
     // host staging
-    uint64_t* h_meta = nullptr;  // pinned: scan_off[batch+1] then chunk_base[batch+1] (as u32)
+    static constexpr int kMetaSlots = 8;
+    cudaEvent_t meta_ev[kMetaSlots] = {};  // the upload from ring slot s has been consumed
+    size_t meta_slot_bytes = 0;
+    int meta_next = 0;
+    uint64_t* h_meta = nullptr;  // pinned ring of kMetaSlots blocks: scan_off[batch+1] (u64) then chunk_base[batch+1] (u32)
     void* h_stage_in = nullptr;  // pinned, lazily allocated, cap_points*16
     uint8_t* h_stage_labels = nullptr;
     uint32_t* h_stats = nullptr;  // pinned 8 words
@@ -172,6 +191,7 @@ static int check_config(const rpw_config* c, std::string& why) {
 }
 
 static void apply_solver(rpw_handle* h) {
+    h->cfg_epoch++;
     h->fp.exact_eig = (h->solver == RPW_SOLVER_EIGEN_QR || h->solver == RPW_SOLVER_REFERENCE) ? 1 : 0;
     h->fp.hybrid = h->solver == RPW_SOLVER_HYBRID ? 1 : 0;
     h->fp.exact_replay = h->solver == RPW_SOLVER_REFERENCE ? 0 : h->exact_replay;
@@ -260,7 +280,8 @@ static void free_capacity_buffers(rpw_handle* h) {
         cudaFree(L.d_counters); L.d_counters = nullptr;
     }
     cudaFree(h->d_scan_off); h->d_scan_off = nullptr;
-    cudaFree(h->d_chunk_base); h->d_chunk_base = nullptr;
+    h->d_chunk_base = nullptr;  // (inside the d_scan_off block)
+    if (h->graph1.exec) { cudaGraphExecDestroy(h->graph1.exec); h->graph1.exec = nullptr; }
     if (h->h_meta) { cudaFreeHost(h->h_meta); h->h_meta = nullptr; }
     free_patch_buffers(h);
     // lazily allocated, sized by the capacity: dropped here, re-created on demand
@@ -290,9 +311,14 @@ static int alloc_capacity_buffers(rpw_handle* h) {
         RPW_ALLOC(cudaMalloc(&L.d_queue[0], (size_t)h->q_cap * sizeof(NodeRef)));
         RPW_ALLOC(cudaMalloc(&L.d_queue[1], (size_t)h->q_cap * sizeof(NodeRef)));
     }
-    RPW_ALLOC(cudaMalloc(&h->d_scan_off, (B + 1) * sizeof(uint64_t)));
-    RPW_ALLOC(cudaMalloc(&h->d_chunk_base, (B + 1) * sizeof(uint32_t)));
-    RPW_ALLOC(cudaMallocHost(&h->h_meta, (B + 1) * (sizeof(uint64_t) + sizeof(uint32_t)) + 64));
+    // one device block: scan_off[batch + 1] (u64) directly followed by chunk_base[batch + 1] (u32) of the CURRENT call,
+    // so that a call uploads its meta data with a single copy
+    h->meta_slot_bytes = ((B + 1) * (sizeof(uint64_t) + sizeof(uint32_t)) + 63) / 64 * 64;
+    RPW_ALLOC(cudaMalloc(&h->d_scan_off, h->meta_slot_bytes));
+    h->d_chunk_base = reinterpret_cast<uint32_t*>(h->d_scan_off + B + 1);
+    RPW_ALLOC(cudaMallocHost(&h->h_meta, h->meta_slot_bytes * rpw_handle::kMetaSlots));
+    h->meta_next = 0;
+    h->cfg_epoch++;
 #undef RPW_ALLOC
     int rc = alloc_patch_buffers(h);
     if (rc != RPW_OK) return rc;
@@ -325,6 +351,7 @@ void rpw_destroy(rpw_handle* h) {
         if (L.main) cudaStreamDestroy(L.main);
     }
     if (h->ev_call) cudaEventDestroy(h->ev_call);
+    for (auto& e : h->meta_ev) if (e) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -390,6 +417,8 @@ int rpw_create(const rpw_config* cfg, int device, size_t max_total_points, size_
         TRYC(cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
     }
     TRYC(cudaEventCreateWithFlags(&h->ev_call, cudaEventDisableTiming));
+    for (auto& e : h->meta_ev) TRYC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (const char* s = getenv("RPW_NO_GRAPH")) h->graphs_enabled = atoi(s) == 0;
     TRYC(cudaMalloc(&h->d_dbg_count, sizeof(uint32_t)));
     TRYC(cudaMemset(h->d_dbg_count, 0, sizeof(uint32_t)));
     TRY(alloc_capacity_buffers(h));
@@ -483,13 +512,29 @@ int rpw_get_config(const rpw_handle* h, rpw_config* out) {
 
 int rpw_set_stream(rpw_handle* h, void* cuda_stream) {
     if (!h) return RPW_ERR_BAD_ARG;
-    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    cudaStream_t next = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    if (next != h->stream) {
+        // work still queued on the old stream uses the handle's buffers: the new stream waits for it
+        RPW_CUDA(h, cudaSetDevice(h->device));
+        RPW_CUDA(h, cudaEventRecord(h->ev_call, h->stream));
+        RPW_CUDA(h, cudaStreamWaitEvent(next, h->ev_call, 0));
+        h->stream = next;
+        h->cfg_epoch++;
+    }
     return RPW_OK;
 }
 
 const char* rpw_last_error(const rpw_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 uint64_t rpw_kernel_launches(const rpw_handle* h) { return h ? h->launches : 0; }
+
+int rpw_scan_graph(rpw_handle* h, int enable, uint64_t* launches, uint64_t* captures) {
+    if (!h) return RPW_ERR_BAD_ARG;
+    if (enable >= 0) h->graphs_enabled = enable != 0;
+    if (launches) *launches = h->graph_launches;
+    if (captures) *captures = h->graph_captures;
+    return RPW_OK;
+}
 
 void* rpw_host_alloc(size_t bytes) {
     void* p = nullptr;
@@ -539,16 +584,20 @@ struct ProfScope {
 // ---------------------------------------------------------------------------------------------
 // launch sequence
 // ---------------------------------------------------------------------------------------------
-// Fills the pinned meta block (scan offsets, chunk bases), uploads it if it changed.
+// Fills a slot of the pinned meta ring (scan offsets relative to the first scan, chunk bases) and uploads it with one
+// copy, unless the call has the same offsets as the previous one.  No synchronisation: a slot is reused eight calls
+// later, after its own upload has been consumed (an event per slot).
 static int upload_meta(rpw_handle* h, const uint64_t* off, size_t batch) {
     if (batch == 0 || batch > h->cap_batch) RPW_FAIL(h, RPW_ERR_CAPACITY, "batch %zu exceeds the handle's max_batch %zu", batch, h->cap_batch);
     if (off[batch] - off[0] > h->cap_points) RPW_FAIL(h, RPW_ERR_CAPACITY, "%llu points exceed the handle's capacity %zu", (unsigned long long)(off[batch] - off[0]), h->cap_points);
-    const bool same = h->last_batch == batch && h->last_off.size() == batch + 1 && memcmp(h->last_off.data(), off, (batch + 1) * sizeof(uint64_t)) == 0;
+    bool same = h->last_batch == batch && h->last_off.size() == batch + 1;
+    for (size_t i = 0; same && i <= batch; ++i) same = h->last_off[i] == off[i] - off[0];
     if (same) return RPW_OK;
-    // the previous call's asynchronous upload may still be reading h_meta
-    RPW_CUDA(h, cudaStreamSynchronize(h->stream));
-    uint64_t* so = h->h_meta;
-    uint32_t* cb = reinterpret_cast<uint32_t*>(h->h_meta + (h->cap_batch + 1));
+    const int slot = h->meta_next;
+    h->meta_next = (slot + 1) % rpw_handle::kMetaSlots;
+    RPW_CUDA(h, cudaEventSynchronize(h->meta_ev[slot]));  // (an event never recorded counts as complete)
+    uint64_t* so = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(h->h_meta) + (size_t)slot * h->meta_slot_bytes);
+    uint32_t* cb = reinterpret_cast<uint32_t*>(so + batch + 1);
     uint32_t run = 0;
     for (size_t i = 0; i <= batch; ++i) {
         so[i] = off[i] - off[0];
@@ -558,8 +607,9 @@ static int upload_meta(rpw_handle* h, const uint64_t* off, size_t batch) {
             run += (uint32_t)((off[i + 1] - off[i] + kBinChunk - 1) / kBinChunk);
         }
     }
-    RPW_CUDA(h, cudaMemcpyAsync(h->d_scan_off, so, (batch + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
-    RPW_CUDA(h, cudaMemcpyAsync(h->d_chunk_base, cb, (batch + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    h->d_chunk_base = reinterpret_cast<uint32_t*>(h->d_scan_off + batch + 1);
+    RPW_CUDA(h, cudaMemcpyAsync(h->d_scan_off, so, (batch + 1) * (sizeof(uint64_t) + sizeof(uint32_t)), cudaMemcpyHostToDevice, h->stream));
+    RPW_CUDA(h, cudaEventRecord(h->meta_ev[slot], h->stream));
     h->last_off.assign(so, so + batch + 1);
     h->last_batch = batch;
     h->last_total = (size_t)so[batch];
@@ -574,13 +624,15 @@ struct StreamSwap {
 };
 
 // One launch group: scans [b0, b0 + nb) of the call on lane `L`, stream `st`.
+// graph_chunks > 0: the launches are being captured into the single-scan graph, whose grids must hold for every scan of
+// up to graph_chunks chunks (blocks past a scan's end leave at once) and must not depend on the previous call.
 static int run_group(rpw_handle* h, rpw_handle::Lane& L, cudaStream_t st, const float* d_pts, const PointLayout& lay, uint8_t* d_labels,
-                     size_t b0, size_t nb) {
+                     size_t b0, size_t nb, int graph_chunks = 0) {
     const uint64_t* so = h->last_off.data();
     uint64_t max_n = 0;
     for (size_t i = b0; i < b0 + nb; ++i) max_n = so[i + 1] - so[i] > max_n ? so[i + 1] - so[i] : max_n;
-    if (so[b0 + nb] == so[b0]) return RPW_OK;  // nothing but empty scans
-    const int max_chunks = (int)((max_n + kBinChunk - 1) / kBinChunk);
+    if (so[b0 + nb] == so[b0] && !graph_chunks) return RPW_OK;  // nothing but empty scans
+    const int max_chunks = graph_chunks ? graph_chunks : (int)((max_n + kBinChunk - 1) / kBinChunk);
     StreamSwap swap(h, st);
     // The kernels index scans relative to the pointers they are given.
     const uint64_t* d_so = h->d_scan_off + b0;
@@ -633,9 +685,9 @@ static int run_group(rpw_handle* h, rpw_handle::Lane& L, cudaStream_t st, const 
         // after one load: the estimate never affects results.
         static const char* no_est = getenv("RPW_NO_GRID_ESTIMATE");
         const ClassBounds cb = fit_class_bounds();
-        const uint64_t group_pts = so[b0 + nb] - so[b0];
+        const uint64_t group_pts = graph_chunks ? (uint64_t)graph_chunks * kBinChunk : so[b0 + nb] - so[b0];
         unsigned grids[kNumFitClasses];
-        const uint32_t est_scans = L.h_counts[kClsWords - 1];
+        const uint32_t est_scans = graph_chunks ? 0u : L.h_counts[kClsWords - 1];
         for (int c = 0; c < kNumFitClasses; ++c) {
             const uint64_t lo = c == 0 ? 0 : cb.hi[c - 1];
             uint64_t bound = group_pts / (lo + 1);
@@ -671,10 +723,61 @@ static int run_group(rpw_handle* h, rpw_handle::Lane& L, cudaStream_t st, const 
     return RPW_OK;
 }
 
+static bool same_layout(const PointLayout& a, const PointLayout& b) {
+    return a.vec4 == b.vec4 && a.stride == b.stride && a.ox == b.ox && a.oy == b.oy && a.oz == b.oz;
+}
+
+// One host-path scan through the captured graph (see rpw_handle::ScanGraph).
+static int run_scan_graph(rpw_handle* h, const PointLayout& lay) {
+    rpw_handle::ScanGraph& g = h->graph1;
+    const int chunks = (int)((h->last_total + kBinChunk - 1) / kBinChunk);
+    if (!g.exec || g.epoch != h->cfg_epoch || g.stream != h->stream || !same_layout(g.lay, lay) || chunks > g.chunks) {
+        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+        int want = chunks + chunks / 4 + 1;  // head room: frames of a stream vary by a few percent
+        const int cap_chunks = (int)(h->cap_points / kBinChunk + 1);
+        if (want > cap_chunks) want = cap_chunks;
+        if (want < chunks) want = chunks;
+        const uint64_t launches_before = h->launches;
+        cudaGraph_t graph = nullptr;
+        RPW_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = RPW_OK;
+        for (auto& L : h->lane) {
+            uint32_t* st = L.d_counters + 2 * (size_t)h->levels_cap;
+            if (cudaMemsetAsync(st, 0, sizeof(uint32_t), h->stream) != cudaSuccess || cudaMemsetAsync(st + 3, 0, sizeof(uint32_t), h->stream) != cudaSuccess) rc = RPW_ERR_CUDA;
+        }
+        if (rc == RPW_OK) rc = run_group(h, h->lane[0], h->stream, h->d_in, lay, h->d_labels, 0, 1, want);
+        const cudaError_t ec = cudaStreamEndCapture(h->stream, &graph);
+        h->launches = launches_before;  // capturing launches nothing
+        cudaError_t ei = cudaSuccess;
+        if (rc == RPW_OK && ec == cudaSuccess && graph) ei = cudaGraphInstantiate(&g.exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (rc != RPW_OK || ec != cudaSuccess || ei != cudaSuccess || !g.exec) {
+            // not fatal: the same launches work outside a graph (the caller falls back to them)
+            g.exec = nullptr;
+            cudaGetLastError();
+            h->graphs_enabled = false;
+            h->err = std::string("single-scan graph unavailable (") + cudaGetErrorString(ec != cudaSuccess ? ec : ei) + "), using plain launches";
+            return -1;
+        }
+        g.chunks = want; g.epoch = h->cfg_epoch; g.lay = lay; g.stream = h->stream;
+        h->graph_captures++;
+    }
+    RPW_CUDA(h, cudaGraphLaunch(g.exec, h->stream));
+    h->graph_launches++;
+    h->launches += 4 + kNumFitClasses;
+    h->launches_call = 4 + kNumFitClasses;
+    return RPW_OK;
+}
+
 // Enqueues K1..K3 for scans [0, batch) whose points are device resident at `d_pts`.
 static int run_pipeline(rpw_handle* h, const float* d_pts, const PointLayout& lay, uint8_t* d_labels, size_t batch) {
     h->launches_call = 0;
     h->last_pts = d_pts; h->last_lay = lay; h->last_labels = d_labels; h->last_fused = h->fusion_arg != nullptr;
+    if (batch == 1 && h->graphs_enabled && h->last_total > 0 && d_pts == h->d_in && d_labels == h->d_labels && !h->fusion_arg &&
+        !h->dbg_enabled && !h->timing_enabled && !h->trace_cap && !h->prof_enabled) {
+        const int rc = run_scan_graph(h, lay);
+        if (rc >= 0) return rc;  // (-1: no graph on this driver, fall through to the plain launches)
+    }
     // stats[0] (levels) and stats[3] (nodes) accumulate over the call's launch groups
     for (auto& L : h->lane) {
         uint32_t* st = L.d_counters + 2 * (size_t)h->levels_cap;
@@ -740,8 +843,18 @@ static int reset_dbg(rpw_handle* h) {
     return RPW_OK;
 }
 
+// A device worklist that overflowed dropped children (their points keep stale labels): the levels kernel reports it
+// through mapped host memory, and every entry point that synchronises checks it, with or without a stats request.
+static int check_overflow(rpw_handle* h) {
+    bool seen = false;
+    for (auto& L : h->lane)
+        if (L.h_counts && L.h_counts[kClsWords - 2]) { L.h_counts[kClsWords - 2] = 0; seen = true; }
+    if (seen) RPW_FAIL(h, RPW_ERR_CAPACITY, "device worklist overflowed (q_cap %u): labels of this call are incomplete", h->q_cap);
+    return RPW_OK;
+}
+
 static int fill_stats(rpw_handle* h, rpw_stats* st, uint8_t* const* labels, const size_t* n, size_t batch) {
-    if (!st) return RPW_OK;
+    if (!st) return check_overflow(h);
     memset(st, 0, sizeof(*st));
     for (int l = 0; l < rpw_handle::kLanes; ++l)
         RPW_CUDA(h, cudaMemcpyAsync(h->h_stats + 16 * l, h->lane[l].d_counters + 2 * (size_t)h->levels_cap, 10 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -751,11 +864,8 @@ static int fill_stats(rpw_handle* h, rpw_stats* st, uint8_t* const* labels, cons
         const uint32_t* s = h->h_stats + 16 * l;
         st->n_levels = s[0] > st->n_levels ? s[0] : st->n_levels;
         st->n_nodes += s[3];
-        if (s[8]) {
-            cudaMemsetAsync(h->lane[l].d_counters + 2 * (size_t)h->levels_cap + 8, 0, sizeof(uint32_t), h->stream);
-            RPW_FAIL(h, RPW_ERR_CAPACITY, "device worklist overflowed (q_cap %u)", h->q_cap);
-        }
     }
+    { const int rc = check_overflow(h); if (rc != RPW_OK) return rc; }
     uint64_t cnt[4] = {0, 0, 0, 0};
     for (size_t b = 0; b < batch; ++b) {
         const uint8_t* l = labels[b];
@@ -827,7 +937,7 @@ int rpw_wait(rpw_handle* h, rpw_stats* stats) {
         if (h->pend_labels.size() != h->last_batch) RPW_FAIL(h, RPW_ERR_BAD_ARG, "no host labels pending for stats");
         return fill_stats(h, stats, h->pend_labels.data(), n.data(), h->last_batch);
     }
-    return RPW_OK;
+    return check_overflow(h);
 }
 
 int rpw_segment_batch(rpw_handle* h, const float* const* clouds, const size_t* n, size_t batch, size_t stride_bytes,
@@ -957,6 +1067,7 @@ int rpw_segment_fused(rpw_handle* h, const rpw_sensor_cloud* sensors, size_t n_s
     if (rc != RPW_OK) return rc;
     RPW_CUDA(h, cudaMemcpyAsync(h->h_stage_labels, h->d_labels, total, cudaMemcpyDeviceToHost, h->stream));
     RPW_CUDA(h, cudaStreamSynchronize(h->stream));
+    { const int rc2 = check_overflow(h); if (rc2 != RPW_OK) return rc2; }
     o = 0;
     for (size_t s = 0; s < n_sensors; ++s) {
         if (sensors[s].n) memcpy(labels_out[s], h->h_stage_labels + o, sensors[s].n);
@@ -1010,6 +1121,7 @@ int rpw_last_clouds(rpw_handle* h, float* ground_xyz, float* nonground_xyz, int 
     h->launches += 2;
     RPW_CUDA(h, cudaMemcpyAsync(h->h_scan_counts, h->d_scan_counts, batch * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     RPW_CUDA(h, cudaStreamSynchronize(h->stream));
+    { const int rc = check_overflow(h); if (rc != RPW_OK) return rc; }
     for (size_t b = 0; b < 2 * batch; ++b) counts[b] = h->h_scan_counts[b];
     if (!on_device) {
         // exactly the bytes of the clouds: scan b's clouds start at record (scan offset b) of the caller's buffers

@@ -1140,7 +1140,8 @@ __global__ void __launch_bounds__(kFitThreads, kLevelBlocksPerSm) rpw_fit_levels
     FitSmem S = carve_smem(smem_raw, A.smem_cap, TT / 32);
     __shared__ uint32_t s_fetch;
     uint32_t n_done = 0, pre = 0, bar_target = 0;
-    if (blockIdx.x == 0 && threadIdx.x < kClsWords && A.host_counts)  // grid estimate for the next launch group (zero-copy store)
+    // grid estimate for the next launch group (zero-copy store); word kClsWords - 2 is the overflow report below
+    if (blockIdx.x == 0 && threadIdx.x < kClsWords && threadIdx.x != kClsWords - 2 && A.host_counts)
         A.host_counts[threadIdx.x] = threadIdx.x < kNumFitClasses ? __ldcg(A.cls_count + threadIdx.x) : (uint32_t)A.n_scans;
     Tick ktick(A.timing);
     int level = 0;
@@ -1186,6 +1187,9 @@ __global__ void __launch_bounds__(kFitThreads, kLevelBlocksPerSm) rpw_fit_levels
             A.stats[2] = 0;
             A.stats[4] = 0;
             for (int l = 0; l <= level + 1; ++l) { A.fetch_ctr[l] = 0; A.q_count[l] = 0; }
+            // a worklist that overflowed dropped children: reported to the host through mapped memory, so that every
+            // entry point sees it after its synchronisation, with or without a stats request
+            if (atomicExch(A.overflow, 0u) != 0u && A.host_counts) A.host_counts[kClsWords - 2] = 1u;
         }
     }
 }
@@ -1198,6 +1202,11 @@ __global__ void __launch_bounds__(kFitThreads, kLevelBlocksPerSm) rpw_fit_levels
 // Finer steps waste less shared memory per resident patch (a 2100-point patch in a 4096-point slot
 // blocks twice the memory it needs for its whole 40 us life), which is what bounds the fit phase.
 struct FitClass { int threads; uint32_t hi; int cap; };
+// (A second, "latency" table for calls of one or two scans -- twice to four times the threads per class, a 1024-thread
+// class keeping patches of up to 16384 points shared-memory resident -- made single scans SLOWER: C2 fit 102 -> 127 us,
+// C5 397 -> 480 us, only C4 596 -> 537 us.  A patch lives on one SM, whose four schedulers issue its pass at the same
+// rate however many warps share the work, and larger blocks pay more for every reduction and barrier of the serial
+// part of an iteration.)
 static const FitClass kFitClasses[kNumFitClasses] = {
     {RPW_T0, 1024, 1024}, {RPW_T1, 2048, 2048}, {128, 3072, 3072}, {128, 4096, 4096}, {256, 5632, 5632}, {256, kCapLarge, kCapLarge},
     {RPW_STREAM_THREADS, 0xFFFFFFFFu, kCapStream},

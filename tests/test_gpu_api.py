@@ -212,6 +212,47 @@ def test_degenerate_cloud_order_is_the_reference(rpw, h, ref):
         assert np.array_equal(ng.view(np.uint32), r["non_ground"].view(np.uint32)), n_in
 
 
+def test_single_scan_graph_path(rpw, gpu_handle_factory, oracle):
+    """Single host-path scans run as one captured CUDA graph per handle: same labels as the plain launches, one capture
+    for a stream of frames of varying size, a new capture when the configuration / solver changes or a frame outgrows
+    the captured grids -- and the debug switches fall back to plain launches."""
+    cfg = rpw.PatchworkConfig(filtering_radius=80.0)
+    hd = gpu_handle_factory(cfg, 1 << 19, 2)
+    frames = [rpw.synth.spinning_scan(4000 + k, 64, 800 + 13 * k) for k in range(6)]   # 51 k .. 55 k points
+    want = [oracle.run(cfg, a)["labels"] for a in frames]
+    hd.scan_graph(0)
+    plain = [hd.segment(a) for a in frames]
+    assert hd.scan_graph() == (0, 0)
+    hd.scan_graph(1)
+    for rep in range(3):
+        for a, p_, w in zip(frames, plain, want):
+            got = hd.segment(a)
+            assert np.array_equal(got, p_) and (got == w).mean() >= 0.999
+    launches, captures = hd.scan_graph()
+    assert launches == 18 and captures == 1, (launches, captures)
+    big = rpw.synth.spinning_scan(4100, 64, 1875)                                         # 120 k points: outgrows the graph
+    assert (hd.segment(big) == oracle.run(cfg, big)["labels"]).mean() >= 0.999
+    assert hd.scan_graph() == (19, 2)
+    assert np.array_equal(hd.segment(frames[0]), plain[0]) and hd.scan_graph() == (20, 2)  # smaller frames reuse the larger graph
+    cfg2 = rpw.PatchworkConfig(filtering_radius=80.0, num_sectors=12)
+    hd.set_config(cfg2.to_c())
+    assert (hd.segment(frames[1]) == oracle.run(cfg2, frames[1])["labels"]).mean() >= 0.999
+    assert hd.scan_graph() == (21, 3)
+    hd.set_plane_solver(rpw.capi.SOLVER_REFERENCE)
+    assert np.array_equal(hd.segment(frames[2]), oracle.run(cfg2, frames[2])["labels"]) and hd.scan_graph() == (22, 4)
+    hd.set_plane_solver(rpw.capi.SOLVER_HYBRID)
+    hd.enable_nodes(True)                                                                 # node records: plain launches
+    hd.segment(frames[3])
+    assert len(hd.debug_nodes()) > 0 and hd.scan_graph()[0] == 22
+    hd.enable_nodes(False)
+    two = hd.segment_batch([frames[0], frames[1]])                                        # batches: plain launches
+    assert hd.scan_graph()[0] == 22 and (two[1] == oracle.run(cfg2, frames[1])["labels"]).mean() >= 0.999
+    # clouds, sample and raster of the last single scan work after a graph launch
+    g, ng, lab = hd.segment_clouds(frames[4])
+    assert hd.scan_graph()[0] == 23 and len(g) == int((lab == 1).sum()) and len(ng) == int(np.isin(lab, (0, 2)).sum())
+    hd.close()
+
+
 def test_reserve_grows_the_handle_in_place(rpw, gpu_handle_factory, oracle):
     cfg = rpw.PatchworkConfig(filtering_radius=80.0)
     hd = gpu_handle_factory(cfg, 1 << 14, 1)
