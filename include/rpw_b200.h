@@ -205,8 +205,9 @@ int rpw_wait(rpw_handle* h, rpw_stats* stats);
 /* One scan straight from a sensor_msgs/PointCloud2 data buffer (little-endian float32 x, y, z
  * fields at byte offsets off_x/off_y/off_z of every point_step-byte record): the device reads the
  * records in place, so the host-side pcl::fromROSMsg + copy loop of the node
- * (RP/src/recursive_patchwork_node.cpp:67-88) disappears.  The buffer is copied as it is
- * (n_points * point_step bytes). */
+ * (RP/src/recursive_patchwork_node.cpp:67-88) disappears.  The buffer is copied as it is (n_points * point_step
+ * bytes) and the kernels read the fields in place.  (Moving only the 12 xyz bytes of every record with a strided copy
+ * was measured and lost: 0.273 against 0.178 ms for a 120 k-point scan of 32-byte records; RPW_PC2_PACK=1 selects it.) */
 int rpw_segment_pc2(rpw_handle* h, const void* data, size_t n_points, size_t point_step, size_t off_x, size_t off_y, size_t off_z,
                     uint8_t* labels_out, rpw_stats* stats);
 
@@ -264,6 +265,11 @@ int rpw_bev_image(rpw_handle* h, int mode, int width, int height, float x_min, f
  * ground_xyz / nonground_xyz: caller buffers of 3*n floats each (either may be NULL). */
 int rpw_segment_clouds(rpw_handle* h, const float* xyz, size_t n, size_t stride_bytes, uint8_t* labels_out,
                        float* ground_xyz, size_t* n_ground, float* nonground_xyz, size_t* n_nonground);
+/* Same without the last copy: *ground_xyz / *nonground_xyz point into the handle's pinned staging memory (packed xyz,
+ * n_ground / n_nonground records) and stay valid until the next call on this handle.  One synchronisation per call:
+ * input copy, pipeline, result assembly and the copies back are enqueued together.  labels_out may be NULL. */
+int rpw_segment_clouds_view(rpw_handle* h, const float* xyz, size_t n, size_t stride_bytes, uint8_t* labels_out,
+                            const float** ground_xyz, size_t* n_ground, const float** nonground_xyz, size_t* n_nonground);
 
 /* ---- the path, device-resident ----------------------------------------------------------- */
 /* d_points: device pointer to packed float4 (x,y,z,ignored) records of all scans back to back;
@@ -326,6 +332,12 @@ typedef struct rpw_profile {
 } rpw_profile;
 int rpw_profile_enable(rpw_handle* h, int enable); /* also resets the accumulators */
 int rpw_profile_read(rpw_handle* h, rpw_profile* out);
+
+/* Host<->device copy rate of this process on `device`, for bench.py's end-to-end ceiling: `reps` copies of `bytes`
+ * between a pinned host buffer and a device buffer on a private stream, timed with CUDA events (seconds for all of
+ * them in *seconds).  flags: bit 0 = device-to-host instead of host-to-device, bit 1 = write-combined host buffer
+ * (cudaHostAllocWriteCombined).  Ranks that call it at the same time measure what they get from the host together. */
+int rpw_copy_probe(int device, size_t bytes, int reps, int flags, double* seconds);
 
 /* ---- utilities --------------------------------------------------------------------------- */
 void* rpw_host_alloc(size_t bytes); /* pinned host memory (NULL on failure) */

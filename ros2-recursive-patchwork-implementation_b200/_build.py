@@ -73,9 +73,25 @@ def build_scangen(force: bool = False) -> Path:
     return SCANGEN
 
 
+DROPIN_LATENCY = ROOT / "tools" / "_bin" / "dropin_latency"
+
+
+def build_tools(force: bool = False) -> Path:
+    """bench.py's C++ drop-in latency probe (tools/dropin_latency.cpp against host/recursive_patchwork.hpp + the library)."""
+    src = ROOT / "tools" / "dropin_latency.cpp"
+    if not force and _newer(DROPIN_LATENCY, [src, PKG / "host" / "recursive_patchwork.hpp", ROOT / "include" / "rpw_b200.h", LIB]):
+        return DROPIN_LATENCY
+    DROPIN_LATENCY.parent.mkdir(parents=True, exist_ok=True)
+    cxx = shutil.which("g++") or "g++"
+    subprocess.run([cxx, "-O2", "-std=c++17", f"-I{ROOT / 'include'}", f"-I{PKG / 'host'}", str(src), "-o", str(DROPIN_LATENCY),
+                    f"-L{PKG}", "-lrpw_b200", "-Wl,-rpath,$ORIGIN/../../ros2-recursive-patchwork-implementation_b200"], check=True)
+    return DROPIN_LATENCY
+
+
 def build_all(force: bool = False) -> None:
     build_cuda(force)
     build_scangen(force)
+    build_tools(force)
 
 
 if __name__ == "__main__":

@@ -53,8 +53,8 @@ NODE_DTYPE = np.dtype([("scan", "<i4"), ("root", "<i4"), ("depth", "<i4"), ("sta
 # Every symbol include/rpw_b200.h declares (tests check that the library exports all of them).
 EXPORTS = ["rpw_default_config", "rpw_zone_model", "rpw_create", "rpw_destroy", "rpw_set_config", "rpw_get_config", "rpw_reserve", "rpw_capacity",
            "rpw_set_plane_solver", "rpw_set_exact_replay", "rpw_set_stream", "rpw_last_error", "rpw_segment", "rpw_segment_batch", "rpw_segment_batch_async", "rpw_wait",
-           "rpw_segment_pc2", "rpw_segment_fused", "rpw_segment_clouds", "rpw_last_clouds", "rpw_sample_ground_and_obstacles", "rpw_bev_image", "rpw_segment_device", "rpw_debug_keys", "rpw_debug_enable_nodes", "rpw_debug_nodes",
-           "rpw_debug_eig3", "rpw_debug_normal", "rpw_debug_atan2", "rpw_debug_fit_timing", "rpw_debug_fit_trace", "rpw_profile_enable", "rpw_profile_read", "rpw_host_alloc", "rpw_host_free", "rpw_kernel_launches", "rpw_scan_graph", "rpw_abi_version"]
+           "rpw_segment_pc2", "rpw_segment_fused", "rpw_segment_clouds", "rpw_segment_clouds_view", "rpw_last_clouds", "rpw_sample_ground_and_obstacles", "rpw_bev_image", "rpw_segment_device", "rpw_debug_keys", "rpw_debug_enable_nodes", "rpw_debug_nodes",
+           "rpw_debug_eig3", "rpw_debug_normal", "rpw_debug_atan2", "rpw_debug_fit_timing", "rpw_debug_fit_trace", "rpw_profile_enable", "rpw_profile_read", "rpw_copy_probe", "rpw_host_alloc", "rpw_host_free", "rpw_kernel_launches", "rpw_scan_graph", "rpw_abi_version"]
 
 _lib = None
 
@@ -98,6 +98,8 @@ def load_library() -> C.CDLL:
     lib.rpw_segment_fused.restype = C.c_int
     lib.rpw_segment_clouds.argtypes = [vp, vp, sz, sz, vp, vp, C.POINTER(sz), vp, C.POINTER(sz)]
     lib.rpw_segment_clouds.restype = C.c_int
+    lib.rpw_segment_clouds_view.argtypes = [vp, vp, sz, sz, vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), C.POINTER(sz)]
+    lib.rpw_segment_clouds_view.restype = C.c_int
     lib.rpw_last_clouds.argtypes = [vp, vp, vp, C.c_int, C.POINTER(C.c_uint64)]
     lib.rpw_last_clouds.restype = C.c_int
     lib.rpw_sample_ground_and_obstacles.argtypes = [vp, C.c_float, C.c_float, C.c_float, sz, C.c_uint64, vp, sz, C.POINTER(sz), C.POINTER(sz)]
@@ -115,6 +117,7 @@ def load_library() -> C.CDLL:
     lib.rpw_debug_fit_trace.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]; lib.rpw_debug_fit_trace.restype = C.c_int
     lib.rpw_profile_enable.argtypes = [vp, C.c_int]; lib.rpw_profile_enable.restype = C.c_int
     lib.rpw_profile_read.argtypes = [vp, C.POINTER(RpwProfile)]; lib.rpw_profile_read.restype = C.c_int
+    lib.rpw_copy_probe.argtypes = [C.c_int, sz, C.c_int, C.c_int, C.POINTER(C.c_double)]; lib.rpw_copy_probe.restype = C.c_int
     lib.rpw_host_alloc.argtypes = [sz]; lib.rpw_host_alloc.restype = vp
     lib.rpw_host_free.argtypes = [vp]; lib.rpw_host_free.restype = None
     lib.rpw_kernel_launches.argtypes = [vp]; lib.rpw_kernel_launches.restype = C.c_uint64
@@ -137,6 +140,15 @@ def zone_model(cfg: RpwConfig):
     if rc != RPW_OK:
         raise RpwError(rc, "rpw_zone_model")
     return np.array(edges[:], np.float32), np.float32(ang.value)
+
+
+def copy_probe(device: int, nbytes: int, reps: int, d2h: bool = False, write_combined: bool = False) -> float:
+    """GB/s of `reps` pinned host<->device copies of `nbytes` on `device` (rpw_copy_probe)."""
+    sec = C.c_double()
+    rc = load_library().rpw_copy_probe(int(device), int(nbytes), int(reps), (1 if d2h else 0) | (2 if write_combined else 0), C.byref(sec))
+    if rc != RPW_OK:
+        raise RpwError(rc, "rpw_copy_probe")
+    return nbytes * reps / sec.value / 1e9
 
 
 class PinnedArray:

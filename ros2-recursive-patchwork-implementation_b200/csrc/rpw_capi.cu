@@ -60,6 +60,8 @@ struct rpw_handle {
     size_t d_in_bytes = 0;
     size_t h_stage_in_bytes = 0;
     size_t field_off[3] = {0, 4, 8};  // byte offsets of x, y, z inside a record for the next host-path call
+    size_t src_pitch = 0, src_off = 0;  // PointCloud2 with adjacent x, y, z: only those 12 bytes of every src_pitch-byte record are copied
+    int pc2_pack = 0;                   // RPW_PC2_PACK=1 switches the strided copy on: it LOST (0.273 against 0.178 ms per 120 k-point scan of 32-byte records: the copy engine spends ~1.6 ns per 12-byte row)
     uint16_t* d_keys = nullptr;
     uint8_t* d_labels = nullptr;
     float4* d_sortedA = nullptr;
@@ -87,6 +89,7 @@ struct rpw_handle {
     uint32_t* h_scan_counts = nullptr;  // pinned copy
     float* d_cloud_g = nullptr;         // 3 floats x cap_points each, only for host-bound clouds
     float* d_cloud_ng = nullptr;
+    float* h_cloud_stage = nullptr;     // pinned, 3 floats x cap_points: both clouds of a single scan, ground first (rpw_segment_clouds_view)
     uint32_t* d_sample_idx = nullptr;   // rpw_sample_ground_and_obstacles: indices of the ground context sample
     uint32_t* d_bev_owner = nullptr;    // rpw_bev_image: winning draw index per pixel, then the BGR image behind it
     size_t bev_pixels_cap = 0;
@@ -290,6 +293,7 @@ static void free_capacity_buffers(rpw_handle* h) {
     if (h->h_scan_counts) { cudaFreeHost(h->h_scan_counts); h->h_scan_counts = nullptr; }
     cudaFree(h->d_cloud_g); h->d_cloud_g = nullptr;
     cudaFree(h->d_cloud_ng); h->d_cloud_ng = nullptr;
+    if (h->h_cloud_stage) { cudaFreeHost(h->h_cloud_stage); h->h_cloud_stage = nullptr; }
     if (h->h_stage_in) { cudaFreeHost(h->h_stage_in); h->h_stage_in = nullptr; h->h_stage_in_bytes = 0; }
     if (h->h_stage_labels) { cudaFreeHost(h->h_stage_labels); h->h_stage_labels = nullptr; }
     cudaFree(h->d_dbg_nodes); h->d_dbg_nodes = nullptr; h->dbg_cap = 0;
@@ -419,6 +423,7 @@ int rpw_create(const rpw_config* cfg, int device, size_t max_total_points, size_
     TRYC(cudaEventCreateWithFlags(&h->ev_call, cudaEventDisableTiming));
     for (auto& e : h->meta_ev) TRYC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     if (const char* s = getenv("RPW_NO_GRAPH")) h->graphs_enabled = atoi(s) == 0;
+    if (const char* s = getenv("RPW_PC2_PACK")) h->pc2_pack = atoi(s) != 0;
     TRYC(cudaMalloc(&h->d_dbg_count, sizeof(uint32_t)));
     TRYC(cudaMemset(h->d_dbg_count, 0, sizeof(uint32_t)));
     TRY(alloc_capacity_buffers(h));
@@ -901,6 +906,13 @@ int rpw_segment_batch_async(rpw_handle* h, const float* const* clouds, const siz
     if (rc != RPW_OK) return rc;
     // H2D: one copy per run of scans that are contiguous in host memory
     char* d_in = reinterpret_cast<char*>(h->d_in);
+    if (h->src_pitch) {
+        // wide records with adjacent x, y, z (a PointCloud2 buffer): a strided copy moves the 12 xyz bytes of every record
+        // and leaves the rest (intensity, ring, time stamps ...) on the host: 12 instead of point_step bytes per point
+        for (size_t b = 0; b < batch; ++b)
+            if (n[b]) RPW_CUDA(h, cudaMemcpy2DAsync(d_in + off[b] * 12, 12, reinterpret_cast<const char*>(clouds[b]) + h->src_off, h->src_pitch, 12, n[b],
+                                                    cudaMemcpyHostToDevice, h->stream));
+    } else
     for (size_t b = 0; b < batch;) {
         size_t e = b + 1;
         const char* base = reinterpret_cast<const char*>(clouds[b]);
@@ -971,14 +983,20 @@ int rpw_segment_batch(rpw_handle* h, const float* const* clouds, const size_t* n
         std::vector<const float*> src(batch);
         std::vector<uint8_t*> dst(batch);
         size_t o = 0;
+        const size_t pitch = h->src_pitch, poff = h->src_off;
         for (size_t b = 0; b < batch; ++b) {
             char* s = reinterpret_cast<char*>(h->h_stage_in) + o * stride_bytes;
-            if (n[b]) memcpy(s, clouds[b], n[b] * stride_bytes);
+            if (n[b] && pitch) {  // pack the xyz triples while staging
+                const char* from = reinterpret_cast<const char*>(clouds[b]) + poff;
+                for (size_t i = 0; i < n[b]; ++i) memcpy(s + i * 12, from + i * pitch, 12);
+            } else if (n[b]) memcpy(s, clouds[b], n[b] * stride_bytes);
             src[b] = reinterpret_cast<const float*>(s);
             dst[b] = h->h_stage_labels + o;
             o += n[b];
         }
+        h->src_pitch = 0;  // the staged records are packed
         rc = rpw_segment_batch_async(h, src.data(), n, batch, stride_bytes, dst.data());
+        h->src_pitch = pitch;
         if (rc != RPW_OK) return rc;
         RPW_CUDA(h, cudaStreamSynchronize(h->stream));
         for (size_t b = 0; b < batch; ++b) if (n[b]) memcpy(labels_out[b], dst[b], n[b]);
@@ -1006,9 +1024,16 @@ int rpw_segment_pc2(rpw_handle* h, const void* data, size_t n_points, size_t poi
     const size_t offs[3] = {off_x, off_y, off_z};
     for (size_t o : offs)
         if (o % 4 != 0 || o + 4 > point_step) RPW_FAIL(h, RPW_ERR_BAD_ARG, "field offset %zu does not address a float32 inside a %zu-byte record", o, point_step);
-    h->field_off[0] = off_x; h->field_off[1] = off_y; h->field_off[2] = off_z;
-    const int rc = rpw_segment(h, reinterpret_cast<const float*>(data), n_points, point_step, labels_out, stats);
-    h->field_off[0] = 0; h->field_off[1] = 4; h->field_off[2] = 8;
+    int rc;
+    if (h->pc2_pack && off_y == off_x + 4 && off_z == off_x + 8 && point_step > 12) {
+        h->src_pitch = point_step; h->src_off = off_x;
+        rc = rpw_segment(h, reinterpret_cast<const float*>(data), n_points, 12, labels_out, stats);
+        h->src_pitch = 0; h->src_off = 0;
+    } else {
+        h->field_off[0] = off_x; h->field_off[1] = off_y; h->field_off[2] = off_z;
+        rc = rpw_segment(h, reinterpret_cast<const float*>(data), n_points, point_step, labels_out, stats);
+        h->field_off[0] = 0; h->field_off[1] = 4; h->field_off[2] = 8;
+    }
     return rc;
 }
 
@@ -1233,27 +1258,93 @@ int rpw_bev_image(rpw_handle* h, int mode, int width, int height, float x_min, f
     return RPW_OK;
 }
 
-int rpw_segment_clouds(rpw_handle* h, const float* xyz, size_t n, size_t stride_bytes, uint8_t* labels_out,
-                       float* ground_xyz, size_t* n_ground, float* nonground_xyz, size_t* n_nonground) {
+// One scan with both clouds, everything enqueued before the only synchronisation: input copy, the pipeline (its graph),
+// the result-assembly kernels writing both clouds into one buffer (ground first), then labels, counts and the cloud
+// buffer back into pinned staging.  This is what the C++ drop-in's filterGroundPoints costs per ROS2 callback.
+int rpw_segment_clouds_view(rpw_handle* h, const float* xyz, size_t n, size_t stride_bytes, uint8_t* labels_out,
+                            const float** ground_xyz, size_t* n_ground, const float** nonground_xyz, size_t* n_nonground) {
     if (!h) return RPW_ERR_BAD_ARG;
     if (n_ground) *n_ground = 0;
     if (n_nonground) *n_nonground = 0;
+    if (ground_xyz) *ground_xyz = nullptr;
+    if (nonground_xyz) *nonground_xyz = nullptr;
     if (n == 0) return RPW_OK;
-    int rc;
-    if (labels_out) {
-        rc = rpw_segment(h, xyz, n, stride_bytes, labels_out, nullptr);
-    } else {
-        rc = ensure_stage(h, n * stride_bytes);
-        if (rc != RPW_OK) return rc;
-        rc = rpw_segment(h, xyz, n, stride_bytes, h->h_stage_labels, nullptr);
+    if (!xyz) RPW_FAIL(h, RPW_ERR_BAD_ARG, "NULL cloud");
+    if (!stride_ok(stride_bytes)) RPW_FAIL(h, RPW_ERR_BAD_ARG, "stride_bytes must be a multiple of 4 in [12, 1024], got %zu", stride_bytes);
+    if (n > h->cap_points) RPW_FAIL(h, RPW_ERR_CAPACITY, "%zu points exceed the handle's capacity %zu", n, h->cap_points);
+    RPW_CUDA(h, cudaSetDevice(h->device));
+    int rc = ensure_stage(h, n * stride_bytes);
+    if (rc != RPW_OK) return rc;
+    if (!h->d_cmp_cnt) {
+        const size_t rows = h->cap_points / kBinChunk + h->cap_batch + 1;
+        RPW_CUDA(h, cudaMalloc(&h->d_cmp_cnt, rows * 4 * sizeof(uint32_t)));
+        RPW_CUDA(h, cudaMalloc(&h->d_scan_counts, h->cap_batch * 2 * sizeof(uint32_t)));
+        RPW_CUDA(h, cudaMallocHost(&h->h_scan_counts, h->cap_batch * 2 * sizeof(uint32_t)));
     }
+    if (!h->d_cloud_g) {
+        RPW_CUDA(h, cudaMalloc(&h->d_cloud_g, h->cap_points * 3 * sizeof(float)));
+        RPW_CUDA(h, cudaMalloc(&h->d_cloud_ng, h->cap_points * 3 * sizeof(float)));
+    }
+    if (!h->h_cloud_stage) RPW_CUDA(h, cudaMallocHost(&h->h_cloud_stage, h->cap_points * 3 * sizeof(float)));
+    // the staging buffers are about to be rewritten: the previous call's copies must be done (they are, unless the
+    // caller mixed in asynchronous calls)
+    RPW_CUDA(h, cudaStreamSynchronize(h->stream));
+    const uint64_t off[2] = {0, (uint64_t)n};
+    rc = upload_meta(h, off, 1);
     if (rc != RPW_OK) return rc;
-    // cloud assembly in the reference's order (RP/src/recursive_patchwork.cpp:402-419) by the K4 kernels
-    uint64_t counts[2] = {0, 0};
-    rc = rpw_last_clouds(h, ground_xyz, nonground_xyz, 0, counts);
+    rc = reset_dbg(h);
     if (rc != RPW_OK) return rc;
-    if (n_ground) *n_ground = (size_t)counts[0];
-    if (n_nonground) *n_nonground = (size_t)counts[1];
+    rc = ensure_d_in(h, n * stride_bytes);
+    if (rc != RPW_OK) return rc;
+    if (is_pinned(xyz)) {
+        RPW_CUDA(h, cudaMemcpyAsync(h->d_in, xyz, n * stride_bytes, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        // pageable input (the std::vector of the reference's callers): staged through pinned memory in four pieces, the
+        // copy engine moving one piece while the CPU stages the next
+        const size_t bytes = n * stride_bytes, piece = (bytes / 4 + 4095) / 4096 * 4096;
+        for (size_t o = 0; o < bytes; o += piece) {
+            const size_t len = bytes - o < piece ? bytes - o : piece;
+            memcpy(reinterpret_cast<char*>(h->h_stage_in) + o, reinterpret_cast<const char*>(xyz) + o, len);
+            RPW_CUDA(h, cudaMemcpyAsync(reinterpret_cast<char*>(h->d_in) + o, reinterpret_cast<char*>(h->h_stage_in) + o, len, cudaMemcpyHostToDevice, h->stream));
+        }
+    }
+    PointLayout lay;
+    lay.stride = (int)(stride_bytes / 4);
+    lay.ox = (int)(h->field_off[0] / 4); lay.oy = (int)(h->field_off[1] / 4); lay.oz = (int)(h->field_off[2] / 4);
+    lay.vec4 = (stride_bytes == 16 && lay.ox == 0 && lay.oy == 1 && lay.oz == 2) ? 1 : 0;
+    rc = run_pipeline(h, h->d_in, lay, h->d_labels, 1);
+    if (rc != RPW_OK) return rc;
+    const int max_chunks = (int)((n + kBinChunk - 1) / kBinChunk);
+    RPW_CUDA(h, launch_compact(h->stream, lay, h->d_in, h->d_labels, h->d_scan_off, h->d_chunk_base, h->d_cmp_cnt, nullptr,
+                               h->d_cloud_g, h->d_cloud_g, h->d_scan_counts, max_chunks, 1, /*packed*/1));
+    h->launches += 2;
+    uint8_t* lab_dst = labels_out && is_pinned(labels_out) ? labels_out : h->h_stage_labels;
+    if (labels_out) RPW_CUDA(h, cudaMemcpyAsync(lab_dst, h->d_labels, n, cudaMemcpyDeviceToHost, h->stream));
+    RPW_CUDA(h, cudaMemcpyAsync(h->h_scan_counts, h->d_scan_counts, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    RPW_CUDA(h, cudaMemcpyAsync(h->h_cloud_stage, h->d_cloud_g, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    RPW_CUDA(h, cudaStreamSynchronize(h->stream));
+    rc = check_overflow(h);
+    if (rc != RPW_OK) return rc;
+    if (labels_out && lab_dst != labels_out) memcpy(labels_out, lab_dst, n);
+    h->pend_labels.clear();
+    const size_t ng = h->h_scan_counts[0], nn = h->h_scan_counts[1];
+    if (n_ground) *n_ground = ng;
+    if (n_nonground) *n_nonground = nn;
+    if (ground_xyz) *ground_xyz = h->h_cloud_stage;
+    if (nonground_xyz) *nonground_xyz = h->h_cloud_stage + 3 * ng;
+    return RPW_OK;
+}
+
+int rpw_segment_clouds(rpw_handle* h, const float* xyz, size_t n, size_t stride_bytes, uint8_t* labels_out,
+                       float* ground_xyz, size_t* n_ground, float* nonground_xyz, size_t* n_nonground) {
+    const float *g = nullptr, *ng = nullptr;
+    size_t cg = 0, cn = 0;
+    const int rc = rpw_segment_clouds_view(h, xyz, n, stride_bytes, labels_out, &g, &cg, &ng, &cn);
+    if (n_ground) *n_ground = cg;
+    if (n_nonground) *n_nonground = cn;
+    if (rc != RPW_OK) return rc;
+    if (ground_xyz && cg) memcpy(ground_xyz, g, cg * 3 * sizeof(float));
+    if (nonground_xyz && cn) memcpy(nonground_xyz, ng, cn * 3 * sizeof(float));
     return RPW_OK;
 }
 
@@ -1420,6 +1511,34 @@ int rpw_profile_enable(rpw_handle* h, int enable) {
     h->prof_enabled = enable != 0;
     for (int k = 0; k < RPW_PROF_KERNELS; ++k) { h->prof_ms[k] = 0; h->prof_launches[k] = 0; }
     return RPW_OK;
+}
+
+int rpw_copy_probe(int device, size_t bytes, int reps, int flags, double* seconds) {
+    if (!seconds || bytes == 0 || reps <= 0) return RPW_ERR_BAD_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return RPW_ERR_NO_DEVICE;
+    void *hbuf = nullptr, *dbuf = nullptr;
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = RPW_ERR_CUDA;
+    if (cudaHostAlloc(&hbuf, bytes, (flags & 2) ? cudaHostAllocWriteCombined : cudaHostAllocDefault) == cudaSuccess &&
+        cudaMalloc(&dbuf, bytes) == cudaSuccess && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess &&
+        cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess) {
+        memset(hbuf, 1, bytes);
+        const bool d2h = flags & 1;
+        cudaMemcpyAsync(d2h ? hbuf : dbuf, d2h ? dbuf : hbuf, bytes, d2h ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice, st);  // warm-up
+        cudaEventRecord(e0, st);
+        for (int r = 0; r < reps; ++r)
+            cudaMemcpyAsync(d2h ? hbuf : dbuf, d2h ? dbuf : hbuf, bytes, d2h ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice, st);
+        cudaEventRecord(e1, st);
+        float ms = 0.f;
+        if (cudaStreamSynchronize(st) == cudaSuccess && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) { *seconds = ms * 1e-3; rc = RPW_OK; }
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (st) cudaStreamDestroy(st);
+    cudaFree(dbuf);
+    if (hbuf) cudaFreeHost(hbuf);
+    return rc;
 }
 
 int rpw_profile_read(rpw_handle* h, rpw_profile* out) {

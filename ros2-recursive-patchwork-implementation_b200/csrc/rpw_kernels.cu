@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(kBinThreads) rpw_compact_scatter_kernel(const 
                                                                          const uint64_t* __restrict__ scan_off, const uint32_t* __restrict__ chunk_base,
                                                                          const uint32_t* __restrict__ cnt, const FusionTable* __restrict__ fusion,
                                                                          float* __restrict__ ground, float* __restrict__ nonground,
-                                                                         uint32_t* __restrict__ scan_counts) {
+                                                                         uint32_t* __restrict__ scan_counts, int packed) {
     constexpr int kWarps = kBinThreads / 32;
     constexpr int kPerWarp = kBinChunk / kWarps;
     __shared__ uint32_t s_base[5];          // ground, non-ground, beyond bases of this chunk; [3] label-0, [4] label-1 total of the scan
@@ -351,9 +351,12 @@ __global__ void __launch_bounds__(kBinThreads) rpw_compact_scatter_kernel(const 
     // the beyond-radius points (RP/src/recursive_patchwork.cpp:339-341), i.e. ONE cloud in plain input order; label-2
     // points then take their place among the label-0 points instead of following them.
     const bool degen = s_base[3] + s_base[4] < 3u;
-    uint32_t o_ng = s_base[1] + s_warp[warp][0] + (degen ? s_base[2] + s_warp[warp][2] : 0u);
+    // packed: both clouds in ONE buffer, the non-ground cloud right behind the scan's ground cloud (nonground == ground),
+    // so that a single copy of (ground + non-ground) records brings both to the host
+    const uint32_t ng0 = packed ? s_base[4] : 0u;
+    uint32_t o_ng = ng0 + s_base[1] + s_warp[warp][0] + (degen ? s_base[2] + s_warp[warp][2] : 0u);
     uint32_t o_g = s_base[0] + s_warp[warp][1];
-    uint32_t o_by = s_base[3] + s_base[2] + s_warp[warp][2];  // beyond-radius points follow ALL label-0 points of the scan
+    uint32_t o_by = ng0 + s_base[3] + s_base[2] + s_warp[warp][2];  // beyond-radius points follow ALL label-0 points of the scan
     const unsigned lt = (1u << lane) - 1u;
     for (int r = 0; r < kPerWarp / 32; ++r) {
         const uint32_t i = base + warp * kPerWarp + r * 32 + lane;
@@ -582,13 +585,13 @@ cudaError_t launch_scatter(cudaStream_t st, const PointLayout& lay, const float*
 
 cudaError_t launch_compact(cudaStream_t st, const PointLayout& lay, const float* pts, const uint8_t* labels, const uint64_t* scan_off,
                            const uint32_t* chunk_base, uint32_t* cnt, const FusionTable* fusion, float* ground, float* nonground,
-                           uint32_t* scan_counts, int max_chunks, int batch) {
+                           uint32_t* scan_counts, int max_chunks, int batch, int packed) {
     dim3 grid(max_chunks, batch);
     cudaError_t e = cudaMemsetAsync(scan_counts, 0, (size_t)batch * 2 * sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
     rpw_compact_count_kernel<<<grid, kBinThreads, 0, st>>>(labels, scan_off, chunk_base, cnt);
-    if (lay.vec4) rpw_compact_scatter_kernel<true><<<grid, kBinThreads, 0, st>>>(pts, lay, labels, scan_off, chunk_base, cnt, fusion, ground, nonground, scan_counts);
-    else rpw_compact_scatter_kernel<false><<<grid, kBinThreads, 0, st>>>(pts, lay, labels, scan_off, chunk_base, cnt, fusion, ground, nonground, scan_counts);
+    if (lay.vec4) rpw_compact_scatter_kernel<true><<<grid, kBinThreads, 0, st>>>(pts, lay, labels, scan_off, chunk_base, cnt, fusion, ground, nonground, scan_counts, packed);
+    else rpw_compact_scatter_kernel<false><<<grid, kBinThreads, 0, st>>>(pts, lay, labels, scan_off, chunk_base, cnt, fusion, ground, nonground, scan_counts, packed);
     return cudaGetLastError();
 }
 

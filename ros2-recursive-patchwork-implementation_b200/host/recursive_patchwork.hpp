@@ -118,29 +118,14 @@ public:
     // (ground, non-ground) exactly as the reference orders them: ground in input order;
     // non-ground in input order followed by the beyond-radius points in input order.
     std::pair<std::vector<Point3D>, std::vector<Point3D>> filterGroundPoints(const std::vector<Point3D>& points) {
-        std::vector<std::uint8_t> labels;
-        return filterGroundPoints(points, labels);
+        return segmentClouds(points, nullptr);
     }
 
     // Same, also returning one label per input point (RPW_LABEL_*).
     std::pair<std::vector<Point3D>, std::vector<Point3D>> filterGroundPoints(const std::vector<Point3D>& points,
                                                                              std::vector<std::uint8_t>& labels) {
-        std::pair<std::vector<Point3D>, std::vector<Point3D>> out;
-        labels.assign(points.size(), RPW_LABEL_DROPPED);
-        if (points.empty()) return out;  // empty in, two empty clouds out
-        ensure(points.size());
-        // labels and both clouds come from the device: the result assembly of recursive_patchwork.cpp:402-419
-        // (ground in input order; non-ground in input order, then the beyond-radius points) is a stable
-        // compaction kernel, the host only receives the bytes
-        static_assert(sizeof(Point3D) == 3 * sizeof(float), "Point3D must be packed xyz");
-        out.first.resize(points.size());
-        out.second.resize(points.size());
-        std::size_t n_ground = 0, n_non = 0;
-        check(rpw_segment_clouds(handle_, &points[0].x, points.size(), sizeof(Point3D), labels.data(), &out.first[0].x, &n_ground,
-                                 &out.second[0].x, &n_non));
-        out.first.resize(n_ground);
-        out.second.resize(n_non);
-        return out;
+        labels.resize(points.size());
+        return segmentClouds(points, labels.empty() ? nullptr : labels.data());
     }
 
     // Multi-LiDAR frame with the fusion front end on the device (what main.cpp:245-268 does with
@@ -246,6 +231,24 @@ public:
     void reserve(std::size_t max_points) { ensure(max_points); }
 
 private:
+    // labels and both clouds come from the device: the result assembly of recursive_patchwork.cpp:402-419 (ground in
+    // input order; non-ground in input order, then the beyond-radius points) is a stable compaction kernel; the call
+    // hands back views of its pinned staging memory, which become the two vectors (one synchronisation per scan)
+    std::pair<std::vector<Point3D>, std::vector<Point3D>> segmentClouds(const std::vector<Point3D>& points, std::uint8_t* labels) {
+        std::pair<std::vector<Point3D>, std::vector<Point3D>> out;
+        if (points.empty()) return out;  // empty in, two empty clouds out
+        ensure(points.size());
+        static_assert(sizeof(Point3D) == 3 * sizeof(float), "Point3D must be packed xyz");
+        const float *g = nullptr, *ng = nullptr;
+        std::size_t n_ground = 0, n_non = 0;
+        check(rpw_segment_clouds_view(handle_, &points[0].x, points.size(), sizeof(Point3D), labels, &g, &n_ground, &ng, &n_non));
+        const Point3D* gp = reinterpret_cast<const Point3D*>(g);
+        const Point3D* np_ = reinterpret_cast<const Point3D*>(ng);
+        out.first.assign(gp, gp + n_ground);
+        out.second.assign(np_, np_ + n_non);
+        return out;
+    }
+
     PatchworkConfig config_;
     int device_ = 0;
     rpw_handle* handle_ = nullptr;
