@@ -17,6 +17,13 @@
  *                               computeAngles / computePlaneDistances, RP/include/cuda_interface.hpp:73-88)
  *   rpw_zone_model             ring edges + sector angle         RP/src/recursive_patchwork.cpp:344-352
  *
+ * Bit-exactness of the ring/sector keys is against the reference built on glibc <= 2.40 (this image: 2.39; ROS2
+ * Humble / Jazzy targets: 2.35 / 2.39): the device restates that libm's atan2f (the fdlibm float algorithm) operation for
+ * operation.  glibc 2.41 switched atan2f to the correctly rounded CORE-MATH routine; a reference built there computes
+ * different angle bits itself (keys differ only for points within an ulp of a sector edge).  tests/test_oracle.py names
+ * the libm it proved the sequence against.  Limits: num_sectors <= 128 (the reference has no limit; keys are 16-bit and
+ * the scatter keeps per-warp counters per patch), < 2^32 - 65536 points per call, patches < 2^24 points.
+ *
  * There is NO CPU fallback: without a usable CUDA device rpw_create fails with RPW_ERR_NO_DEVICE.
  *
  * Threading: a handle owns one device, one stream and its buffers; it is not re-entrant (one

@@ -4,6 +4,8 @@
 // rpw_create fails, and every entry point reports CUDA errors instead of hiding them.
 #include "rpw_kernels.h"
 
+#include <nvtx3/nvToolsExt.h>  // header-only; ranges cost nothing unless a profiler is attached
+
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -567,10 +569,13 @@ static int prof_fold(rpw_handle* h) {
     return RPW_OK;
 }
 
+static const char* const kProfNames[RPW_PROF_KERNELS] = {"rpw K1 bin", "rpw K1b offsets", "rpw K2 scatter", "rpw K3 fit"};
+
 struct ProfScope {
     rpw_handle* h;
     size_t slot = (size_t)-1;
     ProfScope(rpw_handle* h_, int kind) : h(h_) {
+        nvtxRangePushA(kProfNames[kind]);  // NVTX range around the launch(es) of every stage
         if (!h->prof_enabled) return;
         if (h->prof_used * 2 >= h->prof_ev.size()) {
             if (h->prof_ev.size() >= 2 * 4096) { if (prof_fold(h) != RPW_OK) return; }
@@ -583,7 +588,10 @@ struct ProfScope {
         h->prof_kind[slot] = kind;
         cudaEventRecord(h->prof_ev[2 * slot], h->stream);
     }
-    ~ProfScope() { if (slot != (size_t)-1) cudaEventRecord(h->prof_ev[2 * slot + 1], h->stream); }
+    ~ProfScope() {
+        if (slot != (size_t)-1) cudaEventRecord(h->prof_ev[2 * slot + 1], h->stream);
+        nvtxRangePop();
+    }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -1141,8 +1149,11 @@ int rpw_last_clouds(rpw_handle* h, float* ground_xyz, float* nonground_xyz, int 
     uint64_t max_n = 0;
     for (size_t i = 0; i < batch; ++i) max_n = so[i + 1] - so[i] > max_n ? so[i + 1] - so[i] : max_n;
     const int max_chunks = (int)((max_n + kBinChunk - 1) / kBinChunk);
-    RPW_CUDA(h, launch_compact(h->stream, h->last_lay, h->last_pts, h->last_labels, h->d_scan_off, h->d_chunk_base, h->d_cmp_cnt,
-                               h->last_fused ? h->d_fusion : nullptr, dg, dng, h->d_scan_counts, max_chunks, (int)batch));
+    nvtxRangePushA("rpw K4 result assembly");
+    const cudaError_t ek4 = launch_compact(h->stream, h->last_lay, h->last_pts, h->last_labels, h->d_scan_off, h->d_chunk_base, h->d_cmp_cnt,
+                                           h->last_fused ? h->d_fusion : nullptr, dg, dng, h->d_scan_counts, max_chunks, (int)batch);
+    nvtxRangePop();
+    RPW_CUDA(h, ek4);
     h->launches += 2;
     RPW_CUDA(h, cudaMemcpyAsync(h->h_scan_counts, h->d_scan_counts, batch * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     RPW_CUDA(h, cudaStreamSynchronize(h->stream));
