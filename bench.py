@@ -490,20 +490,18 @@ def main():
     barrier()
     copy_bytes = min(total * 12, 512 << 20)
     reps = 6
+    mix = rpw.capi.copy_probe(local_rank, copy_bytes, reps, both=True)  # the path's own mix: 12 B in + 1 B out per point, both engines
+    barrier()
     h2d = rpw.capi.copy_probe(local_rank, copy_bytes, reps)
     barrier()
     h2d_wc = rpw.capi.copy_probe(local_rank, copy_bytes, reps, write_combined=True)
     barrier()
     d2h = rpw.capi.copy_probe(local_rank, max(1, copy_bytes // 12), reps, d2h=True)
-    copy_rates = gather_ranks([h2d, h2d_wc, d2h])
+    copy_rates = gather_ranks([mix, h2d, h2d_wc, d2h])
     clocks = sampler.stop()
 
-    # the copy engines of one GPU run both directions at once, so the ceiling of a rank is set by the slower of
-    # (12 B/pt in at the host->device rate) and (1 B/pt out at the device->host rate)
-    def ceiling(rates, col):
-        return sum(1.0 / max(POINTS_PER_SCAN * 12 / (r[col] * 1e9), POINTS_PER_SCAN / (r[2] * 1e9)) for r in rates)
-
-    e2e_ceiling = ceiling(copy_rates, 0)
+    # ceiling: every rank moving 12 B per point in and 1 B out at the same time as every other rank, nothing else running
+    e2e_ceiling = sum(r[0] * 1e9 / (POINTS_PER_SCAN * 12) for r in copy_rates)
 
     lat, shapes, pc2 = None, None, None
     if rank == 0:
@@ -600,9 +598,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": total * 12, "d2h_bytes_per_step": total,
                     "api": f"rpw_segment_batch_async + rpw_wait (C-ABI) rolling over {n_handles} handles, pinned host xyz stride 12 in, labels out",
                     "ceiling_scans_per_sec": e2e_ceiling, "frac_of_ceiling": e2e_value / e2e_ceiling if e2e_ceiling else None,
-                    "ceiling_note": "all ranks copying at the same time and nothing else (rpw_copy_probe): per rank min(host->device rate / 12 B, device->host rate / 1 B) per point, summed over ranks",
-                    "copy_gbs_per_rank": {"columns": ["h2d_pinned", "h2d_write_combined", "d2h_pinned"], "rows": copy_rates},
-                    "ceiling_write_combined_scans_per_sec": ceiling(copy_rates, 1),
+                    "ceiling_note": "all ranks copying at the same time and nothing else (rpw_copy_probe): 12 B per point host->device with 1 B per point device->host on the other copy engine, summed over ranks",
+                    "copy_gbs_per_rank": {"columns": ["h2d_with_d2h_mix", "h2d_alone", "h2d_alone_write_combined", "d2h_alone"], "rows": copy_rates},
                     "steps": e2e_steps, "gpu_launches": int(launches_e2e)},
             "e2e_pointcloud2": pc2,
             "single_scan_latency": lat,

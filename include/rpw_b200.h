@@ -343,7 +343,9 @@ int rpw_profile_read(rpw_handle* h, rpw_profile* out);
 /* Host<->device copy rate of this process on `device`, for bench.py's end-to-end ceiling: `reps` copies of `bytes`
  * between a pinned host buffer and a device buffer on a private stream, timed with CUDA events (seconds for all of
  * them in *seconds).  flags: bit 0 = device-to-host instead of host-to-device, bit 1 = write-combined host buffer
- * (cudaHostAllocWriteCombined).  Ranks that call it at the same time measure what they get from the host together. */
+ * (cudaHostAllocWriteCombined), bit 2 = the path's own mix: every host-to-device copy of `bytes` runs together with a
+ * device-to-host copy of bytes / 12 on a second stream (12 B of xyz in, 1 B of label out per point), the time is until both
+ * are done.  Ranks that call it at the same time measure what they get from the host together. */
 int rpw_copy_probe(int device, size_t bytes, int reps, int flags, double* seconds);
 
 /* ---- utilities --------------------------------------------------------------------------- */

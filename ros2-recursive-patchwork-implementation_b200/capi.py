@@ -142,10 +142,11 @@ def zone_model(cfg: RpwConfig):
     return np.array(edges[:], np.float32), np.float32(ang.value)
 
 
-def copy_probe(device: int, nbytes: int, reps: int, d2h: bool = False, write_combined: bool = False) -> float:
-    """GB/s of `reps` pinned host<->device copies of `nbytes` on `device` (rpw_copy_probe)."""
+def copy_probe(device: int, nbytes: int, reps: int, d2h: bool = False, write_combined: bool = False, both: bool = False) -> float:
+    """GB/s of `reps` pinned host<->device copies of `nbytes` on `device` (rpw_copy_probe); both: with nbytes / 12 going back
+    at the same time (the rate is that of the host-to-device bytes)."""
     sec = C.c_double()
-    rc = load_library().rpw_copy_probe(int(device), int(nbytes), int(reps), (1 if d2h else 0) | (2 if write_combined else 0), C.byref(sec))
+    rc = load_library().rpw_copy_probe(int(device), int(nbytes), int(reps), (1 if d2h else 0) | (2 if write_combined else 0) | (4 if both else 0), C.byref(sec))
     if rc != RPW_OK:
         raise RpwError(rc, "rpw_copy_probe")
     return nbytes * reps / sec.value / 1e9

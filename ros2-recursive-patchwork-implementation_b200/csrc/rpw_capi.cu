@@ -1527,28 +1527,39 @@ int rpw_profile_enable(rpw_handle* h, int enable) {
 int rpw_copy_probe(int device, size_t bytes, int reps, int flags, double* seconds) {
     if (!seconds || bytes == 0 || reps <= 0) return RPW_ERR_BAD_ARG;
     if (cudaSetDevice(device) != cudaSuccess) return RPW_ERR_NO_DEVICE;
-    void *hbuf = nullptr, *dbuf = nullptr;
-    cudaStream_t st = nullptr;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const bool d2h = flags & 1, both = flags & 4;
+    const size_t back = both ? (bytes / 12 ? bytes / 12 : 1) : 0;  // labels: one byte back per 12 bytes in
+    void *hbuf = nullptr, *dbuf = nullptr, *hbuf2 = nullptr, *dbuf2 = nullptr;
+    cudaStream_t st = nullptr, st2 = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
     int rc = RPW_ERR_CUDA;
     if (cudaHostAlloc(&hbuf, bytes, (flags & 2) ? cudaHostAllocWriteCombined : cudaHostAllocDefault) == cudaSuccess &&
         cudaMalloc(&dbuf, bytes) == cudaSuccess && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess &&
-        cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess) {
+        cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking) == cudaSuccess &&
+        cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess && cudaEventCreateWithFlags(&e2, cudaEventDisableTiming) == cudaSuccess &&
+        (!both || (cudaHostAlloc(&hbuf2, back, cudaHostAllocDefault) == cudaSuccess && cudaMalloc(&dbuf2, back) == cudaSuccess))) {
         memset(hbuf, 1, bytes);
-        const bool d2h = flags & 1;
         cudaMemcpyAsync(d2h ? hbuf : dbuf, d2h ? dbuf : hbuf, bytes, d2h ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice, st);  // warm-up
+        cudaStreamSynchronize(st);
         cudaEventRecord(e0, st);
-        for (int r = 0; r < reps; ++r)
+        if (both) cudaStreamWaitEvent(st2, e0, 0);
+        for (int r = 0; r < reps; ++r) {
             cudaMemcpyAsync(d2h ? hbuf : dbuf, d2h ? dbuf : hbuf, bytes, d2h ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice, st);
+            if (both) cudaMemcpyAsync(hbuf2, dbuf2, back, cudaMemcpyDeviceToHost, st2);  // the other copy engine, at the same time
+        }
+        if (both) { cudaEventRecord(e2, st2); cudaStreamWaitEvent(st, e2, 0); }
         cudaEventRecord(e1, st);
         float ms = 0.f;
         if (cudaStreamSynchronize(st) == cudaSuccess && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) { *seconds = ms * 1e-3; rc = RPW_OK; }
     }
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
+    if (e2) cudaEventDestroy(e2);
     if (st) cudaStreamDestroy(st);
-    cudaFree(dbuf);
+    if (st2) cudaStreamDestroy(st2);
+    cudaFree(dbuf); cudaFree(dbuf2);
     if (hbuf) cudaFreeHost(hbuf);
+    if (hbuf2) cudaFreeHost(hbuf2);
     return rc;
 }
 
