@@ -56,6 +56,7 @@ struct rpw_handle {
     int fit_blocks = 0;
     int solver = RPW_SOLVER_HYBRID;
     int exact_replay = -1;  // rpw_set_exact_replay
+    int fit_profile = -1;   // class table: -1 by batch size, 0 throughput, 1 latency (RPW_FIT_PROFILE)
 
     // device buffers
     float* d_in = nullptr;       // staged input records of host-path calls
@@ -425,6 +426,7 @@ int rpw_create(const rpw_config* cfg, int device, size_t max_total_points, size_
     TRYC(cudaEventCreateWithFlags(&h->ev_call, cudaEventDisableTiming));
     for (auto& e : h->meta_ev) TRYC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     if (const char* s = getenv("RPW_NO_GRAPH")) h->graphs_enabled = atoi(s) == 0;
+    if (const char* s = getenv("RPW_FIT_PROFILE")) h->fit_profile = atoi(s) < 0 ? -1 : (atoi(s) ? 1 : 0);
     if (const char* s = getenv("RPW_PC2_PACK")) h->pc2_pack = atoi(s) != 0;
     TRYC(cudaMalloc(&h->d_dbg_count, sizeof(uint32_t)));
     TRYC(cudaMemset(h->d_dbg_count, 0, sizeof(uint32_t)));
@@ -646,6 +648,9 @@ static int run_group(rpw_handle* h, rpw_handle::Lane& L, cudaStream_t st, const 
     for (size_t i = b0; i < b0 + nb; ++i) max_n = so[i + 1] - so[i] > max_n ? so[i + 1] - so[i] : max_n;
     if (so[b0 + nb] == so[b0] && !graph_chunks) return RPW_OK;  // nothing but empty scans
     const int max_chunks = graph_chunks ? graph_chunks : (int)((max_n + kBinChunk - 1) / kBinChunk);
+    // class table of the level-0 fit: calls of one or two scans are latency-bound (most SMs stay empty, the call ends with
+    // its longest-iterating patch) and spread big patches over thread-block clusters; the reference-order kernels do not
+    const int profile = h->fp.exact_replay >= 0 ? 0 : (h->fit_profile < 0 ? (nb <= 2 ? 1 : 0) : h->fit_profile);
     StreamSwap swap(h, st);
     // The kernels index scans relative to the pointers they are given.
     const uint64_t* d_so = h->d_scan_off + b0;
@@ -654,7 +659,7 @@ static int run_group(rpw_handle* h, rpw_handle::Lane& L, cudaStream_t st, const 
     { ProfScope ps(h, 0);
       RPW_CUDA(h, launch_bin(st, lay, d_pts, d_so, d_cb, h->zm, h->d_keys, d_labels, h->d_blk_hist, L.d_cls_count, h->fusion_arg, max_chunks, (int)nb)); }
     { ProfScope ps(h, 1);
-      RPW_CUDA(h, launch_offsets(st, d_so, d_cb, h->d_blk_hist, d_ps, L.d_cls_count, L.d_cls_list, h->cls_cap, h->P, (int)nb)); }
+      RPW_CUDA(h, launch_offsets(st, d_so, d_cb, h->d_blk_hist, d_ps, L.d_cls_count, L.d_cls_list, h->cls_cap, h->P, (int)nb, profile)); }
     { ProfScope ps(h, 2);
       RPW_CUDA(h, launch_scatter(st, lay, d_pts, d_so, d_cb, h->d_keys, h->d_blk_hist, d_ps, h->d_sortedA,
                                  h->P, h->fusion_arg, max_chunks, (int)nb)); }
@@ -684,6 +689,7 @@ static int run_group(rpw_handle* h, rpw_handle::Lane& L, cudaStream_t st, const 
     A.n_scans = (int)nb;
     A.P = h->P;
     A.smem_cap = h->smem_cap;
+    A.profile = profile;
     A.scan_base = (uint32_t)b0;
     A.fp = h->fp;
     {
@@ -697,7 +703,7 @@ static int run_group(rpw_handle* h, rpw_handle::Lane& L, cudaStream_t st, const 
         // Too small only makes some blocks take a second patch, too large starts blocks that leave
         // after one load: the estimate never affects results.
         static const char* no_est = getenv("RPW_NO_GRID_ESTIMATE");
-        const ClassBounds cb = fit_class_bounds();
+        const ClassBounds cb = fit_class_bounds(A.profile);
         const uint64_t group_pts = graph_chunks ? (uint64_t)graph_chunks * kBinChunk : so[b0 + nb] - so[b0];
         unsigned grids[kNumFitClasses];
         const uint32_t est_scans = graph_chunks ? 0u : L.h_counts[kClsWords - 1];

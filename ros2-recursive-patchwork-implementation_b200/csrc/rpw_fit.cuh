@@ -7,6 +7,8 @@
 
 #include "rpw_kernels.h"
 
+#include <cooperative_groups.h>
+
 #ifndef RPW_LB128
 #define RPW_LB128 5  // resident blocks per SM the 128-thread fit kernels are compiled for (5 x 40 KB slots fill an SM)
 #endif
@@ -54,8 +56,8 @@ struct FitSmem {
 };
 
 constexpr int kRedMax = 16;
-// FitSmem::misc, in words: [0, 1] radix select, [2..4] heap-select replay, [8..10] plane normal, [16..24] sequential sums
-constexpr int kMiscWords = 32;
+// FitSmem::misc, in words: [0, 1] radix select, [2..4] heap-select replay, [8..10] plane normal, [16..24] sequential sums, [32..79] cluster exchange
+constexpr int kMiscWords = 96;
 constexpr int kCapTiny = 1024;   // points a 64-thread block keeps in shared memory
 constexpr int kCapSmall = 4096;  // points a 128-thread block keeps in shared memory
 constexpr int kCapLarge = 8192;  // largest shared-memory slot (256-thread block); larger patches stream from L2 ...
@@ -228,6 +230,60 @@ __device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v
     return t;
 }
 
+// ---------------------------------------------------------------------------------------------
+// A node spread over the CL thread blocks of a cluster (the single-scan path, where most SMs would otherwise idle and
+// a call ends with its longest-iterating patch): block `rank` keeps the points [lo, lo + nl) of the node in ITS shared
+// memory and runs the same control flow as every other block of the cluster; wherever a block-wide reduction decides
+// something, the blocks' partial results are combined through distributed shared memory in rank order, so every block
+// holds bit-identical totals and takes the same branches.  A pass then costs n / CL points per SM instead of n.
+// CL == 1: a node on one block; everything below compiles away.
+// ---------------------------------------------------------------------------------------------
+namespace cg = cooperative_groups;
+
+template <int CL>
+struct Clu {
+    unsigned rank = 0;
+    uint32_t lo = 0;       // first point of this block's slice
+    float* xch = nullptr;  // [2][16] this block's partial values (two exchanges in flight at most)
+    float* tot = nullptr;  // [16] combined values
+    int xphase = 0;
+    __device__ __forceinline__ bool lead() const { return CL == 1 || rank == 0; }
+};
+
+template <int K, int CL, typename Op>
+__device__ __forceinline__ void cluster_combine(float (&v)[K], Clu<CL>& cc, Op op) {
+    if constexpr (CL > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+        float* my = cc.xch + cc.xphase * 16;
+        cc.xphase ^= 1;
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) my[k] = v[k];
+        }
+        cluster.sync();
+        if (threadIdx.x < K) {
+            float t = cluster.map_shared_rank(my, 0)[threadIdx.x];
+#pragma unroll
+            for (int r = 1; r < CL; ++r) t = op(t, cluster.map_shared_rank(my, r)[threadIdx.x]);  // rank order: the same bits in every block
+            cc.tot[threadIdx.x] = t;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] = cc.tot[k];
+    }
+}
+
+template <int TT, int K, int CL>
+__device__ __forceinline__ void node_sum(float (&v)[K], const FitSmem& S, int& phase, Clu<CL>& cc) {
+    block_sum<TT, K>(v, S.red, phase);
+    cluster_combine<K, CL>(v, cc, [](float a, float b) { return a + b; });
+}
+template <int TT, int K, int CL>
+__device__ __forceinline__ void node_min(float (&v)[K], const FitSmem& S, int& phase, Clu<CL>& cc) {
+    block_min<TT, K>(v, S.red, phase);
+    cluster_combine<K, CL>(v, cc, [](float a, float b) { return fminf(a, b); });
+}
+
 // Point access: shared-memory resident (node fits) or streamed from the L2-resident segment.
 template <bool SMEM>
 struct NodeView {
@@ -249,7 +305,8 @@ struct NodeView {
 
 // k-th smallest (0-based) of one coordinate over the node: exact 4x8-bit radix select.
 // Reference: std::sort + index (RP/src/recursive_patchwork.cpp:156-159, :259-260, :267-268).
-template <int TT, bool SMEM>
+// n: the points this block holds; k: rank over the whole node (CL > 1: the histograms of the cluster's blocks are added).
+template <int TT, bool SMEM, int CL = 1>
 __device__ float radix_select(const NodeView<SMEM>& nv, uint32_t n, int axis, uint32_t k) {
     uint32_t* hist = nv.s.hist;
     uint32_t* misc = nv.s.misc;
@@ -262,6 +319,25 @@ __device__ float radix_select(const NodeView<SMEM>& nv, uint32_t n, int axis, ui
             if ((u & pmask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
         }
         __syncthreads();
+        if constexpr (CL > 1) {
+            cg::cluster_group cluster = cg::this_cluster();
+            cluster.sync();  // every block's histogram is complete
+            uint32_t sum[(256 + TT - 1) / TT];
+#pragma unroll
+            for (int j = 0; j < (256 + TT - 1) / TT; ++j) {
+                const int b = threadIdx.x + j * TT;
+                sum[j] = 0;
+                if (b < 256)
+                    for (int r = 0; r < CL; ++r) sum[j] += cluster.map_shared_rank(hist, r)[b];
+            }
+            cluster.sync();  // every block has read every histogram
+#pragma unroll
+            for (int j = 0; j < (256 + TT - 1) / TT; ++j) {
+                const int b = threadIdx.x + j * TT;
+                if (b < 256) hist[b] = sum[j];
+            }
+            __syncthreads();
+        }
         if (threadIdx.x < 32) {
             // lane l owns bins [8l, 8l+8)
             uint32_t c[8], tot = 0;
@@ -315,10 +391,12 @@ __device__ __forceinline__ void dbg_record(const FitArgs& A, const NodeRef& nd, 
 // :126-129, :138-140).  Slot j of the node labels input point sortedA[start + j].w — the
 // positional read-back of SURVEY Q1.
 template <int TT>
-__device__ __forceinline__ void label_const(const FitArgs& A, const NodeRef& nd, uint8_t v) {
-    for (uint32_t i = threadIdx.x; i < nd.n; i += TT)
-        A.labels[__float_as_uint(A.sortedA[nd.start + i].w)] = v;
+__device__ __forceinline__ void label_const(const FitArgs& A, uint32_t start, uint32_t n, uint8_t v) {
+    for (uint32_t i = threadIdx.x; i < n; i += TT)
+        A.labels[__float_as_uint(A.sortedA[start + i].w)] = v;
 }
+template <int TT>
+__device__ __forceinline__ void label_const(const FitArgs& A, const NodeRef& nd, uint8_t v) { label_const<TT>(A, nd.start, nd.n, v); }
 
 // Strided loop over a node's points, four rows per trip: the loads of a trip are issued together
 // before any of its arithmetic (memory-level parallelism instead of one dependent chain per row).
@@ -630,23 +708,34 @@ static __device__ __noinline__ void exact_refit(const NodeView<SMEM> nv, const u
     out->residual = residual; out->cnt = cnt; out->iters = iters;
 }
 
-template <int TT, bool SMEM, bool EXACT, bool REPLAY>
-__device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth, FitSmem S) {
+// CL > 1: the node is spread over the CL blocks of a cluster (see Clu); this block holds the points [lo, lo + nl).
+// n is the node's size (what the reference's formulas see), nl what this block loops over.
+template <int TT, bool SMEM, bool EXACT, bool REPLAY, int CL = 1>
+__device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth, FitSmem S, Clu<CL> cc = Clu<CL>()) {
+    static_assert(CL == 1 || (SMEM && !REPLAY), "cluster nodes are shared-memory resident and take the default arithmetic");
     const FitParams& fp = A.fp;
     const uint32_t n = nd.n;
     const int tid = threadIdx.x;
     int phase = 0;
     Tick tick(A.timing);
+    uint32_t lo = 0, nl = n;
+    if constexpr (CL > 1) {
+        const uint32_t per = ((n + CL - 1) / CL + 3u) & ~3u;
+        lo = min(n, cc.rank * per);
+        nl = min(n - lo, per);
+        cc.lo = lo;
+    }
+    const bool lead = cc.lead();  // the block that speaks for the node (records, queues, per-node stores)
 
     if (n < 3 || depth > fp.max_split_depth) {  // :111-113
-        label_const<TT>(A, nd, 0);
-        if (tid == 0) dbg_record(A, nd, depth, RPW_NODE_SMALL, 0, 0, -1, 0, 0, 0, 0, 0, 1, FLT_MAX, 0, 0);
+        label_const<TT>(A, nd.start + lo, nl, 0);
+        if (tid == 0 && lead) dbg_record(A, nd, depth, RPW_NODE_SMALL, 0, 0, -1, 0, 0, 0, 0, 0, 1, FLT_MAX, 0, 0);
         return 0;
     }
     NodeView<SMEM> nv;
     nv.s = S;
-    nv.src = (depth == 0 ? A.sortedA : ((depth & 1) ? A.bufB : A.bufC)) + nd.start;
-    nv.gmask = A.gmask + nd.start;
+    nv.src = (depth == 0 ? A.sortedA : ((depth & 1) ? A.bufB : A.bufC)) + nd.start + lo;
+    nv.gmask = A.gmask + nd.start + lo;
 
     // ---- pass 1: load, bounding box, (root only) mean range ------------------------------
     float mm[6] = {FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX};  // min x,y,z, min -x,-y,-z
@@ -670,35 +759,35 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
         // (A bare predicated copy loop followed by a short second loop over shared memory for the bounding box and the
         // range sum -- 550 instructions less code -- measured the same: 1.846 against 1.838 ms per 512 scans.)
         uint32_t i = tid;
-        for (; i + (kWide - 1) * TT < n; i += kWide * TT) {
+        for (; i + (kWide - 1) * TT < nl; i += kWide * TT) {
             float4 v[kWide];
 #pragma unroll
             for (int u = 0; u < kWide; ++u) v[u] = ld_rec(nv.src + i + u * TT);
 #pragma unroll
             for (int u = 0; u < kWide; ++u) take(i + u * TT, v[u]);
         }
-        for (; i + 3 * TT < n; i += 4 * TT) {
+        for (; i + 3 * TT < nl; i += 4 * TT) {
             float4 v[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) v[u] = ld_rec(nv.src + i + u * TT);
 #pragma unroll
             for (int u = 0; u < 4; ++u) take(i + u * TT, v[u]);
         }
-        for (; i < n; i += TT) take(i, ld_rec(nv.src + i));
+        for (; i < nl; i += TT) take(i, ld_rec(nv.src + i));
         sd[1] = ar.ok() ? 0.f : 1.f;
     }
     tick(12);
-    block_min<TT, 6>(mm, S.red, phase);
+    node_min<TT, 6, CL>(mm, S, phase, cc);
     float mean_dist;
     // < 0: off; 0: every fit in the reference's arithmetic order; K > 0: fits of more than K iterations.  A template
     // parameter so that the kernels of the default path do not carry the reference-order code (it cost them 1.8 %)
     const int replay = REPLAY ? fp.exact_replay : -1;
     if (depth == 0) {
-        block_sum<TT, 2>(sd, S.red, phase);
+        node_sum<TT, 2, CL>(sd, S, phase, cc);
         if (sd[1] != 0.f) {  // (never for patch points, whose range is at least 1 m: kept for safety)
             sd[0] = 0.f;
-            for (uint32_t i = tid; i < n; i += TT) sd[0] += range2d(nv.coord(i, 0), nv.coord(i, 1));
-            block_sum<TT, 2>(sd, S.red, phase);
+            for (uint32_t i = tid; i < nl; i += TT) sd[0] += range2d(nv.coord(i, 0), nv.coord(i, 1));
+            node_sum<TT, 2, CL>(sd, S, phase, cc);
         }
         if (replay >= 0) {  // the reference's running sum (:383-387), so that z_th and the distance threshold carry its bits
             float sr[1];
@@ -707,7 +796,7 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
             sd[0] = sr[0];
         }
         mean_dist = sd[0] / (float)n;  // :383-387
-        if (tid == 0) A.root_mean[nd.root] = mean_dist;
+        if (tid == 0 && lead) A.root_mean[nd.root] = mean_dist;
     } else {
         mean_dist = __ldcg(A.root_mean + nd.root);  // Q4: inherited unchanged
     }
@@ -715,13 +804,13 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
     const float x_min = mm[0], x_max = -mm[3], y_min = mm[1], y_max = -mm[4], z_min = mm[2], z_max = -mm[5];
     const float area = (x_max - x_min) * (y_max - y_min);
     if (area < 25.0f && depth > 0) {  // :126-129
-        label_const<TT>(A, nd, 1);
-        if (tid == 0) dbg_record(A, nd, depth, RPW_NODE_AREA, 0, 0, -1, 0, 0, 0, 0, 0, 1, FLT_MAX, 0, mean_dist);
+        label_const<TT>(A, nd.start + lo, nl, 1);
+        if (tid == 0 && lead) dbg_record(A, nd, depth, RPW_NODE_AREA, 0, 0, -1, 0, 0, 0, 0, 0, 1, FLT_MAX, 0, mean_dist);
         return 0;
     }
     if ((z_max - z_min) < 0.05f && n > 10) {  // :138-140
-        label_const<TT>(A, nd, 1);
-        if (tid == 0) dbg_record(A, nd, depth, RPW_NODE_FLAT, 0, 0, -1, 0, 0, 0, 0, 0, 1, FLT_MAX, 0, mean_dist);
+        label_const<TT>(A, nd.start + lo, nl, 1);
+        if (tid == 0 && lead) dbg_record(A, nd, depth, RPW_NODE_FLAT, 0, 0, -1, 0, 0, 0, 0, 0, 1, FLT_MAX, 0, mean_dist);
         return 0;
     }
     // (the barrier inside block_min already made every thread's shared-memory stores visible)
@@ -733,7 +822,7 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
         z_th = fp.sensor_height + 0.2f * rel_dist;
     } else {
         const uint32_t idx = (uint32_t)(0.1f * (float)n);
-        z_th = radix_select<TT, SMEM>(nv, n, 2, idx) + fp.th_seeds;
+        z_th = radix_select<TT, SMEM, CL>(nv, nl, 2, idx) + fp.th_seeds;
     }
     const float tau = fp.th_dist * (1.0f + 0.2f * rel_dist);  // :203
 
@@ -745,7 +834,7 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
     // covariance pass about the centroid.
     const float px = 0.5f * (x_min + x_max), py = 0.5f * (y_min + y_max), pz = z_min;
     float acc[10] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // count, s, S' (xx yx yy zx zy zz)
-    for_points<TT, SMEM, false>(nv, n, [&](uint32_t i, float x, float y, float z, uint8_t) {
+    for_points<TT, SMEM, false>(nv, nl, [&](uint32_t i, float x, float y, float z, uint8_t) {
         const bool m = z < z_th;
         nv.set_mask(i, m ? 1 : 0);
         const float dx = m ? x - px : 0.f, dy = m ? y - py : 0.f, dz = m ? z - pz : 0.f;
@@ -753,35 +842,55 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
         acc[4] = fmaf(dx, dx, acc[4]); acc[5] = fmaf(dy, dx, acc[5]); acc[6] = fmaf(dy, dy, acc[6]);
         acc[7] = fmaf(dz, dx, acc[7]); acc[8] = fmaf(dz, dy, acc[8]); acc[9] = fmaf(dz, dz, acc[9]);
     });
-    block_sum<TT, 10>(acc, S.red, phase);
+    node_sum<TT, 10, CL>(acc, S, phase, cc);
     bool seeds_by_height = true;
     uint32_t chosen[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
     if (acc[0] < 3.f) {
         // the three lowest-z points (std::partial_sort over indices, :173-181).  Parallel pick by
         // (z, index); if z ties reach across the cut the SET libstdc++'s heap-select keeps depends on
         // its heap history, so in that (rare) case one thread replays the heap exactly.
+        // (indices below are positions in the NODE; with a cluster a point of another block is read through
+        // distributed shared memory: rare path, three points or one sequential replay)
+        auto gcoord = [&](uint32_t g, int axis) -> float {
+            if constexpr (CL > 1) {
+                const uint32_t per = ((n + CL - 1) / CL + 3u) & ~3u, r = g / per;
+                float* base = axis == 0 ? S.x : (axis == 1 ? S.y : S.z);
+                return cg::this_cluster().map_shared_rank(base, r)[g - r * per];
+            } else {
+                return nv.coord(g, axis);
+            }
+        };
         for (int r = 0; r < 3; ++r) {
             unsigned long long best = ~0ull;
-            for (uint32_t i = tid; i < n; i += TT) {
-                if (i == chosen[0] || i == chosen[1]) continue;
-                const unsigned long long key = ((unsigned long long)f2ord(nv.coord(i, 2)) << 32) | i;
+            for (uint32_t i = tid; i < nl; i += TT) {
+                const uint32_t g = lo + i;
+                if (g == chosen[0] || g == chosen[1]) continue;
+                const unsigned long long key = ((unsigned long long)f2ord(nv.coord(i, 2)) << 32) | g;
                 best = key < best ? key : best;
             }
             best = block_min_u64<TT>(best, S.red, phase);
+            if constexpr (CL > 1) {  // the smallest key of the cluster
+                cg::cluster_group cluster = cg::this_cluster();
+                unsigned long long* my = reinterpret_cast<unsigned long long*>(cc.xch + cc.xphase * 16);
+                cc.xphase ^= 1;
+                if (tid == 0) my[0] = best;
+                cluster.sync();
+                for (int q = 0; q < CL; ++q) { const unsigned long long o = cluster.map_shared_rank(my, q)[0]; best = o < best ? o : best; }
+            }
             chosen[r] = (uint32_t)(best & 0xFFFFFFFFu);
         }
         {
-            const float v3 = nv.coord(chosen[2], 2);
+            const float v3 = gcoord(chosen[2], 2);
             float ties[1] = {0.f};
-            for (uint32_t i = tid; i < n; i += TT) ties[0] += (nv.coord(i, 2) <= v3) ? 1.f : 0.f;
-            block_sum<TT, 1>(ties, S.red, phase);
+            for (uint32_t i = tid; i < nl; i += TT) ties[0] += (nv.coord(i, 2) <= v3) ? 1.f : 0.f;
+            node_sum<TT, 1, CL>(ties, S, phase, cc);
             if (ties[0] > 3.f) {
                 // replay of std::__heap_select(first, first + 3, last, z[a] < z[b]) on a 3-element heap
                 // (make_heap with one __adjust_heap, then __pop_heap for every later element that is
                 // strictly below the root); same code as oracle/rpw_oracle.c:lowest3
-                if (tid == 0) {
+                if (tid == 0 && lead) {
                     uint32_t hp[3] = {0, 1, 2};
-                    auto zz = [&](uint32_t i) { return nv.coord(i, 2); };
+                    auto zz = [&](uint32_t i) { return gcoord(i, 2); };
                     auto adjust = [&](uint32_t value) {
                         uint32_t hole = 0;
                         uint32_t second = 2;
@@ -796,22 +905,26 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
                         if (zz(i) < zz(hp[0])) adjust(i);
                     S.misc[2] = hp[0]; S.misc[3] = hp[1]; S.misc[4] = hp[2];
                 }
-                __syncthreads();
-                chosen[0] = S.misc[2]; chosen[1] = S.misc[3]; chosen[2] = S.misc[4];
-                __syncthreads();
+                if constexpr (CL > 1) {
+                    cg::cluster_group cluster = cg::this_cluster();
+                    cluster.sync();
+                    const uint32_t* m0 = cluster.map_shared_rank(S.misc, 0);
+                    chosen[0] = m0[2]; chosen[1] = m0[3]; chosen[2] = m0[4];
+                    cluster.sync();
+                } else {
+                    __syncthreads();
+                    chosen[0] = S.misc[2]; chosen[1] = S.misc[3]; chosen[2] = S.misc[4];
+                    __syncthreads();
+                }
             }
         }
         // ascending index so that the 3-term sums follow the reference's order
         if (chosen[0] > chosen[1]) { const uint32_t t = chosen[0]; chosen[0] = chosen[1]; chosen[1] = t; }
         if (chosen[1] > chosen[2]) { const uint32_t t = chosen[1]; chosen[1] = chosen[2]; chosen[2] = t; }
         if (chosen[0] > chosen[1]) { const uint32_t t = chosen[0]; chosen[0] = chosen[1]; chosen[1] = t; }
-        for (uint32_t i = tid; i < n; i += TT) nv.set_mask(i, (i == chosen[0] || i == chosen[1] || i == chosen[2]) ? 1 : 0);
+        for (uint32_t i = tid; i < nl; i += TT) nv.set_mask(i, (lo + i == chosen[0] || lo + i == chosen[1] || lo + i == chosen[2]) ? 1 : 0);
         acc[0] = 3.f; acc[1] = acc[2] = acc[3] = 0.f;
-        for (int r = 0; r < 3; ++r) {
-            float x, y, z;
-            nv.get(chosen[r], x, y, z);
-            acc[1] += x; acc[2] += y; acc[3] += z;
-        }
+        for (int r = 0; r < 3; ++r) { acc[1] += gcoord(chosen[r], 0); acc[2] += gcoord(chosen[r], 1); acc[3] += gcoord(chosen[r], 2); }
         seeds_by_height = false;
     }
 
@@ -840,13 +953,13 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
     auto covariance_pass = [&]() {  // computeCovariance about the centroid (point_cloud_processor.cpp:72-86)
 #pragma unroll
         for (int k = 0; k < 6; ++k) cv[k] = 0.f;
-        for_points<TT, SMEM, true>(nv, n, [&](uint32_t, float x, float y, float z, uint8_t m) {
+        for_points<TT, SMEM, true>(nv, nl, [&](uint32_t, float x, float y, float z, uint8_t m) {
             // masked-out points contribute exact zeros
             const float dx = m ? x - cx : 0.f, dy = m ? y - cy : 0.f, dz = m ? z - cz : 0.f;
             cv[0] = fmaf(dx, dx, cv[0]); cv[1] = fmaf(dy, dx, cv[1]); cv[2] = fmaf(dy, dy, cv[2]);
             cv[3] = fmaf(dz, dx, cv[3]); cv[4] = fmaf(dz, dy, cv[4]); cv[5] = fmaf(dz, dz, cv[5]);
         });
-        block_sum<TT, 6>(cv, S.red, phase);
+        node_sum<TT, 6, CL>(cv, S, phase, cc);
         have_cv = true;
     };
     for (int iter = 0; iter < fp.max_iter; ++iter) {
@@ -859,11 +972,11 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
         // distances, new mask, convergence, residual of the fit just made, moments of the new mask
         float st[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #if RPW_PACKED_PASS
-        const uint32_t done = dist_pass_packed<TT, SMEM>(nv, n, cx, cy, cz, nx, ny, nz, tau, st);
+        const uint32_t done = dist_pass_packed<TT, SMEM>(nv, nl, cx, cy, cz, nx, ny, nz, tau, st);
 #else
         const uint32_t done = 0;
 #endif
-        for_points<TT, SMEM, true>(nv, n, done, [&](uint32_t i, float x, float y, float z, uint8_t om) {
+        for_points<TT, SMEM, true>(nv, nl, done, [&](uint32_t i, float x, float y, float z, uint8_t om) {
             const float dx = x - cx, dy = y - cy, dz = z - cz;
             const float p0 = dx * nx, p1 = dy * ny, p2 = dz * nz;
             const float dist = fabsf(p0 + (p1 + p2));  // Eigen's dot order, see plane_dist
@@ -878,7 +991,7 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
             // against 1.202 ms per 512 scans -- ptxas turns the block into a branch)
         });
         tick(4);
-        block_sum<TT, 12>(st, S.red, phase);
+        node_sum<TT, 12, CL>(st, S, phase, cc);
         tick(13);
         if (st[4] == 0.f) {  // :215 converged: the final fit repeats this one
             residual = st[5] / cnt;
@@ -900,10 +1013,10 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
             if (!have_cv) covariance_pass();
             plane_normal<EXACT, TT>(cv, cnt, bc, nx, ny, nz, fp.hybrid != 0, A.timing);
             float rs[1] = {0.f};
-            for_points<TT, SMEM, true>(nv, n, [&](uint32_t, float x, float y, float z, uint8_t m) {
+            for_points<TT, SMEM, true>(nv, nl, [&](uint32_t, float x, float y, float z, uint8_t m) {
                 rs[0] += m ? plane_dist(x, y, z, cx, cy, cz, nx, ny, nz) : 0.f;
             });
-            block_sum<TT, 1>(rs, S.red, phase);
+            node_sum<TT, 1, CL>(rs, S, phase, cc);
             residual = rs[0] / cnt;
         } else {
             cx = cy = cz = 0.f; nx = ny = 0.f; nz = 1.f; residual = FLT_MAX;  // :78-80
@@ -930,27 +1043,27 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
     if (!(residual > split_threshold && depth < fp.max_split_depth && n >= min_patch)) {
         // leaf: slot j labels input point sortedA[start + j].w (positional read-back, Q1)
         {
-            const float4* rec = A.sortedA + nd.start;
+            const float4* rec = A.sortedA + nd.start + lo;
             constexpr int kWide = TT <= 256 ? RPW_WIDE : 8;
             auto ld_w = [&](const float* p) { return __ldcg(p); };
             uint32_t i = tid;
-            for (; i + (kWide - 1) * TT < n; i += kWide * TT) {
+            for (; i + (kWide - 1) * TT < nl; i += kWide * TT) {
                 uint32_t w[kWide];
 #pragma unroll
                 for (int u = 0; u < kWide; ++u) w[u] = __float_as_uint(ld_w(&rec[i + u * TT].w));
 #pragma unroll
                 for (int u = 0; u < kWide; ++u) A.labels[w[u]] = nv.mask(i + u * TT);
             }
-            for (; i + 3 * TT < n; i += 4 * TT) {
+            for (; i + 3 * TT < nl; i += 4 * TT) {
                 uint32_t w[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) w[u] = __float_as_uint(ld_w(&rec[i + u * TT].w));
 #pragma unroll
                 for (int u = 0; u < 4; ++u) A.labels[w[u]] = nv.mask(i + u * TT);
             }
-            for (; i < n; i += TT) A.labels[__float_as_uint(ld_w(&rec[i].w))] = nv.mask(i);
+            for (; i < nl; i += TT) A.labels[__float_as_uint(ld_w(&rec[i].w))] = nv.mask(i);
         }
-        if (tid == 0) dbg_record(A, nd, depth, RPW_NODE_FIT, iters, n_in, -1, cx, cy, cz, nx, ny, nz, residual, 0, mean_dist);
+        if (tid == 0 && lead) dbg_record(A, nd, depth, RPW_NODE_FIT, iters, n_in, -1, cx, cy, cz, nx, ny, nz, residual, 0, mean_dist);
         tick(6);
         return iters;
     }
@@ -970,29 +1083,29 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
                               });
         if (TT > 32) __syncthreads();  // the histogram area goes back to the radix select
     } else {
-    for (uint32_t i = tid; i < n; i += TT) {
+    for (uint32_t i = tid; i < nl; i += TT) {
         float x, y, z;
         nv.get(i, x, y, z);
         sxy[0] += x; sxy[1] += y;
     }
-    block_sum<TT, 2>(sxy, S.red, phase);
+    node_sum<TT, 2, CL>(sxy, S, phase, cc);
     ccx = sxy[0] / (float)n; ccy = sxy[1] / (float)n;
-    for (uint32_t i = tid; i < n; i += TT) {
+    for (uint32_t i = tid; i < nl; i += TT) {
         float x, y, z;
         nv.get(i, x, y, z);
         const float dx = x - ccx, dy = y - ccy;
         var[0] = fmaf(dx, dx, var[0]); var[1] = fmaf(dy, dy, var[1]);
     }
-    block_sum<TT, 2>(var, S.red, phase);
+    node_sum<TT, 2, CL>(var, S, phase, cc);
     }
     const int axis = (var[0] / (float)n > var[1] / (float)n) ? 0 : 1;  // :250
-    const float median = radix_select<TT, SMEM>(nv, n, axis, n / 2);       // upper median (Q7)
+    const float median = radix_select<TT, SMEM, CL>(nv, nl, axis, n / 2);   // upper median (Q7)
 
-    // stable partition: thread t owns the contiguous run [t*per, (t+1)*per)
-    const uint32_t per = (n + TT - 1) / TT;
-    const uint32_t lo = min(n, (uint32_t)tid * per), hi = min(n, lo + per);
+    // stable partition: thread t owns the contiguous run [t*rper, (t+1)*rper) of this block's points
+    const uint32_t rper = (nl + TT - 1) / TT;
+    const uint32_t rlo = min(nl, (uint32_t)tid * rper), rhi = min(nl, rlo + rper);
     uint32_t nleft = 0;
-    for (uint32_t i = lo; i < hi; ++i) nleft += nv.coord(i, axis) <= median;
+    for (uint32_t i = rlo; i < rhi; ++i) nleft += nv.coord(i, axis) <= median;
     // block exclusive scan of nleft
     uint32_t* wsum = S.hist;  // reuse (256 words)
     const int lane = tid & 31, warp = tid >> 5;
@@ -1012,10 +1125,26 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
         if (w < warp) wbase += v;
         total_left += v;
     }
-    uint32_t lpos = wbase + inc - nleft;  // lefts before my run
-    uint32_t rpos = total_left + (lo - lpos);
+    uint32_t lefts_before_block = 0;
+    if constexpr (CL > 1) {
+        // the blocks of the cluster in rank order: lefts of the blocks before this one, lefts of the whole node
+        cg::cluster_group cluster = cg::this_cluster();
+        uint32_t* my = reinterpret_cast<uint32_t*>(cc.xch + cc.xphase * 16);
+        cc.xphase ^= 1;
+        if (tid == 0) my[0] = total_left;
+        cluster.sync();
+        uint32_t all = 0;
+        for (int q = 0; q < CL; ++q) {
+            const uint32_t v = cluster.map_shared_rank(my, q)[0];
+            if (q < (int)cc.rank) lefts_before_block += v;
+            all += v;
+        }
+        total_left = all;
+    }
+    uint32_t lpos = lefts_before_block + wbase + inc - nleft;  // lefts of the node before my run
+    uint32_t rpos = total_left + (lo + rlo - lpos);             // rights before my run = points before it - lefts before it
     float4* dst = (((depth + 1) & 1) ? A.bufB : A.bufC) + nd.start;
-    for (uint32_t i = lo; i < hi; ++i) {
+    for (uint32_t i = rlo; i < rhi; ++i) {
         float x, y, z;
         nv.get(i, x, y, z);
         const float v = axis == 0 ? x : y;
@@ -1027,15 +1156,15 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
     NodeRef L, R;
     L.start = nd.start; L.n = total_left; L.root = nd.root; L.pad = 0;
     R.start = nd.start + total_left; R.n = n - total_left; R.root = nd.root; R.pad = 0;
-    if (L.n < 3) {
+    if (L.n < 3 && lead) {
         label_const<TT>(A, L, 0);
         if (tid == 0) dbg_record(A, L, depth + 1, RPW_NODE_SMALL, 0, 0, -1, 0, 0, 0, 0, 0, 1, FLT_MAX, 0, 0);
     }
-    if (R.n < 3) {
+    if (R.n < 3 && lead) {
         label_const<TT>(A, R, 0);
         if (tid == 0) dbg_record(A, R, depth + 1, RPW_NODE_SMALL, 0, 0, -1, 0, 0, 0, 0, 0, 1, FLT_MAX, 0, 0);
     }
-    if (tid == 0) {
+    if (tid == 0 && lead) {
         const uint32_t k = (L.n >= 3) + (R.n >= 3);
         if (k) {
             uint32_t slot = atomicAdd(A.q_count + depth + 1, k);
@@ -1108,6 +1237,39 @@ rpw_fit_roots_kernel(FitArgs A, int cls, int cap) {
         if (next >= count) break;
         i = next;
         __syncthreads();  // the next node reuses the shared-memory arrays
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3a, cluster form (calls of one or two scans): one thread-block CLUSTER per listed root patch, the patch's points
+// spread over the shared memory of its CL blocks (see Clu).  A call of a single scan leaves most SMs empty and ends with
+// its longest-iterating patch; an iteration of a big patch is bounded by the pass, which one SM issues at n x ~38
+// instructions / 4 schedulers: CL SMs issue it CL times faster, the serial rest of the iteration (reduction, eigensolve)
+// stays, plus one cluster barrier per reduction.
+// ---------------------------------------------------------------------------------------------
+template <int TT, bool EXACT, int CL>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TT, 1) rpw_fit_cluster_kernel(FitArgs A, int cls, int cap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint4* list = A.cls_list + (size_t)cls * A.cls_cap;
+    const uint32_t count = min(__ldcg(A.cls_count + cls), A.cls_cap);
+    const uint32_t stride = gridDim.x / CL;
+    FitSmem S = carve_smem(smem_raw, cap, TT / 32);
+    Clu<CL> cc;
+    cc.rank = cluster.block_rank();
+    cc.xch = reinterpret_cast<float*>(S.misc + 32);
+    cc.tot = reinterpret_cast<float*>(S.misc + 64);
+    FitArgs Aq = A;  // the per-node timeline is written by the cluster's first block only
+    if (cc.rank != 0) { Aq.trace = nullptr; Aq.timing = nullptr; }
+    for (uint32_t i = blockIdx.x / CL; i < count; i += stride) {  // the same trip count in every block of a cluster
+        const uint4 item = __ldcg(list + i);
+        NodeRef nd;
+        nd.start = item.x; nd.n = item.y; nd.root = item.z; nd.pad = 0;
+        TraceScope trace(Aq, nd.n, 0, cls);
+        const int iters = process_node<TT, true, EXACT, false, CL>(Aq, nd, 0, S, cc);
+        trace.done(iters);
+        if (threadIdx.x == 0 && cc.rank == 0) atomicAdd(A.stats + 1, 1u);
+        cluster.sync();  // nobody reads this block's shared memory any more: the next node may overwrite it
     }
 }
 
@@ -1201,15 +1363,19 @@ __global__ void __launch_bounds__(kFitThreads, kLevelBlocksPerSm) rpw_fit_levels
 // Size classes of the level-0 kernel: (threads, largest patch, shared-memory capacity in points).
 // Finer steps waste less shared memory per resident patch (a 2100-point patch in a 4096-point slot
 // blocks twice the memory it needs for its whole 40 us life), which is what bounds the fit phase.
-struct FitClass { int threads; uint32_t hi; int cap; };
-// (A second, "latency" table for calls of one or two scans -- twice to four times the threads per class, a 1024-thread
-// class keeping patches of up to 16384 points shared-memory resident -- made single scans SLOWER: C2 fit 102 -> 127 us,
-// C5 397 -> 480 us, only C4 596 -> 537 us.  A patch lives on one SM, whose four schedulers issue its pass at the same
-// rate however many warps share the work, and larger blocks pay more for every reduction and barrier of the serial
-// part of an iteration.)
-static const FitClass kFitClasses[kNumFitClasses] = {
-    {RPW_T0, 1024, 1024}, {RPW_T1, 2048, 2048}, {128, 3072, 3072}, {128, 4096, 4096}, {256, 5632, 5632}, {256, kCapLarge, kCapLarge},
-    {RPW_STREAM_THREADS, 0xFFFFFFFFu, kCapStream},
+struct FitClass { int threads; uint32_t hi; int cap; int cluster; };
+// Two tables.  [0] throughput: batches keep every SM full of patches, so a patch gets just enough threads and the
+// smallest shared-memory slot that holds it.  [1] latency (calls of one or two scans, most SMs empty, the call ends with its
+// longest-iterating patch): patches above 4096 points go to thread-block clusters of 4 (<= 8192 points, 2048 per block)
+// or 8 blocks (<= 65536 points, 8192 per block), which issue a pass 4 / 8 times faster than one SM can.
+// (What did NOT work for the latency table: more threads per patch on ONE SM -- twice to four times the threads per class,
+// a 1024-thread class keeping up to 16384 points resident: C2 fit 102 -> 127 us, C5 397 -> 480 us, C4 596 -> 537 us.  One SM's
+// four schedulers issue a pass at the same rate however many warps share it, and larger blocks pay more per barrier.)
+static const FitClass kFitClasses[2][kNumFitClasses] = {
+    {{RPW_T0, 1024, 1024, 1}, {RPW_T1, 2048, 2048, 1}, {128, 3072, 3072, 1}, {128, 4096, 4096, 1}, {256, 5632, 5632, 1},
+     {256, kCapLarge, kCapLarge, 1}, {RPW_STREAM_THREADS, 0xFFFFFFFFu, kCapStream, 1}},
+    {{RPW_T0, 1024, 1024, 1}, {RPW_T1, 2048, 2048, 1}, {128, 3072, 3072, 1}, {128, 4096, 4096, 1}, {256, 8192, 2048, 4},
+     {256, 65536, 8192, 8}, {RPW_STREAM_THREADS, 0xFFFFFFFFu, kCapStream, 1}},
 };
 
 inline size_t fit_smem_bytes_inl(int smem_cap, int threads) {
@@ -1224,7 +1390,8 @@ static cudaError_t set_smem(KernelT k, size_t bytes) {
 template <int TT, bool REPLAY>
 static cudaError_t configure_roots() {
     size_t need = 0;
-    for (const FitClass& c : kFitClasses) if (c.threads == TT) need = fit_smem_bytes_inl(c.cap, TT) > need ? fit_smem_bytes_inl(c.cap, TT) : need;
+    for (const auto& table : kFitClasses)
+        for (const FitClass& c : table) if (c.threads == TT && c.cluster == 1) need = fit_smem_bytes_inl(c.cap, TT) > need ? fit_smem_bytes_inl(c.cap, TT) : need;
     cudaError_t e = set_smem(rpw_fit_roots_kernel<TT, true, REPLAY>, need);
     if (e != cudaSuccess) return e;
     return set_smem(rpw_fit_roots_kernel<TT, false, REPLAY>, need);
@@ -1238,6 +1405,12 @@ static cudaError_t fit_configure_t(int smem_cap, int* blocks_per_sm) {
     if ((e = configure_roots<128, REPLAY>()) != cudaSuccess) return e;
     if ((e = configure_roots<256, REPLAY>()) != cudaSuccess) return e;
     if ((e = configure_roots<RPW_STREAM_THREADS, REPLAY>()) != cudaSuccess) return e;
+    if constexpr (!REPLAY) {
+        if ((e = set_smem(rpw_fit_cluster_kernel<256, true, 4>, fit_smem_bytes_inl(2048, 256))) != cudaSuccess) return e;
+        if ((e = set_smem(rpw_fit_cluster_kernel<256, false, 4>, fit_smem_bytes_inl(2048, 256))) != cudaSuccess) return e;
+        if ((e = set_smem(rpw_fit_cluster_kernel<256, true, 8>, fit_smem_bytes_inl(8192, 256))) != cudaSuccess) return e;
+        if ((e = set_smem(rpw_fit_cluster_kernel<256, false, 8>, fit_smem_bytes_inl(8192, 256))) != cudaSuccess) return e;
+    }
     const size_t smem = fit_smem_bytes_inl(smem_cap, kFitThreads);
     if ((e = set_smem(rpw_fit_levels_kernel<true, REPLAY>, smem)) != cudaSuccess) return e;
     if ((e = set_smem(rpw_fit_levels_kernel<false, REPLAY>, smem)) != cudaSuccess) return e;
@@ -1258,8 +1431,22 @@ static void launch_roots_tt(cudaStream_t st, const FitArgs& args, int cls, int c
 // size class cls in [0, kNumFitClasses): patches with kFitClasses[cls-1].hi < n <= kFitClasses[cls].hi
 template <bool REPLAY>
 static cudaError_t launch_fit_roots_t(cudaStream_t st, const FitArgs& args, int cls, unsigned grid) {
-    const FitClass& c = kFitClasses[cls];
+    const FitClass& c = kFitClasses[(!REPLAY && args.profile) ? 1 : 0][cls];
     if (grid == 0) grid = 1;
+    if constexpr (!REPLAY) {
+        if (c.cluster > 1) {  // one cluster per listed patch
+            const size_t sm = fit_smem_bytes_inl(c.cap, 256);
+            const unsigned g = grid * (unsigned)c.cluster;
+            if (c.cluster == 4) {
+                if (args.fp.exact_eig) rpw_fit_cluster_kernel<256, true, 4><<<g, 256, sm, st>>>(args, cls, c.cap);
+                else rpw_fit_cluster_kernel<256, false, 4><<<g, 256, sm, st>>>(args, cls, c.cap);
+            } else {
+                if (args.fp.exact_eig) rpw_fit_cluster_kernel<256, true, 8><<<g, 256, sm, st>>>(args, cls, c.cap);
+                else rpw_fit_cluster_kernel<256, false, 8><<<g, 256, sm, st>>>(args, cls, c.cap);
+            }
+            return cudaGetLastError();
+        }
+    }
     if (c.threads == RPW_T0) launch_roots_tt<RPW_T0, REPLAY>(st, args, cls, c.cap, grid);
     else if (c.threads == RPW_T1) launch_roots_tt<RPW_T1, REPLAY>(st, args, cls, c.cap, grid);
     else if (c.threads == 128) launch_roots_tt<128, REPLAY>(st, args, cls, c.cap, grid);

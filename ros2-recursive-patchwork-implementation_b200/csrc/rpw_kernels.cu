@@ -567,9 +567,9 @@ cudaError_t launch_bin(cudaStream_t st, const PointLayout& lay, const float* pts
 }
 
 cudaError_t launch_offsets(cudaStream_t st, const uint64_t* scan_off, const uint32_t* chunk_base, uint32_t* blk_hist,
-                           uint32_t* patch_start, uint32_t* cls_count, uint4* cls_list, uint32_t cls_cap, int P, int batch) {
+                           uint32_t* patch_start, uint32_t* cls_count, uint4* cls_list, uint32_t cls_cap, int P, int batch, int profile) {
     rpw_offsets_kernel<<<batch, 256, (size_t)(2 * P) * 4, st>>>(scan_off, chunk_base, blk_hist, patch_start, cls_count, cls_list, cls_cap,
-                                                                fit_class_bounds(), P);
+                                                                fit_class_bounds(profile), P);
     return cudaGetLastError();
 }
 

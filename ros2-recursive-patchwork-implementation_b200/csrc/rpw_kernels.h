@@ -47,6 +47,7 @@ struct FitArgs {
     int n_scans;               // scans in this launch group
     int P;
     int smem_cap;              // points a block can hold in shared memory
+    int profile;               // class table of the level-0 fit: 0 throughput, 1 latency (thread-block clusters for big patches)
     uint32_t scan_base;        // index of the launch group's first scan inside the call's batch (debug records)
     FitParams fp;
 };
@@ -54,7 +55,7 @@ struct FitArgs {
 constexpr int kNumFitClasses = 7;  // size classes of the level-0 fit kernel (rpw_kernels.cu: kFitClasses)
 constexpr int kClsWords = 16;      // words of a class-count array: counts [0, kNumFitClasses), scan count in the last
 struct ClassBounds { uint32_t hi[kNumFitClasses]; };  // class c holds patches with hi[c-1] < n <= hi[c]
-ClassBounds fit_class_bounds();
+ClassBounds fit_class_bounds(int profile);  // 0: throughput table (batches), 1: latency table (one or two scans per call; rpw_fit.cuh)
 size_t fit_smem_bytes(int smem_cap, int threads);
 cudaError_t fit_configure(int smem_cap, int* blocks_per_sm);
 
@@ -62,7 +63,7 @@ cudaError_t launch_bin(cudaStream_t st, const PointLayout& lay, const float* pts
                        const ZoneModel& zm, uint16_t* keys, uint8_t* labels, uint32_t* blk_hist, uint32_t* cls_count,
                        const FusionTable* fusion, int max_chunks, int batch);
 cudaError_t launch_offsets(cudaStream_t st, const uint64_t* scan_off, const uint32_t* chunk_base, uint32_t* blk_hist,
-                           uint32_t* patch_start, uint32_t* cls_count, uint4* cls_list, uint32_t cls_cap, int P, int batch);
+                           uint32_t* patch_start, uint32_t* cls_count, uint4* cls_list, uint32_t cls_cap, int P, int batch, int profile);
 cudaError_t launch_scatter(cudaStream_t st, const PointLayout& lay, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
                            const uint16_t* keys, const uint32_t* blk_hist, const uint32_t* patch_start, float4* sorted,
                            int P, const FusionTable* fusion, int max_chunks, int batch);

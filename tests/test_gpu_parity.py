@@ -150,6 +150,38 @@ def test_exact_replay_of_long_fits(rpw, h, oracle):
         assert replayed >= LABEL_BAR and replayed >= fast
 
 
+@pytest.mark.parametrize("case", ["C2_120k", "C4_300k", "C5_262k_deep", "C5_262k_deep_b", "C1_nonadaptive", "C1_10000_splits"])
+def test_cluster_fit_agrees_with_single_block_fit(case, rpw, built, oracle, monkeypatch):
+    """Calls of one or two scans spread patches above 4096 points over thread-block clusters (distributed shared memory,
+    rpw_fit_cluster_kernel); batches keep a patch on one block.  Same algorithm, the moments summed in another tree order:
+    both forms must meet the bar against the oracle, make the same node decisions (outcome, split axis, median) and agree with
+    each other to the same bar."""
+    cfg, pts = CASES[case](rpw)
+    if case.startswith("C1"):  # small clouds: widen the patches so that some exceed 4096 points
+        cfg.num_sectors = 1
+    o = oracle.run(cfg, pts, want_nodes=True)
+    got = {}
+    for profile in ("0", "1"):
+        monkeypatch.setenv("RPW_FIT_PROFILE", profile)
+        hd = rpw.Handle(cfg.to_c(), 0, len(pts) + 4096, 1)
+        hd.enable_nodes(True)
+        labels = hd.segment(pts)
+        nodes = hd.debug_nodes()
+        hd.enable_nodes(False)
+        again = hd.segment(pts)  # the captured graph
+        assert np.array_equal(again, labels)
+        hd.close()
+        rep = parity.compare_scan(labels, None, o)
+        nrep = parity.compare_nodes(nodes, o["nodes"])
+        print(case, "profile", profile, rep, nrep)
+        assert rep["label_agreement"] >= LABEL_BAR and nrep["max_angle"] <= NORMAL_BAR
+        assert nrep["outcome_mismatch"] <= max(1, nrep["n_shared"] // 100)
+        got[profile] = (labels, nodes)
+    big = got["1"][1][got["1"][1]["n"] > 4096]
+    assert len(big) > 0, "no patch large enough for the cluster kernels in this case"
+    assert (got["0"][0] == got["1"][0]).mean() >= LABEL_BAR
+
+
 def test_deep_recursion_is_exercised(rpw, h, oracle):
     """C5 must actually recurse (demonstrated, not assumed)."""
     cfg, pts = CASES["C5_262k_deep_b"](rpw)
