@@ -575,7 +575,7 @@ struct TraceScope {
 // fixed points (or creeps until max_iter) amplifies into different masks.  Here the sums are taken in the
 // reference's order: NV running sums are NV dependent chains of FADDs, one lane each; the warp's 32 lanes first
 // compute the addends of 32 consecutive points side by side and hand them over through shared memory, so the chain
-// lanes only load and add (about six cycles per point, against ~0.5 for the tree).  Masked-out points contribute
+// lanes only load and add (four to five cycles per point, the latency of a dependent FADD, against ~0.5 for the tree).  Masked-out points contribute
 // +0.0f, which leaves a sum's bits unchanged (a sum that starts at +0 never becomes -0).  Everything else of a plane
 // fit is element-wise and already the reference's operations.  With these sums, the QR eigensolver and the exact
 // medians / percentiles, every decision of fitPlaneAndSplit is taken on the reference's bits.
@@ -590,29 +590,42 @@ __device__ __forceinline__ void seq_sums(const NodeView<SMEM>& nv, uint32_t n, f
     const int lane = threadIdx.x & 31;
     if (TT > 32) __syncthreads();  // scratch and bc may still be read by the previous user
     if (TT == 32 || threadIdx.x < 32) {
-        float acc = 0.f;  // lane k < NV owns sum k
-        for (uint32_t base = 0; base < n; base += 32) {
-            const uint32_t i = base + lane;
+        // Software pipeline over chunks of 32 points, one basic block per chunk so that the compiler can fill the chain's
+        // latency (32 dependent FADDs, 4 cycles each) with the other chunks' work: while chunk c is added, chunk c+1's
+        // addends are computed and stored and chunk c+2's points are loaded.  Every lane runs the chain (lanes >= NV repeat
+        // the last row and are ignored): no divergence.  Chunks past the end store zeros, which are never read.
+        float acc = 0.f;
+        const float4* rowp = reinterpret_cast<const float4*>(scratch + (lane < NV ? lane : NV - 1) * kSeqStride);
+        float x, y, z;
+        uint8_t m;
+        auto fetch = [&](uint32_t base) {
+            const uint32_t i = min(base + (uint32_t)lane, n - 1u);
+            nv.get(i, x, y, z);
+            m = nv.mask(i);
+        };
+        auto put = [&](uint32_t base) {
             float v[NV];
+            produce(base + lane, x, y, z, m, v);
+            const bool live = base + lane < n;
 #pragma unroll
-            for (int k = 0; k < NV; ++k) v[k] = 0.f;
-            if (i < n) {
-                float x, y, z;
-                nv.get(i, x, y, z);
-                produce(i, x, y, z, nv.mask(i), v);
+            for (int k = 0; k < NV; ++k) scratch[k * kSeqStride + lane] = live ? v[k] : 0.f;
+        };
+        fetch(0);
+        put(0);
+        fetch(32);
+        __syncwarp();
+        for (uint32_t base = 0; base < n; base += 32) {
+            float4 t[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) t[q] = rowp[q];
+            __syncwarp();       // every lane holds its row of chunk `base`: the rows can be overwritten
+            put(base + 32);     // addends of the next chunk (its points arrived during the previous chain)
+            fetch(base + 64);   // points of the chunk after that, in flight during this chain
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                acc = __fadd_rn(acc, t[q].x); acc = __fadd_rn(acc, t[q].y); acc = __fadd_rn(acc, t[q].z); acc = __fadd_rn(acc, t[q].w);
             }
-#pragma unroll
-            for (int k = 0; k < NV; ++k) scratch[k * kSeqStride + lane] = v[k];
-            __syncwarp();
-            if (lane < NV) {
-                const float4* p = reinterpret_cast<const float4*>(scratch + lane * kSeqStride);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 t = p[q];
-                    acc = __fadd_rn(acc, t.x); acc = __fadd_rn(acc, t.y); acc = __fadd_rn(acc, t.z); acc = __fadd_rn(acc, t.w);
-                }
-            }
-            __syncwarp();
+            __syncwarp();       // the next chunk's rows are complete
         }
 #pragma unroll
         for (int k = 0; k < NV; ++k) out[k] = __shfl_sync(0xffffffffu, acc, k);
