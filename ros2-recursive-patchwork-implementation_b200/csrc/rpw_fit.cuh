@@ -27,6 +27,15 @@
 #ifndef RPW_T1
 #define RPW_T1 64    // threads of the <= 2048-point class
 #endif
+#ifndef RPW_LT0
+#define RPW_LT0 RPW_T0  // threads of the latency table's classes <= 1024 / <= 2048 / <= 3072 and <= 4096 points
+#endif
+#ifndef RPW_LT1
+#define RPW_LT1 RPW_T1
+#endif
+#ifndef RPW_LT2
+#define RPW_LT2 256  // (128 -> 256 threads for the 2049..4096-point classes of single-scan calls: C2 p50 0.143 -> 0.134 ms)
+#endif
 #ifndef RPW_LB64
 #define RPW_LB64 8  // resident blocks per SM the 64-thread fit kernels are compiled for
 #endif
@@ -1308,6 +1317,8 @@ __device__ __forceinline__ void grid_barrier(uint32_t* ctr, uint32_t target) {
     __syncthreads();
 }
 
+// (A second form for calls of one or two scans -- 256 threads, one block per SM with an 8192-point slot -- changed nothing:
+// C5 single scan 0.408 -> 0.405 ms; the deeper levels of a scan are ~15 us each, mostly the grid barrier and a few short nodes.)
 template <bool EXACT, bool REPLAY>
 __global__ void __launch_bounds__(kFitThreads, kLevelBlocksPerSm) rpw_fit_levels_kernel(FitArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1387,7 +1398,7 @@ struct FitClass { int threads; uint32_t hi; int cap; int cluster; };
 static const FitClass kFitClasses[2][kNumFitClasses] = {
     {{RPW_T0, 1024, 1024, 1}, {RPW_T1, 2048, 2048, 1}, {128, 3072, 3072, 1}, {128, 4096, 4096, 1}, {256, 5632, 5632, 1},
      {256, kCapLarge, kCapLarge, 1}, {RPW_STREAM_THREADS, 0xFFFFFFFFu, kCapStream, 1}},
-    {{RPW_T0, 1024, 1024, 1}, {RPW_T1, 2048, 2048, 1}, {128, 3072, 3072, 1}, {128, 4096, 4096, 1}, {256, 8192, 2048, 4},
+    {{RPW_LT0, 1024, 1024, 1}, {RPW_LT1, 2048, 2048, 1}, {RPW_LT2, 3072, 3072, 1}, {RPW_LT2, 4096, 4096, 1}, {256, 8192, 2048, 4},
      {256, 65536, 8192, 8}, {RPW_STREAM_THREADS, 0xFFFFFFFFu, kCapStream, 1}},
 };
 
