@@ -663,15 +663,16 @@ __device__ __forceinline__ void plane_of_mask_seq(const NodeView<SMEM>& nv, uint
     float* sbc = reinterpret_cast<float*>(S.misc + 16);
     float s3[3];
     seq_sums<TT, SMEM, 3>(nv, n, reinterpret_cast<float*>(S.hist), sbc, s3, [](uint32_t, float x, float y, float z, uint8_t m, float (&v)[3]) {
-        v[0] = m ? x : 0.f; v[1] = m ? y : 0.f; v[2] = m ? z : 0.f;
+        v[0] = (m & 1) ? x : 0.f; v[1] = (m & 1) ? y : 0.f; v[2] = (m & 1) ? z : 0.f;  // (bit 0: the current mask; exact_refit keeps older ones above it)
     });
     cx = s3[0] / cnt; cy = s3[1] / cnt; cz = s3[2] / cnt;  // centroid /= points.size()
     const float ccx = cx, ccy = cy, ccz = cz;
     float cv[6];  // xx yx yy zx zy zz (diff * diff^T is symmetric bit for bit: float products commute)
     seq_sums<TT, SMEM, 6>(nv, n, reinterpret_cast<float*>(S.hist), sbc, cv, [=](uint32_t, float x, float y, float z, uint8_t m, float (&v)[6]) {
         const float d0 = x - ccx, d1 = y - ccy, d2 = z - ccz;
-        v[0] = m ? d0 * d0 : 0.f; v[1] = m ? d1 * d0 : 0.f; v[2] = m ? d1 * d1 : 0.f;
-        v[3] = m ? d2 * d0 : 0.f; v[4] = m ? d2 * d1 : 0.f; v[5] = m ? d2 * d2 : 0.f;
+        const bool in = m & 1;
+        v[0] = in ? d0 * d0 : 0.f; v[1] = in ? d1 * d0 : 0.f; v[2] = in ? d1 * d1 : 0.f;
+        v[3] = in ? d2 * d0 : 0.f; v[4] = in ? d2 * d1 : 0.f; v[5] = in ? d2 * d2 : 0.f;
     });
     plane_normal<true, TT>(cv, cnt, bc, nx, ny, nz, false);  // cov /= (size - 1), Eigen's QR sequence, z-up flip
 }
@@ -695,23 +696,59 @@ static __device__ __noinline__ void exact_refit(const NodeView<SMEM> nv, const u
     float cx = 0.f, cy = 0.f, cz = 0.f, nx = 0.f, ny = 0.f, nz = 1.f;
     bool plane_is_final = false;
     int iters = 0;
+    // In this arithmetic a fit is a pure function of the mask (centroid and covariance are recomputed from the inliers every
+    // time, as in the reference), so the sequence of masks M_0, M_1 = F(M_0), ... is determined by M_0 alone: once a mask
+    // repeats, the rest of the max_iter iterations is known.  The mask byte keeps the last four masks above the current one
+    // (bit j = the mask j iterations ago); a new mask equal to the one p iterations back (p = 2 .. 4) closes a cycle of period
+    // p, and the mask the reference is left with after max_iter iterations is read out of the history instead of being
+    // iterated to.  (Bistable patches: the 100-iteration tails of this mode.)
     for (int iter = 0; iter < max_iter; ++iter) {
         if (cnt < 3.f) break;  // :196
         plane_of_mask_seq<TT, SMEM>(nv, n, cnt, S, cx, cy, cz, nx, ny, nz);
         iters++;
-        float st[2] = {0.f, 0.f};  // new count, changed
+        float st[5] = {0.f, 0.f, 0.f, 0.f, 0.f};  // new count; differs from the current mask, from the masks 1, 2, 3 iterations before it
         for (uint32_t i = tid; i < n; i += TT) {
             float x, y, z;
             nv.get(i, x, y, z);
-            const bool nm = plane_dist(x, y, z, cx, cy, cz, nx, ny, nz) < tau;
-            const bool om = nv.mask(i) != 0;
-            if (nm != om) { st[1] = 1.f; nv.set_mask(i, nm ? 1 : 0); }  // in place: a point's test does not read other masks
+            const uint32_t b = nv.mask(i);
+            const uint32_t nm = plane_dist(x, y, z, cx, cy, cz, nx, ny, nz) < tau ? 1u : 0u;
             st[0] += nm ? 1.f : 0.f;
+            st[1] += (nm != (b & 1u)) ? 1.f : 0.f;
+            st[2] += (nm != ((b >> 1) & 1u)) ? 1.f : 0.f;
+            st[3] += (nm != ((b >> 2) & 1u)) ? 1.f : 0.f;
+            st[4] += (nm != ((b >> 3) & 1u)) ? 1.f : 0.f;
+            nv.set_mask(i, (uint8_t)(nm | ((b << 1) & 0x1Eu)));  // in place: a point's test does not read other masks
         }
-        block_sum<TT, 2>(st, S.red, phase);
+        block_sum<TT, 5>(st, S.red, phase);
+        // (the history now reads: bit 0 = M_{iter+1}, bit 1 = M_iter, bit 2 = M_{iter-1}, ...)
         if (st[1] == 0.f) { plane_is_final = true; break; }  // :215
         cnt = st[0];
+        int period = 0;
+        if (st[2] == 0.f && iter >= 1) period = 2;
+        else if (st[3] == 0.f && iter >= 2) period = 3;
+        else if (st[4] == 0.f && iter >= 3) period = 4;
+        if (period && iter + 1 < max_iter) {
+            // M_{iter+1} == M_{iter+1-period}: from there on the masks repeat with that period.  The reference stops after
+            // max_iter iterations holding M_{max_iter} = the mask at position (max_iter - (iter + 1)) mod period of the cycle
+            // that starts at M_{iter+1-period}, which is bit (period - that position) of the history (position 0: bit 0).
+            const int pos = (max_iter - (iter + 1)) % period;
+            const int bit = pos == 0 ? 0 : period - pos;
+            float c2v[1] = {0.f};
+            for (uint32_t i = tid; i < n; i += TT) {
+                const uint32_t b = nv.mask(i);
+                const uint32_t fm = (b >> bit) & 1u;
+                nv.set_mask(i, (uint8_t)fm);
+                c2v[0] += fm ? 1.f : 0.f;
+            }
+            block_sum<TT, 1>(c2v, S.red, phase);
+            cnt = c2v[0];
+            iters = max_iter;  // what the reference's loop counts
+            break;
+        }
     }
+    // the history bits go: from here on the byte is the mask (the leaf's labels are copied from it)
+    for (uint32_t i = tid; i < n; i += TT) nv.set_mask(i, nv.mask(i) & 1u);
+    if (TT > 32) __syncthreads();
     float residual = FLT_MAX;
     if (cnt >= 3.f) {  // :220-228, fitPlanePCA on the final mask
         if (!plane_is_final) plane_of_mask_seq<TT, SMEM>(nv, n, cnt, S, cx, cy, cz, nx, ny, nz);
@@ -719,7 +756,7 @@ static __device__ __noinline__ void exact_refit(const NodeView<SMEM> nv, const u
         const float fcx = cx, fcy = cy, fcz = cz, fnx = nx, fny = ny, fnz = nz;
         seq_sums<TT, SMEM, 1>(nv, n, reinterpret_cast<float*>(S.hist), reinterpret_cast<float*>(S.misc + 16), rs,
                               [=](uint32_t, float x, float y, float z, uint8_t m, float (&v)[1]) {
-                                  v[0] = m ? plane_dist(x, y, z, fcx, fcy, fcz, fnx, fny, fnz) : 0.f;
+                                  v[0] = (m & 1) ? plane_dist(x, y, z, fcx, fcy, fcz, fnx, fny, fnz) : 0.f;
                               });
         residual = rs[0] / cnt;
     } else {
