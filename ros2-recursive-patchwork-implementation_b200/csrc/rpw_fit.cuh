@@ -769,6 +769,10 @@ static __device__ __noinline__ void exact_refit(const NodeView<SMEM> nv, const u
 
 // CL > 1: the node is spread over the CL blocks of a cluster (see Clu); this block holds the points [lo, lo + nl).
 // n is the node's size (what the reference's formulas see), nl what this block loops over.
+// (Moving the cold paths out of line -- the seed fallback, the split, the radix select and the node record as __noinline__
+// functions, to shorten the instruction stream the resident patches' warps fetch -- made the fit 11 % SLOWER, 1.34 against
+// 1.20 ms per 512 scans: the node view and the shared-memory carve-out they take by reference then live on the stack, and
+// the hot loop pays for it.  Only the QR fallback, which takes scalars, is out of line.)
 template <int TT, bool SMEM, bool EXACT, bool REPLAY, int CL = 1>
 __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth, FitSmem S, Clu<CL> cc = Clu<CL>()) {
     static_assert(CL == 1 || (SMEM && !REPLAY), "cluster nodes are shared-memory resident and take the default arithmetic");
