@@ -53,3 +53,25 @@ def test_label_gather_world_size_2_gloo():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def test_reference_arm_contract_under_torchrun(built):
+    """bench.py --impl reference (the reference's own CPU code on the host cores, no GPU involved) launched the way the
+    driver launches every arm for N > 1: rank 0 alone prints ONE JSON line, the other rank exits 0 without work; the line
+    names the same configuration the repository's arm would name for the same flags."""
+    import json
+    import subprocess
+    port = 29600 + (os.getpid() % 300)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0",
+                        "--scans", "8"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "scans_per_sec" and d["n_gpus"] == 2 and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    sys.path.insert(0, str(ROOT))
+    import bench
+    assert d["config"] == bench.config_dict(8, 2)
