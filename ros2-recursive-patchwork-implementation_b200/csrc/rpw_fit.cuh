@@ -399,10 +399,18 @@ __device__ __forceinline__ void dbg_record(const FitArgs& A, const NodeRef& nd, 
 // Labels of a whole node set to one value (early-outs; RP/src/recursive_patchwork.cpp:111-113,
 // :126-129, :138-140).  Slot j of the node labels input point sortedA[start + j].w — the
 // positional read-back of SURVEY Q1.
+// Input index of patch slot `slot` (positional read-back).
+__device__ __forceinline__ uint32_t slot_input_index(const FitArgs& A, uint32_t slot) {
+#if RPW_GATHER
+    return __ldcg(A.sorted_idx + slot);
+#else
+    return __float_as_uint(__ldcg(&A.sortedA[slot].w));
+#endif
+}
+
 template <int TT>
 __device__ __forceinline__ void label_const(const FitArgs& A, uint32_t start, uint32_t n, uint8_t v) {
-    for (uint32_t i = threadIdx.x; i < n; i += TT)
-        A.labels[__float_as_uint(A.sortedA[start + i].w)] = v;
+    for (uint32_t i = threadIdx.x; i < n; i += TT) A.labels[slot_input_index(A, start + i)] = v;
 }
 template <int TT>
 __device__ __forceinline__ void label_const(const FitArgs& A, const NodeRef& nd, uint8_t v) { label_const<TT>(A, nd.start, nd.n, v); }
@@ -797,7 +805,13 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
     }
     NodeView<SMEM> nv;
     nv.s = S;
+#if RPW_GATHER
+    // depth 0: the points are gathered from the input through the patch's index list; a root too large for shared memory
+    // keeps a packed copy in the even levels' buffer (its own slot range, free until its grandchildren exist) and streams that
+    nv.src = ((depth & 1) ? A.bufB : A.bufC) + nd.start + lo;
+#else
     nv.src = (depth == 0 ? A.sortedA : ((depth & 1) ? A.bufB : A.bufC)) + nd.start + lo;
+#endif
     nv.gmask = A.gmask + nd.start + lo;
 
     // ---- pass 1: load, bounding box, (root only) mean range ------------------------------
@@ -819,6 +833,39 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
         constexpr int kWide = TT <= 256 ? RPW_WIDE : 8;
         // (.ca loads for level 0, so that the leaf's label write would find the input indices in L1: no gain)
         auto ld_rec = [&](const float4* p) { return __ldcg(p); };
+#if RPW_GATHER
+        if (depth == 0) {
+            // gather: the slot's input index, then the record it names.  Packed float4 input: one 16-byte load per point, kWide
+            // index loads and then kWide record loads in flight per thread; other layouts (12-byte AoS, PointCloud2 records):
+            // three scalar loads.  Fused frames are rotated into the vehicle frame here (the same fuse_point as K1).
+            const uint32_t* sidx = A.sorted_idx + nd.start + lo;
+            float4* keep = SMEM ? nullptr : const_cast<float4*>(nv.src);  // streamed roots: the packed copy later passes read
+            auto fetch = [&](uint32_t idx) -> float4 {
+                float4 v;
+                if (A.lay.vec4) {
+                    v = __ldcg(reinterpret_cast<const float4*>(A.pts) + idx);
+                } else {
+                    const float* q = A.pts + (uint64_t)idx * (uint64_t)A.lay.stride;
+                    v.x = __ldcg(q + A.lay.ox); v.y = __ldcg(q + A.lay.oy); v.z = __ldcg(q + A.lay.oz);
+                }
+                if (A.fusion != nullptr) fuse_point(*A.fusion, idx, v.x, v.y);
+                v.w = 0.f;
+                return v;
+            };
+            uint32_t i = tid;
+            for (; i + (kWide - 1) * TT < nl; i += kWide * TT) {
+                uint32_t ix[kWide];
+                float4 v[kWide];
+#pragma unroll
+                for (int u = 0; u < kWide; ++u) ix[u] = __ldcg(sidx + i + u * TT);
+#pragma unroll
+                for (int u = 0; u < kWide; ++u) v[u] = fetch(ix[u]);
+#pragma unroll
+                for (int u = 0; u < kWide; ++u) { take(i + u * TT, v[u]); if (!SMEM) keep[i + u * TT] = v[u]; }
+            }
+            for (; i < nl; i += TT) { const float4 v = fetch(__ldcg(sidx + i)); take(i, v); if (!SMEM) keep[i] = v; }
+        } else {
+#endif
         // (A bare predicated copy loop followed by a short second loop over shared memory for the bounding box and the
         // range sum -- 550 instructions less code -- measured the same: 1.846 against 1.838 ms per 512 scans.)
         uint32_t i = tid;
@@ -837,6 +884,9 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
             for (int u = 0; u < 4; ++u) take(i + u * TT, v[u]);
         }
         for (; i < nl; i += TT) take(i, ld_rec(nv.src + i));
+#if RPW_GATHER
+        }
+#endif
         sd[1] = ar.ok() ? 0.f : 1.f;
     }
     tick(12);
@@ -1106,25 +1156,24 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
     if (!(residual > split_threshold && depth < fp.max_split_depth && n >= min_patch)) {
         // leaf: slot j labels input point sortedA[start + j].w (positional read-back, Q1)
         {
-            const float4* rec = A.sortedA + nd.start + lo;
+            const uint32_t slot0 = nd.start + lo;
             constexpr int kWide = TT <= 256 ? RPW_WIDE : 8;
-            auto ld_w = [&](const float* p) { return __ldcg(p); };
             uint32_t i = tid;
             for (; i + (kWide - 1) * TT < nl; i += kWide * TT) {
                 uint32_t w[kWide];
 #pragma unroll
-                for (int u = 0; u < kWide; ++u) w[u] = __float_as_uint(ld_w(&rec[i + u * TT].w));
+                for (int u = 0; u < kWide; ++u) w[u] = slot_input_index(A, slot0 + i + u * TT);
 #pragma unroll
                 for (int u = 0; u < kWide; ++u) A.labels[w[u]] = nv.mask(i + u * TT);
             }
             for (; i + 3 * TT < nl; i += 4 * TT) {
                 uint32_t w[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) w[u] = __float_as_uint(ld_w(&rec[i + u * TT].w));
+                for (int u = 0; u < 4; ++u) w[u] = slot_input_index(A, slot0 + i + u * TT);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) A.labels[w[u]] = nv.mask(i + u * TT);
             }
-            for (; i < nl; i += TT) A.labels[__float_as_uint(ld_w(&rec[i].w))] = nv.mask(i);
+            for (; i < nl; i += TT) A.labels[slot_input_index(A, slot0 + i)] = nv.mask(i);
         }
         if (tid == 0 && lead) dbg_record(A, nd, depth, RPW_NODE_FIT, iters, n_in, -1, cx, cy, cz, nx, ny, nz, residual, 0, mean_dist);
         tick(6);
