@@ -182,6 +182,32 @@ def test_cluster_fit_agrees_with_single_block_fit(case, rpw, built, oracle, monk
     assert (got["0"][0] == got["1"][0]).mean() >= LABEL_BAR
 
 
+def test_cluster_fit_seed_fallback_and_ties(rpw, built, oracle, monkeypatch):
+    """The rare seed path on a cluster node: a big patch (> 4096 points) with no point below z_th takes its three LOWEST points
+    as seeds (RP/src/recursive_patchwork.cpp:173-181); with ties in z across the cut libstdc++'s heap-select is replayed by one
+    thread, which then reads the other blocks' points through distributed shared memory.  Labels must equal the oracle's in both
+    forms (these slabs are clean planes: no borderline points)."""
+    rng = np.random.default_rng(11)
+    n = 9000
+    ang = rng.uniform(0.05, 0.55, n)            # one sector of ten
+    rad = rng.uniform(18.0, 26.0, n)            # one ring
+    for ties in (False, True):
+        z = 4.0 + 0.02 * rad + rng.normal(0, 0.004, n)   # a tilted slab well above sensor_height + 0.2 * rel
+        if ties:
+            z = np.round(z, 2)                  # many equal heights, also among the lowest
+            z[rng.choice(n, 7, replace=False)] = z.min()
+        pts = np.stack([rad * np.cos(ang), rad * np.sin(ang), z], 1).astype(np.float32)
+        cfg = rpw.PatchworkConfig(filtering_radius=80.0)
+        o = oracle.run(cfg, pts, want_nodes=True)
+        assert o["nodes"]["n"].max() > 4096
+        for profile in ("0", "1"):
+            monkeypatch.setenv("RPW_FIT_PROFILE", profile)
+            hd = rpw.Handle(cfg.to_c(), 0, n + 4096, 1)
+            labels = hd.segment(pts)
+            hd.close()
+            assert np.array_equal(labels, o["labels"]), (ties, profile, int((labels != o["labels"]).sum()))
+
+
 def test_deep_recursion_is_exercised(rpw, h, oracle):
     """C5 must actually recurse (demonstrated, not assumed)."""
     cfg, pts = CASES["C5_262k_deep_b"](rpw)
