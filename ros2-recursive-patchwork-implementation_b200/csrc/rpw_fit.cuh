@@ -42,6 +42,19 @@
 #ifndef RPW_STREAM_THREADS
 #define RPW_STREAM_THREADS 512  // block size of the class whose patches stream from L2 (no shared-memory slot)
 #endif
+#ifndef RPW_STREAM_TMA
+// 1: the streamed class's passes read their records through a ring of TMA bulk copies (cp.async.bulk + mbarrier) instead of
+// per-thread LDG.128.  Built and measured (labels bit-identical), and it LOSES: fit per 64 C4 scans 1.18 ms with plain loads,
+// 1.80 ms with 3 stages x 2048 records, 2.14 ms with 6 x 1024, 2.68 ms with 8 x 512; C5 1.22 -> 1.31; C2 1.185 -> 1.196
+// (profiles/r02_fit_issue_bound.md).  Compiled out.
+#define RPW_STREAM_TMA 0
+#endif
+#ifndef RPW_TMA_ROWS
+#define RPW_TMA_ROWS 4    // records per thread in one ring tile
+#endif
+#ifndef RPW_TMA_STAGES
+#define RPW_TMA_STAGES 3  // ring depth
+#endif
 
 namespace rpw {
 
@@ -62,10 +75,13 @@ struct FitSmem {
     float* red;        // 2 * (TT / 32) * kRedMax floats (ping-pong)
     uint32_t* hist;    // 256
     uint32_t* misc;    // small broadcast area
+    float4* ring;      // streamed class only: RPW_TMA_STAGES tiles of RPW_TMA_ROWS * RPW_STREAM_THREADS records (else nullptr)
+    uint64_t* bar;     // ... and one mbarrier per tile
 };
 
 constexpr int kRedMax = 16;
-// FitSmem::misc, in words: [0, 1] radix select, [2..4] heap-select replay, [8..10] plane normal, [16..24] sequential sums, [32..79] cluster exchange
+// FitSmem::misc, in words: [0, 1] radix select, [2..4] heap-select replay, [8..10] plane normal, [16..24] sequential sums, [32..79] cluster exchange,
+// [80] phase bits of the ring's mbarriers
 constexpr int kMiscWords = 96;
 constexpr int kCapTiny = 1024;   // points a 64-thread block keeps in shared memory
 constexpr int kCapSmall = 4096;  // points a 128-thread block keeps in shared memory
@@ -428,8 +444,91 @@ __device__ __forceinline__ void label_const(const FitArgs& A, const NodeRef& nd,
 #define RPW_WIDE 8
 #endif
 constexpr int kUnroll = RPW_UNROLL;
+
+// ---- streamed nodes: records through a ring of TMA bulk copies --------------------------------------------------------
+// A node too large for a shared-memory slot is re-read from L2 on every pass.  With plain loads each thread has
+// kUnroll 16-byte requests in flight and waits for them before its arithmetic starts.  Here one thread keeps
+// RPW_TMA_STAGES - 1 tiles of RPW_TMA_ROWS * TT records in flight ahead of the tile being consumed (cp.async.bulk,
+// completion counted in bytes on the tile's mbarrier; SASS: UBLKCP + SYNCS), and the block reads a landed tile with one
+// LDS.128 per record.  Point i is still handled by thread i mod TT in ascending order, so every sum is bit-identical to the
+// plain-load path.  The mask bytes stay in global memory (a node's mask range is not 16-byte aligned, which a bulk copy
+// needs); their loads are issued before the wait on the tile.
+// Why it loses: a pass is bound by instruction issue, not by load latency (two resident 512-thread blocks already keep
+// 32 warps x 4 LDG.128 in flight per SM), and LDS.128 replaces LDG.128 one for one, so no instruction is saved; what the
+// ring adds is one block barrier and one mbarrier wait per tile, which put all 16 warps in lockstep with the slowest one
+// where the plain loop lets them run free -- the smaller the tile, the more often.
+constexpr int kRingTile = RPW_TMA_ROWS * RPW_STREAM_THREADS;
+constexpr size_t kRingBytes = RPW_STREAM_TMA ? (size_t)RPW_TMA_STAGES * kRingTile * 16 + 128 + 8 * RPW_TMA_STAGES : 0;
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ring_init(const FitSmem& S) {
+    if (S.ring == nullptr) return;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < RPW_TMA_STAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(S.bar + s)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        S.misc[80] = 0;
+    }
+    __syncthreads();
+}
+template <int TT, bool WITH_MASK, typename F>
+__device__ __forceinline__ void for_points_ring(const float4* src, const uint8_t* gmask, const FitSmem& S, uint32_t n, F body) {
+    constexpr int R = RPW_TMA_ROWS, NS = RPW_TMA_STAGES;
+    constexpr uint32_t TILE = R * TT;
+    const uint32_t tiles = (n + TILE - 1) / TILE;
+    const uint32_t ring0 = smem_addr(S.ring), bar0 = smem_addr(S.bar);
+    __syncthreads();  // the previous call's phase word is written, its last tile read
+    uint32_t ph = S.misc[80];
+    auto issue = [&](uint32_t t) {
+        const uint32_t s = t % NS, rows = min(TILE, n - t * TILE), bar = bar0 + 8 * s;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(rows * 16u) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(ring0 + s * TILE * 16u), "l"(src + (size_t)t * TILE), "r"(rows * 16u), "r"(bar) : "memory");
+    };
+    if (threadIdx.x == 0)
+        for (uint32_t t = 0; t < tiles && t < (uint32_t)NS; ++t) issue(t);
+    uint32_t s = 0;
+    for (uint32_t t = 0; t < tiles; ++t) {
+        const uint32_t base = t * TILE + threadIdx.x;
+        const bool full = (t + 1) * TILE <= n;
+        uint8_t m[R];
+#pragma unroll
+        for (int u = 0; u < R; ++u) m[u] = (WITH_MASK && (full || base + u * TT < n)) ? gmask[base + u * TT] : (uint8_t)1;
+        const uint32_t bar = bar0 + 8 * s, parity = (ph >> s) & 1u;
+        uint32_t ok;
+        do {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        } while (!ok);
+        ph ^= 1u << s;
+        const float4* tile = S.ring + s * TILE + threadIdx.x;
+        float4 v[R];
+#pragma unroll
+        for (int u = 0; u < R; ++u) v[u] = tile[u * TT];
+        if (full) {
+#pragma unroll
+            for (int u = 0; u < R; ++u) body(base + u * TT, v[u].x, v[u].y, v[u].z, m[u]);
+        } else {
+#pragma unroll
+            for (int u = 0; u < R; ++u)
+                if (base + u * TT < n) body(base + u * TT, v[u].x, v[u].y, v[u].z, m[u]);
+        }
+        __syncthreads();  // the tile is consumed: its stage may be refilled
+        if (threadIdx.x == 0 && t + NS < tiles) issue(t + NS);
+        s = (s + 1 == (uint32_t)NS) ? 0u : s + 1;
+    }
+    if (threadIdx.x == 0) S.misc[80] = ph;
+}
+
 template <int TT, bool SMEM, bool WITH_MASK, typename F>
 __device__ __forceinline__ void for_points(const NodeView<SMEM>& nv, uint32_t n, uint32_t first, F body) {
+#if RPW_STREAM_TMA
+    if constexpr (!SMEM && TT == RPW_STREAM_THREADS) {
+        if (first == 0 && nv.s.ring != nullptr) {  // (block-uniform)
+            for_points_ring<TT, WITH_MASK>(nv.src, nv.gmask, nv.s, n, body);
+            return;
+        }
+    }
+#endif
     uint32_t i = first + threadIdx.x;
     for (; i + (kUnroll - 1) * TT < n; i += kUnroll * TT) {
         float x[kUnroll], y[kUnroll], z[kUnroll];
@@ -1294,7 +1393,7 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
     return iters;
 }
 
-__device__ __forceinline__ FitSmem carve_smem(unsigned char* raw, int cap, int warps) {
+__device__ __forceinline__ FitSmem carve_smem(unsigned char* raw, int cap, int warps, bool with_ring = false) {
     FitSmem S;
     S.x = reinterpret_cast<float*>(raw);
     S.y = S.x + cap;
@@ -1303,6 +1402,12 @@ __device__ __forceinline__ FitSmem carve_smem(unsigned char* raw, int cap, int w
     S.hist = reinterpret_cast<uint32_t*>(S.red + 2 * warps * kRedMax);
     S.misc = S.hist + 256;
     S.m = reinterpret_cast<uint8_t*>(S.misc + kMiscWords);
+    S.ring = nullptr; S.bar = nullptr;
+    if (with_ring) {
+        const uintptr_t at = (reinterpret_cast<uintptr_t>(S.m) + (size_t)cap + 127) & ~(uintptr_t)127;
+        S.ring = reinterpret_cast<float4*>(at);
+        S.bar = reinterpret_cast<uint64_t*>(S.ring + (size_t)RPW_TMA_STAGES * kRingTile);
+    }
     return S;
 }
 
@@ -1334,7 +1439,9 @@ rpw_fit_roots_kernel(FitArgs A, int cls, int cap) {
     uint4 item = __ldcg(list + (i < A.cls_cap ? i : 0));
     const uint32_t count = min(__ldcg(A.cls_count + cls), A.cls_cap);
     if (i >= count) return;
-    FitSmem S = carve_smem(smem_raw, cap, TT / 32);
+    constexpr bool kRing = RPW_STREAM_TMA && TT == RPW_STREAM_THREADS;
+    FitSmem S = carve_smem(smem_raw, cap, TT / 32, kRing && cap == kCapStream);
+    if constexpr (kRing) ring_init(S);
     for (;;) {
         NodeRef nd;
         nd.start = item.x; nd.n = item.y; nd.root = item.z; nd.pad = 0;
@@ -1495,6 +1602,10 @@ static const FitClass kFitClasses[2][kNumFitClasses] = {
 inline size_t fit_smem_bytes_inl(int smem_cap, int threads) {
     return (size_t)smem_cap * 13 + (2 * (threads / 32) * kRedMax + 256 + kMiscWords) * 4 + 16;
 }
+// the streamed class of the roots kernel also carries the TMA ring
+inline size_t roots_smem_bytes(int cap, int threads) {
+    return fit_smem_bytes_inl(cap, threads) + ((threads == RPW_STREAM_THREADS && cap == kCapStream) ? kRingBytes : 0);
+}
 
 template <typename KernelT>
 static cudaError_t set_smem(KernelT k, size_t bytes) {
@@ -1505,7 +1616,7 @@ template <int TT, bool REPLAY>
 static cudaError_t configure_roots() {
     size_t need = 0;
     for (const auto& table : kFitClasses)
-        for (const FitClass& c : table) if (c.threads == TT && c.cluster == 1) need = fit_smem_bytes_inl(c.cap, TT) > need ? fit_smem_bytes_inl(c.cap, TT) : need;
+        for (const FitClass& c : table) if (c.threads == TT && c.cluster == 1) need = roots_smem_bytes(c.cap, TT) > need ? roots_smem_bytes(c.cap, TT) : need;
     cudaError_t e = set_smem(rpw_fit_roots_kernel<TT, true, REPLAY>, need);
     if (e != cudaSuccess) return e;
     return set_smem(rpw_fit_roots_kernel<TT, false, REPLAY>, need);
@@ -1537,7 +1648,7 @@ static cudaError_t fit_configure_t(int smem_cap, int* blocks_per_sm) {
 
 template <int TT, bool REPLAY>
 static void launch_roots_tt(cudaStream_t st, const FitArgs& args, int cls, int cap, unsigned grid) {
-    const size_t sm = fit_smem_bytes_inl(cap, TT);
+    const size_t sm = roots_smem_bytes(cap, TT);
     if (args.fp.exact_eig) rpw_fit_roots_kernel<TT, true, REPLAY><<<grid, TT, sm, st>>>(args, cls, cap);
     else rpw_fit_roots_kernel<TT, false, REPLAY><<<grid, TT, sm, st>>>(args, cls, cap);
 }

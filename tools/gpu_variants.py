@@ -2,7 +2,7 @@
 (built into ros2-recursive-patchwork-implementation_b200/_variants/ with different -D flags) and prints a checksum
 of the labels, which must not depend on the variant.
 
-    python tools/gpu_variants.py [scans] name1 name2 ...      (names of _variants/*.so; 'default' = the shipped library)
+    python tools/gpu_variants.py [C2|C4|C5] [scans] name1 name2 ...   (names of _variants/*.so; 'default' = the shipped library)
 """
 import hashlib, importlib, os, subprocess, sys, tempfile
 from concurrent.futures import ThreadPoolExecutor
@@ -18,7 +18,7 @@ def child(path, B):
     data = np.load(path)
     pts, off = data["pts"], data["off"]
     total = int(off[-1])
-    h = rpw.Handle(rpw.PatchworkConfig(filtering_radius=80.0).to_c(), 0, total, B)
+    h = rpw.Handle(rpw.synth.config_for(os.environ.get("RPW_VARIANT_SHAPE", "C2")).to_c(), 0, total, B)
     st = torch.cuda.Stream(); torch.cuda.set_stream(st); h.set_stream(st.cuda_stream)
     d = torch.from_numpy(pts).cuda(); lab = torch.empty(total, dtype=torch.uint8, device="cuda")
     for _ in range(5): h.segment_device(d.data_ptr(), off, lab.data_ptr())
@@ -52,11 +52,15 @@ if __name__ == "__main__":
         child(sys.argv[2], int(sys.argv[3]))
         sys.exit(0)
     args = sys.argv[1:]
-    B = 512
+    shape = args.pop(0) if args and args[0] in ("C2", "C4", "C5") else "C2"
+    os.environ["RPW_VARIANT_SHAPE"] = shape
+    B = 512 if shape == "C2" else 64
     if args and args[0].isdigit(): B = int(args.pop(0))
     rpw = importlib.import_module("ros2-recursive-patchwork-implementation_b200")
+    gen = {"C2": lambda s: rpw.synth.spinning_scan(1000 + s), "C4": lambda s: rpw.synth.solidstate_merged(2000 + s),
+           "C5": lambda s: rpw.synth.dense_urban_scan(3000 + s)}[shape]
     with ThreadPoolExecutor(16) as ex:
-        scans = list(ex.map(lambda s: rpw.synth.spinning_scan(s), range(1000, 1000 + B)))
+        scans = list(ex.map(gen, range(B)))
     off = np.zeros(B + 1, np.uint64); off[1:] = np.cumsum([len(s) for s in scans])
     path = os.path.join(tempfile.gettempdir(), "rpw_variant_batch.npz")
     np.savez(path, pts=np.concatenate(scans), off=off)
