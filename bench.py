@@ -477,6 +477,10 @@ def main():
         per_scan.index_add_(0, scan_of, diff_ref.double())
         worst_scan_vs_ref = float((1.0 - per_scan / torch.tensor(n_pts, dtype=torch.float64, device=dev)).min().item())
         del scan_of
+    n_sample = min(8, B)  # kept for the cpu_baseline leg: the strict reference build checks these scans' labels in this run
+    sample_pts = int(sum(n_pts[:n_sample]))
+    sample_labels_ref_mode = labels_ref[:sample_pts].cpu().numpy()
+    sample_labels_timed = d_labels[:sample_pts].cpu().numpy()
     del labels_qr, labels_ref, diff_ref
     parity_counts = gather_ranks([float(n_diff_vs_ref), float(total), worst_scan_vs_ref])
 
@@ -554,6 +558,8 @@ def main():
                 if not args.no_cpu_baseline:
                     v, kind, sample = cpu_reference_throughput(sc[:16], pc, max(4.0, args.cpu_seconds / 3), ncpu, what="this shape's seeds")
                     entry["cpu_baseline"] = {"value": v, "unit": "scans/s", "cores": ncpu, "kind": kind, "sample": sample}
+                    v1, _, sample1 = cpu_reference_throughput(sc[:16], pc, 1.5, 1, what="this shape's seeds")
+                    entry["cpu_baseline"]["one_core"] = {"value": v1, "unit": "scans/s", "sample": sample1}
                 shapes[name] = entry
 
     if rank == 0:
@@ -618,6 +624,20 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             v, kind, sample = cpu_reference_throughput(scans[:16], cfg, args.cpu_seconds, os.cpu_count() or 1)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": kind, "sample": sample}
+            v1, _, sample1 = cpu_reference_throughput(scans[:16], cfg, 3.0, 1)  # one core next to all cores
+            out["cpu_baseline"]["one_core"] = {"value": v1, "unit": UNIT, "mpoints_per_sec": v1 * POINTS_PER_SCAN / 1e6, "sample": sample1}
+            out["cpu_baseline"]["mpoints_per_sec"] = v * POINTS_PER_SCAN / 1e6
+            # the same leg doubles as the checker: the reference's strict-IEEE build labels the first scans of the batch
+            sys.path.insert(0, str(ROOT / "tests"))
+            import oracle_lib
+            strict = oracle_lib.try_reference("strict")
+            if strict is not None:
+                runs = [strict.run(oracle_lib.to_cfg(cfg), a) for a in scans[:n_sample]]
+                ref_labels = np.concatenate([r["labels"] for r in runs])
+                out["cpu_baseline"]["parity_sample"] = {
+                    "scans": n_sample, "points": int(len(ref_labels)), "bit_equal_duplicate_points": int(sum(r["ambiguous"] for r in runs)),
+                    "labels_differing_reference_order_mode_vs_libref_strict": int((ref_labels != sample_labels_ref_mode).sum()),
+                    "labels_differing_timed_solver_vs_libref_strict": int((ref_labels != sample_labels_timed).sum())}
         emit(out)
     h.close()
     if world > 1:
