@@ -67,6 +67,12 @@ def test_reference_binaries_link_the_product_library(built):
         syms = subprocess.run(["nm", "-C", str(exe)], capture_output=True, text=True).stdout
         # the reference's own segmentation translation unit is NOT in the binary: no host fitPlaneAndSplit to fall back to
         assert "fitPlaneAndSplit" not in syms and "U rpw_segment_clouds" in syms
+        # ... and is not stale: every rpw_* symbol it needs is one the library in the tree exports
+        need = {ln.split()[-1] for ln in subprocess.run(["nm", "-D", "--undefined-only", str(exe)], capture_output=True, text=True).stdout.splitlines()
+                if ln.split() and ln.split()[-1].startswith("rpw_")}
+        have = {ln.split()[-1] for ln in subprocess.run(["nm", "-D", "--defined-only", str(ROOT / "ros2-recursive-patchwork-implementation_b200" / "librpw_b200.so")],
+                                                        capture_output=True, text=True).stdout.splitlines() if ln.split()}
+        assert need and need <= have, sorted(need - have)
 
 
 def test_reference_test_binary_fails_loudly_without_a_gpu(built):
