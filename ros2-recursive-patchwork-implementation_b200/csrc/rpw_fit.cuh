@@ -1514,6 +1514,12 @@ __device__ __forceinline__ void grid_barrier(uint32_t* ctr, uint32_t target) {
     __syncthreads();
 }
 
+// (Fitting the children inside the block that split the parent -- depth first, a small stack in shared memory, no queue, no
+// level kernel work for the few splits of a C2 batch -- was built three ways, labels identical each time.  One call site with
+// a run-time depth: the roots' own fits slow down 5 % (the depth-0 specialisation is lost), net C2 1.830 -> 1.843 ms per 512
+// scans, C5 1.470 -> 1.379 per 64, C4 1.486 -> 1.713 (two halves of a 20 k-point patch are better off on two SMs).  A second
+// inlined call site for the children: C2 2.197.  The children out of line behind a __grid_constant__ parameter, resident
+// parents only: C2 1.817, C4 1.437 -> 1.472, C5 1.471 -> 1.466.  Nothing worth its code; the queue stays.)
 // (A second form for calls of one or two scans -- 256 threads, one block per SM with an 8192-point slot -- changed nothing:
 // C5 single scan 0.408 -> 0.405 ms; the deeper levels of a scan are ~15 us each, mostly the grid barrier and a few short nodes.)
 template <bool EXACT, bool REPLAY>
