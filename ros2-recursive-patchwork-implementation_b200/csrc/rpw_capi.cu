@@ -67,8 +67,7 @@ struct rpw_handle {
     int pc2_pack = 0;                   // RPW_PC2_PACK=1 switches the strided copy on: it LOST (0.273 against 0.178 ms per 120 k-point scan of 32-byte records: the copy engine spends ~1.6 ns per 12-byte row)
     uint16_t* d_keys = nullptr;
     uint8_t* d_labels = nullptr;
-    float4* d_sortedA = nullptr;       // (RPW_GATHER=0 builds only)
-    uint32_t* d_sorted_idx = nullptr;  // input index of every patch slot, patch-major, input order inside a patch
+    float4* d_sortedA = nullptr;       // the patches: (x, y, z, bits of the input index), patch-major, input order inside a patch
     float4* d_bufB = nullptr;
     float4* d_bufC = nullptr;
     uint8_t* d_gmask = nullptr;
@@ -279,7 +278,6 @@ static void free_capacity_buffers(rpw_handle* h) {
     cudaFree(h->d_keys); h->d_keys = nullptr;
     cudaFree(h->d_labels); h->d_labels = nullptr;
     cudaFree(h->d_sortedA); h->d_sortedA = nullptr;
-    cudaFree(h->d_sorted_idx); h->d_sorted_idx = nullptr;
     cudaFree(h->d_bufB); h->d_bufB = nullptr;
     cudaFree(h->d_bufC); h->d_bufC = nullptr;
     cudaFree(h->d_gmask); h->d_gmask = nullptr;
@@ -311,11 +309,7 @@ static int alloc_capacity_buffers(rpw_handle* h) {
     h->d_in_bytes = N * 16;
     RPW_ALLOC(cudaMalloc(&h->d_keys, N * sizeof(uint16_t)));
     RPW_ALLOC(cudaMalloc(&h->d_labels, N));
-#if RPW_GATHER
-    RPW_ALLOC(cudaMalloc(&h->d_sorted_idx, N * sizeof(uint32_t)));
-#else
     RPW_ALLOC(cudaMalloc(&h->d_sortedA, N * sizeof(float4)));
-#endif
     RPW_ALLOC(cudaMalloc(&h->d_bufB, N * sizeof(float4)));
     RPW_ALLOC(cudaMalloc(&h->d_bufC, N * sizeof(float4)));
     RPW_ALLOC(cudaMalloc(&h->d_gmask, N));
@@ -667,10 +661,10 @@ static int run_group(rpw_handle* h, rpw_handle::Lane& L, cudaStream_t st, const 
     { ProfScope ps(h, 1);
       RPW_CUDA(h, launch_offsets(st, d_so, d_cb, h->d_blk_hist, d_ps, L.d_cls_count, L.d_cls_list, h->cls_cap, h->P, (int)nb, profile)); }
     { ProfScope ps(h, 2);
-      RPW_CUDA(h, launch_scatter(st, lay, d_pts, d_so, d_cb, h->d_keys, h->d_blk_hist, d_ps, h->d_sortedA, h->d_sorted_idx,
+      RPW_CUDA(h, launch_scatter(st, lay, d_pts, d_so, d_cb, h->d_keys, h->d_blk_hist, d_ps, h->d_sortedA,
                                  h->P, h->fusion_arg, max_chunks, (int)nb)); }
     FitArgs A;
-    A.sortedA = h->d_sortedA; A.sorted_idx = h->d_sorted_idx; A.pts = d_pts; A.lay = lay; A.fusion = h->fusion_arg;
+    A.sortedA = h->d_sortedA;
     A.bufB = h->d_bufB; A.bufC = h->d_bufC; A.gmask = h->d_gmask;
     A.labels = d_labels;
     A.patch_start = d_ps;

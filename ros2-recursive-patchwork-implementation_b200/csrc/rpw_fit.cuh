@@ -417,11 +417,7 @@ __device__ __forceinline__ void dbg_record(const FitArgs& A, const NodeRef& nd, 
 // positional read-back of SURVEY Q1.
 // Input index of patch slot `slot` (positional read-back).
 __device__ __forceinline__ uint32_t slot_input_index(const FitArgs& A, uint32_t slot) {
-#if RPW_GATHER
-    return __ldcg(A.sorted_idx + slot);
-#else
     return __float_as_uint(__ldcg(&A.sortedA[slot].w));
-#endif
 }
 
 template <int TT>
@@ -552,64 +548,13 @@ __device__ __forceinline__ void for_points(const NodeView<SMEM>& nv, uint32_t n,
     for_points<TT, SMEM, WITH_MASK>(nv, n, 0u, body);
 }
 
-// The distance / mask / moments pass of the plane-fit loop on Blackwell's packed FP32 instructions (FADD2, FMUL2,
-// FFMA2: two IEEE single-precision operations per instruction, each rounded exactly like the scalar form).  A thread
-// takes its rows two at a time, one row per half of every register pair; the halves keep separate running sums that
-// are added at the end.  Covers the rows [0, 4 * TT * floor(n / (4 * TT))) and returns that bound; the caller's
-// scalar loop finishes the rest and adds into the same totals.  15 floating-point instructions per point instead of
-// 24 -- and measured 0.7 % SLOWER end to end (1.897 against 1.884 ms per 512 scans, labels identical): the packed
-// instructions occupy the FMA pipe for two cycles, so the pass, which is not bound by issue slots, gains nothing.
-// Compiled out by default (RPW_PACKED_PASS=1 builds it).
-#ifndef RPW_PACKED_PASS
-#define RPW_PACKED_PASS 0
-#endif
-#if RPW_PACKED_PASS
-template <int TT, bool SMEM>
-__device__ __forceinline__ uint32_t dist_pass_packed(const NodeView<SMEM>& nv, uint32_t n, float cx, float cy, float cz, float nx, float ny,
-                                                     float nz, float tau, float (&st)[12]) {
-    const float2 ncx = make_float2(-cx, -cx), ncy = make_float2(-cy, -cy), ncz = make_float2(-cz, -cz);
-    const float2 nx2 = make_float2(nx, nx), ny2 = make_float2(ny, ny), nz2 = make_float2(nz, nz);
-    float2 a[12];
-#pragma unroll
-    for (int k = 0; k < 12; ++k) a[k] = make_float2(0.f, 0.f);
-    bool changed = false;
-    const uint32_t bound = (n / (4u * TT)) * (4u * TT);
-    for (uint32_t i = threadIdx.x; i < bound; i += 4 * TT) {
-        float x[4], y[4], z[4];
-        uint8_t m[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            nv.get(i + u * TT, x[u], y[u], z[u]);
-            m[u] = nv.mask(i + u * TT);
-        }
-#pragma unroll
-        for (int p = 0; p < 4; p += 2) {
-            const float2 dx = __fadd2_rn(make_float2(x[p], x[p + 1]), ncx);
-            const float2 dy = __fadd2_rn(make_float2(y[p], y[p + 1]), ncy);
-            const float2 dz = __fadd2_rn(make_float2(z[p], z[p + 1]), ncz);
-            const float2 p0 = __fmul2_rn(dx, nx2), p1 = __fmul2_rn(dy, ny2), p2 = __fmul2_rn(dz, nz2);
-            // Eigen's dot order p0 + (p1 + p2), see plane_dist.  Scalar additions on purpose: ptxas (12.9) contracts
-            // mul.rn.f32x2 followed by add.rn.f32x2 into FFMA2 even under -fmad=false, which would round the distance
-            // differently from the reference; it leaves packed products feeding scalar additions alone.
-            const float da = fabsf(__fadd_rn(p0.x, __fadd_rn(p1.x, p2.x))), db = fabsf(__fadd_rn(p0.y, __fadd_rn(p1.y, p2.y)));
-            const bool na = da < tau, nb = db < tau;
-            const float2 w = make_float2(na ? 1.f : 0.f, nb ? 1.f : 0.f);
-            a[5] = __fadd2_rn(a[5], make_float2(m[p] ? da : 0.f, m[p + 1] ? db : 0.f));
-            if (na != (m[p] != 0)) { changed = true; nv.set_mask(i + p * TT, na ? 1 : 0); }
-            if (nb != (m[p + 1] != 0)) { changed = true; nv.set_mask(i + (p + 1) * TT, nb ? 1 : 0); }
-            // masked-out rows contribute exact zeros (d * 0)
-            const float2 ex = __fmul2_rn(dx, w), ey = __fmul2_rn(dy, w), ez = __fmul2_rn(dz, w);
-            a[0] = __fadd2_rn(a[0], w); a[1] = __fadd2_rn(a[1], ex); a[2] = __fadd2_rn(a[2], ey); a[3] = __fadd2_rn(a[3], ez);
-            a[6] = __ffma2_rn(ex, ex, a[6]); a[7] = __ffma2_rn(ey, ex, a[7]); a[8] = __ffma2_rn(ey, ey, a[8]);
-            a[9] = __ffma2_rn(ez, ex, a[9]); a[10] = __ffma2_rn(ez, ey, a[10]); a[11] = __ffma2_rn(ez, ez, a[11]);
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 12; ++k) st[k] = a[k].x + a[k].y;
-    st[4] = changed ? 1.f : 0.f;
-    return bound;
-}
-#endif
+// (Experiment, measured and not adopted, code removed: the distance / mask / moments pass on Blackwell's packed FP32
+// instructions -- FADD2, FMUL2, FFMA2, two IEEE single-precision operations per instruction, each rounded exactly like the
+// scalar form; a thread takes its rows two at a time, one per half of every register pair.  15 floating-point instructions
+// per point instead of 24, and 0.7 % SLOWER end to end, 1.897 against 1.884 ms per 512 scans, labels identical: the packed
+// instructions occupy the FMA pipe for two cycles.  One trap for whoever retries it: ptxas 12.9 contracts mul.rn.f32x2
+// followed by add.rn.f32x2 into FFMA2 even under -fmad=false, which rounds the distance differently from the reference;
+// packed products feeding SCALAR additions are left alone.)
 
 // Optional cycle accounting (rpw_debug_fit_timing): thread 0 of every block adds the cycles it spent
 // in each section of process_node to A.timing[section].  Sections: 0 load+bbox, 1 seeds, 2 covariance
@@ -904,13 +849,7 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
     }
     NodeView<SMEM> nv;
     nv.s = S;
-#if RPW_GATHER
-    // depth 0: the points are gathered from the input through the patch's index list; a root too large for shared memory
-    // keeps a packed copy in the even levels' buffer (its own slot range, free until its grandchildren exist) and streams that
-    nv.src = ((depth & 1) ? A.bufB : A.bufC) + nd.start + lo;
-#else
     nv.src = (depth == 0 ? A.sortedA : ((depth & 1) ? A.bufB : A.bufC)) + nd.start + lo;
-#endif
     nv.gmask = A.gmask + nd.start + lo;
 
     // ---- pass 1: load, bounding box, (root only) mean range ------------------------------
@@ -932,39 +871,6 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
         constexpr int kWide = TT <= 256 ? RPW_WIDE : 8;
         // (.ca loads for level 0, so that the leaf's label write would find the input indices in L1: no gain)
         auto ld_rec = [&](const float4* p) { return __ldcg(p); };
-#if RPW_GATHER
-        if (depth == 0) {
-            // gather: the slot's input index, then the record it names.  Packed float4 input: one 16-byte load per point, kWide
-            // index loads and then kWide record loads in flight per thread; other layouts (12-byte AoS, PointCloud2 records):
-            // three scalar loads.  Fused frames are rotated into the vehicle frame here (the same fuse_point as K1).
-            const uint32_t* sidx = A.sorted_idx + nd.start + lo;
-            float4* keep = SMEM ? nullptr : const_cast<float4*>(nv.src);  // streamed roots: the packed copy later passes read
-            auto fetch = [&](uint32_t idx) -> float4 {
-                float4 v;
-                if (A.lay.vec4) {
-                    v = __ldcg(reinterpret_cast<const float4*>(A.pts) + idx);
-                } else {
-                    const float* q = A.pts + (uint64_t)idx * (uint64_t)A.lay.stride;
-                    v.x = __ldcg(q + A.lay.ox); v.y = __ldcg(q + A.lay.oy); v.z = __ldcg(q + A.lay.oz);
-                }
-                if (A.fusion != nullptr) fuse_point(*A.fusion, idx, v.x, v.y);
-                v.w = 0.f;
-                return v;
-            };
-            uint32_t i = tid;
-            for (; i + (kWide - 1) * TT < nl; i += kWide * TT) {
-                uint32_t ix[kWide];
-                float4 v[kWide];
-#pragma unroll
-                for (int u = 0; u < kWide; ++u) ix[u] = __ldcg(sidx + i + u * TT);
-#pragma unroll
-                for (int u = 0; u < kWide; ++u) v[u] = fetch(ix[u]);
-#pragma unroll
-                for (int u = 0; u < kWide; ++u) { take(i + u * TT, v[u]); if (!SMEM) keep[i + u * TT] = v[u]; }
-            }
-            for (; i < nl; i += TT) { const float4 v = fetch(__ldcg(sidx + i)); take(i, v); if (!SMEM) keep[i] = v; }
-        } else {
-#endif
         // (A bare predicated copy loop followed by a short second loop over shared memory for the bounding box and the
         // range sum -- 550 instructions less code -- measured the same: 1.846 against 1.838 ms per 512 scans.)
         uint32_t i = tid;
@@ -983,9 +889,6 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
             for (int u = 0; u < 4; ++u) take(i + u * TT, v[u]);
         }
         for (; i < nl; i += TT) take(i, ld_rec(nv.src + i));
-#if RPW_GATHER
-        }
-#endif
         sd[1] = ar.ok() ? 0.f : 1.f;
     }
     tick(12);
@@ -1183,12 +1086,7 @@ __device__ int process_node(const FitArgs& A, const NodeRef nd, const int depth,
         tick(3);
         // distances, new mask, convergence, residual of the fit just made, moments of the new mask
         float st[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#if RPW_PACKED_PASS
-        const uint32_t done = dist_pass_packed<TT, SMEM>(nv, nl, cx, cy, cz, nx, ny, nz, tau, st);
-#else
-        const uint32_t done = 0;
-#endif
-        for_points<TT, SMEM, true>(nv, nl, done, [&](uint32_t i, float x, float y, float z, uint8_t om) {
+        for_points<TT, SMEM, true>(nv, nl, [&](uint32_t i, float x, float y, float z, uint8_t om) {
             const float dx = x - cx, dy = y - cy, dz = z - cz;
             const float p0 = dx * nx, p1 = dy * ny, p2 = dz * nz;
             const float dist = fabsf(p0 + (p1 + p2));  // Eigen's dot order, see plane_dist

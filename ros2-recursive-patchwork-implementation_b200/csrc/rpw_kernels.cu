@@ -177,8 +177,7 @@ template <bool VEC4>
 __global__ void __launch_bounds__(kBinThreads) rpw_scatter_kernel(const float* __restrict__ pts, PointLayout lay, const uint64_t* __restrict__ scan_off,
                                                                  const uint32_t* __restrict__ chunk_base,
                                                                  const uint16_t* __restrict__ keys, const uint32_t* __restrict__ blk_hist,
-                                                                 const uint32_t* __restrict__ patch_start, float4* __restrict__ sorted,
-                                                                 uint32_t* __restrict__ sorted_idx, int P, const FusionTable* __restrict__ fusion) {
+                                                                 const uint32_t* __restrict__ patch_start, float4* __restrict__ sorted, int P, const FusionTable* __restrict__ fusion) {
     extern __shared__ uint32_t s_off[];  // [warps][P]
     constexpr int kWarps = kBinThreads / 32;
     constexpr int kPerWarp = kBinChunk / kWarps;
@@ -224,21 +223,6 @@ __global__ void __launch_bounds__(kBinThreads) rpw_scatter_kernel(const float* _
         }
     }
     __syncthreads();
-#if RPW_GATHER
-    // phase 3: ranks and scatter of the INPUT INDEX of every patch point (4 bytes written per point; the level-0 fit gathers
-    // the points themselves from the input when it loads a patch: 34 -> 6 bytes per point in this kernel)
-#pragma unroll
-    for (int r = 0; r < kRounds; ++r) {
-        const uint32_t i = wbase + r * 32 + lane;
-        const uint32_t kk = kreg[r];
-        const unsigned peers = __match_any_sync(0xffffffffu, kk);
-        if (kk != 0xFFFFFFFFu) sorted_idx[my[kk] + __popc(peers & ((1u << lane) - 1u))] = (uint32_t)(off + i);
-        __syncwarp();
-        if (kk != 0xFFFFFFFFu && lane == __ffs(peers) - 1) my[kk] += __popc(peers);
-        __syncwarp();
-    }
-    return;
-#endif
     // phase 3: ranks and scatter, four rounds per trip with their point loads issued together
     constexpr int kGroup = 4;
 #pragma unroll
@@ -589,12 +573,12 @@ cudaError_t launch_offsets(cudaStream_t st, const uint64_t* scan_off, const uint
 }
 
 cudaError_t launch_scatter(cudaStream_t st, const PointLayout& lay, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
-                           const uint16_t* keys, const uint32_t* blk_hist, const uint32_t* patch_start, float4* sorted, uint32_t* sorted_idx,
+                           const uint16_t* keys, const uint32_t* blk_hist, const uint32_t* patch_start, float4* sorted,
                            int P, const FusionTable* fusion, int max_chunks, int batch) {
     dim3 grid(max_chunks, batch);
     const size_t smem = (size_t)(kBinThreads / 32) * P * 4;
-    if (lay.vec4) rpw_scatter_kernel<true><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, keys, blk_hist, patch_start, sorted, sorted_idx, P, fusion);
-    else rpw_scatter_kernel<false><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, keys, blk_hist, patch_start, sorted, sorted_idx, P, fusion);
+    if (lay.vec4) rpw_scatter_kernel<true><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, keys, blk_hist, patch_start, sorted, P, fusion);
+    else rpw_scatter_kernel<false><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, keys, blk_hist, patch_start, sorted, P, fusion);
     return cudaGetLastError();
 }
 

@@ -5,14 +5,11 @@
 #include "rpw_b200.h"
 #include "rpw_device.cuh"
 
-// RPW_GATHER=1 (experiment, measured and NOT adopted): K2 scatters input INDICES (4 B per point instead of reading and
-// writing the 16-byte record) and the level-0 fit gathers its points from the input through the index list.  Scatter
+// (Experiment, measured and not adopted, code removed: K2 scattering input INDICES -- 4 B per point instead of reading and
+// writing the 16-byte record -- with the level-0 fit gathering its points from the input through the index list.  Scatter
 // 0.349 -> 0.205 ms per 512 scans, but the fit 1.204 -> 1.391 ms: a patch's points lie in runs of a few records per azimuth
 // step, so every 16-byte lane load of the gather is its own sector request (32 per warp instruction instead of 4), on top
-// of a second dependent memory round trip per patch.  Step 1.846 -> 1.893 ms.  Labels identical.
-#ifndef RPW_GATHER
-#define RPW_GATHER 0
-#endif
+// of a second dependent memory round trip per patch.  Step 1.846 -> 1.893 ms.  Labels identical.)
 
 namespace rpw {
 
@@ -27,11 +24,7 @@ struct __align__(16) NodeRef {
 };
 
 struct FitArgs {
-    const float4* sortedA;     // (RPW_GATHER=0 only) level 0: (x, y, z, bits of global input index), patch-major, input order inside a patch
-    const uint32_t* sorted_idx;  // level 0: global input index of every patch slot, patch-major, input order inside a patch
-    const float* pts;          // the call's input records (the level-0 fit gathers its points from them)
-    PointLayout lay;
-    const FusionTable* fusion; // non-null for a fused multi-LiDAR frame (batch of one): rotation applied when the points are gathered
+    const float4* sortedA;     // level 0: (x, y, z, bits of global input index), patch-major, input order inside a patch
     float4* bufB;              // odd levels: partitioned children (x, y, z, -)
     float4* bufC;              // even levels >= 2
     uint8_t* gmask;            // per-slot mask scratch for nodes that do not fit in shared memory
@@ -78,7 +71,7 @@ cudaError_t launch_bin(cudaStream_t st, const PointLayout& lay, const float* pts
 cudaError_t launch_offsets(cudaStream_t st, const uint64_t* scan_off, const uint32_t* chunk_base, uint32_t* blk_hist,
                            uint32_t* patch_start, uint32_t* cls_count, uint4* cls_list, uint32_t cls_cap, int P, int batch, int profile);
 cudaError_t launch_scatter(cudaStream_t st, const PointLayout& lay, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
-                           const uint16_t* keys, const uint32_t* blk_hist, const uint32_t* patch_start, float4* sorted, uint32_t* sorted_idx,
+                           const uint16_t* keys, const uint32_t* blk_hist, const uint32_t* patch_start, float4* sorted,
                            int P, const FusionTable* fusion, int max_chunks, int batch);
 cudaError_t launch_compact(cudaStream_t st, const PointLayout& lay, const float* pts, const uint8_t* labels, const uint64_t* scan_off,
                            const uint32_t* chunk_base, uint32_t* cnt, const FusionTable* fusion, float* ground, float* nonground,
