@@ -423,7 +423,36 @@ def _quantised_z(rpw):
     return p
 
 
+def _degenerate_geometry(rpw):
+    """A cloud whose patches hold collinear runs, exact duplicates and coplanar sheets: zero and rank-one covariances."""
+    rng = np.random.default_rng(61)
+    t = np.linspace(2.0, 55.0, 6000, dtype=np.float32)
+    line = np.stack([t, np.float32(0.3) * t, np.full_like(t, 0.05)], 1)                         # one straight line
+    dup = np.tile(np.array([[12.0, -7.0, 0.1]], np.float32), (3000, 1))                         # 3000 identical points
+    sheet = np.stack([rng.uniform(-40, 40, 20000), rng.uniform(-40, 40, 20000), np.zeros(20000)], 1).astype(np.float32)  # z == 0 exactly
+    wall = np.stack([np.full(4000, 20.0), rng.uniform(-10, 10, 4000), rng.uniform(0, 3, 4000)], 1).astype(np.float32)    # x == 20 exactly
+    return np.concatenate([line, dup, sheet, wall])
+
+
+def _extreme_magnitudes(rpw):
+    p = rpw.synth.testsuite_cloud(62, 20000)[:, :3].copy()
+    p[::97] *= np.float32(1e20)      # x*x overflows to inf: beyond the radius
+    p[5::101] *= np.float32(1e-30)   # denormal-scale coordinates: inside 1 m, in no ring
+    p[7::103, 2] = np.float32(3e38)  # finite but enormous height inside the zone
+    p[11::107, 0] = np.float32(-0.0)
+    return p
+
+
 EDGE_CASES = {
+    # the fixed-point loop of :185-217 cut short: one iteration, and none at all (the final fit then sees the seed mask)
+    "max_iter_one": lambda rpw: (rpw.PatchworkConfig(filtering_radius=80.0, max_iter=1), rpw.synth.spinning_scan(1003, 64, 900)),
+    "max_iter_zero": lambda rpw: (rpw.PatchworkConfig(filtering_radius=80.0, max_iter=0), rpw.synth.spinning_scan(1004, 64, 900)),
+    "degenerate_geometry": lambda rpw: (rpw.PatchworkConfig(filtering_radius=60.0), _degenerate_geometry(rpw)),
+    "extreme_magnitudes": lambda rpw: (rpw.PatchworkConfig(filtering_radius=60.0), _extreme_magnitudes(rpw)),
+    # R = inf: the ring table is 1, inf, inf, ...: every point from 1 m out lands in ring 0
+    "radius_infinite": lambda rpw: (rpw.PatchworkConfig(filtering_radius=float("inf")), rpw.synth.testsuite_cloud(63, 20000)),
+    "percentile_seeds_many_sectors": lambda rpw: (rpw.PatchworkConfig(adaptive_seed_height=False, num_sectors=90, filtering_radius=70.0, th_seeds=0.05),
+                                                  rpw.synth.spinning_scan(1005, 32, 1200)),
     # a 300k-point patch: streamed from L2 at depth 0, collapses and splits many levels deep, so the
     # radix select, the stable partition and the level kernel all run in streaming mode first
     "one_huge_patch_two_layers": lambda rpw: (rpw.PatchworkConfig(), _one_patch_cloud(300000, 1, True)),
