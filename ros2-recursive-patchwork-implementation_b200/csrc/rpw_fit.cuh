@@ -86,7 +86,12 @@ constexpr int kMiscWords = 96;
 constexpr int kCapTiny = 1024;   // points a 64-thread block keeps in shared memory
 constexpr int kCapSmall = 4096;  // points a 128-thread block keeps in shared memory
 constexpr int kCapLarge = 8192;  // largest shared-memory slot (256-thread block); larger patches stream from L2 ...
-constexpr int kCapStream = 256;  // ... in 512-thread blocks that keep nothing resident
+#ifndef RPW_CAP_STREAM
+// (Giving the 512-thread class a resident slot -- 12288 or 16384 points, one block per SM instead of two streaming ones:
+// C2 unchanged, 1.838 -> 1.835 ms per 512 scans; C4 1.50 -> 1.66 / 1.68 per 64; C5 1.52 -> 1.46 / 1.41.)
+#define RPW_CAP_STREAM 256
+#endif
+constexpr int kCapStream = RPW_CAP_STREAM;  // ... in 512-thread blocks that keep nothing resident
 
 // Sum of K floats over the block; every thread receives the totals (bitwise identical in all
 // threads).  One __syncthreads per call; the scratch area alternates so that back-to-back calls do
