@@ -533,6 +533,46 @@ def main():
             hq.close()
         os.environ.pop("RPW_PC2_PACK", None)
 
+        # ---- multi-LiDAR frame with the fusion front end on the device: three sensors' clouds in their own
+        # frames (a C4 frame cut into its three 120-degree sectors and rotated back), pageable host buffers in, labels out ----
+        fused = None
+        if not args.no_shapes:
+            merged = rpw.synth.solidstate_merged(2000)[:, :3]
+            az = np.degrees(np.arctan2(merged[:, 1], merged[:, 0]))
+            yaws, clouds = [0.0, 120.0, -120.0], []
+            for yaw in yaws:
+                sel = merged[np.abs((az - yaw + 180.0) % 360.0 - 180.0) <= 60.0]
+                a = np.radians(-yaw)
+                rot = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]], np.float32)
+                c = sel.copy()
+                c[:, :2] = sel[:, :2] @ rot.T
+                clouds.append(np.ascontiguousarray(c, np.float32))
+            egos = [2.5, 2.5, 2.5]
+            hf = rpw.Handle(rpw.PatchworkConfig().to_c(), local_rank, sum(map(len, clouds)) + 4096, 1)
+            hf.set_plane_solver(solver_id)
+            ts = []
+            for r in range(60):
+                t0 = time.perf_counter()
+                lab_f = hf.segment_fused(clouds, yaws, egos)
+                ts.append(time.perf_counter() - t0)
+            hf.close()
+            got = np.concatenate(lab_f)
+            fused = {"sensors": 3, "points": int(sum(map(len, clouds))), "rpw_segment_fused_ms": latency_stats(ts[10:]),
+                     "ground_fraction": float((got == 1).mean()), "ego_removed": int((got == 4).sum()),
+                     "api": "rpw_segment_fused: rotation + ego removal + merge inside the binning kernel, pageable per-sensor buffers"}
+            if not args.no_cpu_baseline:
+                ref, kind, oracle_lib = load_reference()
+                tr = []
+                for r in range(5):
+                    t0 = time.perf_counter()
+                    out = ref.fuse(clouds, yaws, egos)
+                    merged_cpu = out[0] if isinstance(out, tuple) else out
+                    t1 = time.perf_counter()
+                    ref.time_scan(oracle_lib.to_cfg(rpw.PatchworkConfig()), merged_cpu, 1)
+                    tr.append((t1 - t0, time.perf_counter() - t1))
+                fused["cpu_reference_ms"] = {"fuse": 1e3 * float(np.median([a for a, _ in tr])), "segment": 1e3 * float(np.median([b for _, b in tr])),
+                                             "kind": kind, "cores": 1, "note": "LidarFusion::fuseLidarPointClouds + filterGroundPoints, one frame on one core"}
+
         # ---- the other named shapes (BASELINE configs[0], [3], [4]): resident batch, end to end, single-scan latency,
         # the reference's CPU build on the same host threads; parity for them is in tests/ ----
         if not args.no_shapes:
@@ -608,6 +648,7 @@ def main():
                     "copy_gbs_per_rank": {"columns": ["h2d_with_d2h_mix", "h2d_alone", "h2d_alone_write_combined", "d2h_alone"], "rows": copy_rates},
                     "steps": e2e_steps, "gpu_launches": int(launches_e2e)},
             "e2e_pointcloud2": pc2,
+            "fused_multi_lidar_frame": fused,
             "single_scan_latency": lat,
             "shapes": shapes,
             "pipelined_two_handles": {"value": pipelined_value, "unit": UNIT,

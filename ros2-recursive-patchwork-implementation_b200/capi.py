@@ -246,7 +246,7 @@ class Handle:
         a = self._as_points(points)
         labels = np.empty(len(a), np.uint8)
         st = RpwStats()
-        self._check(self.lib.rpw_segment(self._h, a.ctypes.data, len(a), a.shape[1] * 4, labels.ctypes.data, C.byref(st)))
+        self._check(self.lib.rpw_segment(self._h, a.ctypes.data, len(a), a.shape[1] * 4, labels.ctypes.data, C.byref(st) if want_stats else None))
         return (labels, st) if want_stats else labels
 
     def segment_batch(self, clouds, want_stats=False, labels_out=None):
@@ -260,7 +260,7 @@ class Handle:
         lp = (C.c_void_p * B)(*[l.ctypes.data for l in labels])
         ns = (C.c_size_t * B)(*[len(a) for a in arrs])
         st = RpwStats()
-        self._check(self.lib.rpw_segment_batch(self._h, cp, ns, B, stride * 4, lp, C.byref(st)))
+        self._check(self.lib.rpw_segment_batch(self._h, cp, ns, B, stride * 4, lp, C.byref(st) if want_stats else None))
         return (labels, st) if want_stats else labels
 
     def segment_batch_async(self, ptrs, ns, stride_bytes, label_ptrs):
@@ -294,7 +294,7 @@ class Handle:
             sens[i].rotation_deg = float(rotations_deg[i]); sens[i].ego_radius = float(ego_radii[i])
         lp = (C.c_void_p * k)(*[l.ctypes.data for l in labels])
         st = RpwStats()
-        self._check(self.lib.rpw_segment_fused(self._h, sens, k, stride * 4, lp, C.byref(st)))
+        self._check(self.lib.rpw_segment_fused(self._h, sens, k, stride * 4, lp, C.byref(st) if want_stats else None))  # (stats: a host pass over the labels)
         return (labels, st) if want_stats else labels
 
     def segment_clouds(self, points):
