@@ -646,6 +646,18 @@ struct TraceScope {
 // fit is element-wise and already the reference's operations.  With these sums, the QR eigensolver and the exact
 // medians / percentiles, every decision of fitPlaneAndSplit is taken on the reference's bits.
 // =============================================================================================
+#ifndef RPW_LB512_REPLAY
+#define RPW_LB512_REPLAY 1
+#endif
+#ifndef RPW_LB256_REPLAY
+#define RPW_LB256_REPLAY 3
+#endif
+#ifndef RPW_LB128_REPLAY
+#define RPW_LB128_REPLAY RPW_LB128
+#endif
+#ifndef RPW_SEQ_AHEAD
+#define RPW_SEQ_AHEAD 4  // chunks a streamed node's sequential sums keep in flight
+#endif
 constexpr int kSeqStride = 36;  // floats between the addend rows of two sums (36: the chain lanes' 16-byte loads spread over the banks)
 
 // Sequential sums over the node's points i = 0 .. n-1, in order.  produce(i, x, y, z, m, v) fills the NV addends of
@@ -676,6 +688,48 @@ __device__ __forceinline__ void seq_sums(const NodeView<SMEM>& nv, uint32_t n, f
 #pragma unroll
             for (int k = 0; k < NV; ++k) scratch[k * kSeqStride + lane] = live ? v[k] : 0.f;
         };
+        if constexpr (!SMEM) {
+            // Streamed node: a point comes from L2 (~700 cycles), so one chunk of look-ahead leaves the chain waiting for its
+            // addends (measured: 20 cycles per point against 10 for a resident node).  kAhead chunks are kept in flight in a
+            // register ring; the loop is unrolled over the ring so that its slots are compile-time registers.  Groups of
+            // kAhead chunks: the chunks past the end add +0.0f, which leaves the sums' bits unchanged.
+            constexpr int kAhead = RPW_SEQ_AHEAD;
+            float fx[kAhead], fy[kAhead], fz[kAhead];
+            uint8_t fm[kAhead];
+            auto fetch_slot = [&](int k, uint32_t base) {
+                const uint32_t i = min(base + (uint32_t)lane, n - 1u);
+                nv.get(i, fx[k], fy[k], fz[k]);
+                fm[k] = nv.mask(i);
+            };
+            auto put_slot = [&](int k, uint32_t base) {
+                float v[NV];
+                produce(base + lane, fx[k], fy[k], fz[k], fm[k], v);
+                const bool live = base + lane < n;
+#pragma unroll
+                for (int q = 0; q < NV; ++q) scratch[q * kSeqStride + lane] = live ? v[q] : 0.f;
+            };
+#pragma unroll
+            for (int k = 0; k < kAhead; ++k) fetch_slot(k, 32u * k);
+            put_slot(0, 0);  // rows = chunk 0; slots 1 .. kAhead-1 hold the chunks after it, slot 0 is free
+            __syncwarp();
+            for (uint32_t base = 0; base < n; base += 32 * kAhead) {
+#pragma unroll
+                for (int u = 0; u < kAhead; ++u) {
+                    const uint32_t cb = base + 32u * u;  // the chunk whose addends are in the rows
+                    float4 t[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) t[q] = rowp[q];
+                    __syncwarp();
+                    fetch_slot(u, cb + 32u * kAhead);               // slot u was consumed when this chunk's rows were written
+                    put_slot((u + 1) % kAhead, cb + 32u);          // the next chunk's addends
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        acc = __fadd_rn(acc, t[q].x); acc = __fadd_rn(acc, t[q].y); acc = __fadd_rn(acc, t[q].z); acc = __fadd_rn(acc, t[q].w);
+                    }
+                    __syncwarp();
+                }
+            }
+        } else {
         fetch(0);
         put(0);
         fetch(32);
@@ -692,6 +746,7 @@ __device__ __forceinline__ void seq_sums(const NodeView<SMEM>& nv, uint32_t n, f
                 acc = __fadd_rn(acc, t[q].x); acc = __fadd_rn(acc, t[q].y); acc = __fadd_rn(acc, t[q].z); acc = __fadd_rn(acc, t[q].w);
             }
             __syncwarp();       // the next chunk's rows are complete
+        }
         }
 #pragma unroll
         for (int k = 0; k < NV; ++k) out[k] = __shfl_sync(0xffffffffu, acc, k);
@@ -1331,7 +1386,9 @@ __device__ __forceinline__ FitSmem carve_smem(unsigned char* raw, int cap, int w
 // float solver, which is enough to tip chaotic two-layer patches the other way).
 // ---------------------------------------------------------------------------------------------
 template <int TT, bool EXACT, bool REPLAY>
-__global__ void __launch_bounds__(TT, (TT <= 32 ? RPW_LB32 : TT <= 64 ? RPW_LB64 : TT <= 128 ? RPW_LB128 : TT <= 256 ? 3 : 2))
+// (the 512-thread kernel of the reference-order build is compiled for one block per SM: its sequential sums run in ONE warp,
+// whose register ring of chunks in flight spilled at the 64 registers two resident blocks allow)
+__global__ void __launch_bounds__(TT, (TT <= 32 ? RPW_LB32 : TT <= 64 ? RPW_LB64 : TT <= 128 ? (REPLAY ? RPW_LB128_REPLAY : RPW_LB128) : TT <= 256 ? (REPLAY ? RPW_LB256_REPLAY : 3) : (REPLAY ? RPW_LB512_REPLAY : 2)))
 rpw_fit_roots_kernel(FitArgs A, int cls, int cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // The class's work list and its length are read together (independent addresses, one latency).
