@@ -40,6 +40,8 @@
 #define RPW_LB64 8  // resident blocks per SM the 64-thread fit kernels are compiled for
 #endif
 #ifndef RPW_STREAM_THREADS
+// (256 threads, four blocks per SM: C4 1.51 -> 1.56 ms per 64 scans, C5 1.52 -> 1.54, C2 the same; 1024 threads, one block:
+// C4 1.54, C5 1.50, C2 1.832 -> 1.877)
 #define RPW_STREAM_THREADS 512  // block size of the class whose patches stream from L2 (no shared-memory slot)
 #endif
 #ifndef RPW_STREAM_TMA
@@ -1388,7 +1390,7 @@ __device__ __forceinline__ FitSmem carve_smem(unsigned char* raw, int cap, int w
 template <int TT, bool EXACT, bool REPLAY>
 // (the 512-thread kernel of the reference-order build is compiled for one block per SM: its sequential sums run in ONE warp,
 // whose register ring of chunks in flight spilled at the 64 registers two resident blocks allow)
-__global__ void __launch_bounds__(TT, (TT <= 32 ? RPW_LB32 : TT <= 64 ? RPW_LB64 : TT <= 128 ? (REPLAY ? RPW_LB128_REPLAY : RPW_LB128) : TT <= 256 ? (REPLAY ? RPW_LB256_REPLAY : 3) : (REPLAY ? RPW_LB512_REPLAY : 2)))
+__global__ void __launch_bounds__(TT, (TT <= 32 ? RPW_LB32 : TT <= 64 ? RPW_LB64 : TT <= 128 ? (REPLAY ? RPW_LB128_REPLAY : RPW_LB128) : TT <= 256 ? (REPLAY ? RPW_LB256_REPLAY : 3) : (REPLAY ? RPW_LB512_REPLAY : (TT > 512 ? 1 : 2))))
 rpw_fit_roots_kernel(FitArgs A, int cls, int cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // The class's work list and its length are read together (independent addresses, one latency).
