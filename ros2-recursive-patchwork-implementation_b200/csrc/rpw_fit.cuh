@@ -660,6 +660,12 @@ struct TraceScope {
 #ifndef RPW_SEQ_AHEAD
 #define RPW_SEQ_AHEAD 4  // chunks a streamed node's sequential sums keep in flight
 #endif
+// (Tried on top of this, labels identical each time, per 512 C2 / 64 C4 / 64 C5 scans in the reference-order mode, from 14.8 / 36.2 /
+// 18.3 ms: every class above 2048 points as 64-thread STREAMING blocks, eight chains to an SM instead of the 2-5 a shared-memory
+// slot allows: 15.9 / 37.0 / 18.0 -- the batches end with single long nodes, residency is not what limits them.  A producer
+// warp filling two row buffers and a consumer warp that only loads and adds, handing buffers over with named barriers: 17.2 /
+// 44.7 / 20.9, two barrier round trips per 32-point chunk cost more than the work they move out of the chain's warp.  The
+// chain written ahead of the next chunk's addend computation in program order: 17.3 / 40.4 / 19.3.)
 constexpr int kSeqStride = 36;  // floats between the addend rows of two sums (36: the chain lanes' 16-byte loads spread over the banks)
 
 // Sequential sums over the node's points i = 0 .. n-1, in order.  produce(i, x, y, z, m, v) fills the NV addends of
