@@ -446,7 +446,11 @@ __device__ __forceinline__ void label_const(const FitArgs& A, const NodeRef& nd,
 #ifndef RPW_WIDE
 #define RPW_WIDE 8
 #endif
-constexpr int kUnroll = RPW_UNROLL;
+#ifndef RPW_UNROLL_STREAM
+// rows per trip of a STREAMED node's passes (records from L2; the 512-thread kernel has 64 registers per thread): two.
+// Per 64 C4 scans 1.81 / 1.42 / 1.69 / 1.50 / 1.73 ms with 1 / 2 / 3 / 4 / 8; C5 1.54 / 1.49 / 1.48 / 1.52 / 1.52; C2 unchanged.
+#define RPW_UNROLL_STREAM 2
+#endif
 
 // ---- streamed nodes: records through a ring of TMA bulk copies --------------------------------------------------------
 // A node too large for a shared-memory slot is re-read from L2 on every pass.  With plain loads each thread has
@@ -532,6 +536,7 @@ __device__ __forceinline__ void for_points(const NodeView<SMEM>& nv, uint32_t n,
         }
     }
 #endif
+    constexpr int kUnroll = SMEM ? RPW_UNROLL : RPW_UNROLL_STREAM;
     uint32_t i = first + threadIdx.x;
     for (; i + (kUnroll - 1) * TT < n; i += kUnroll * TT) {
         float x[kUnroll], y[kUnroll], z[kUnroll];
