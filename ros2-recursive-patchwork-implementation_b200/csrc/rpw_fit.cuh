@@ -37,7 +37,7 @@
 #define RPW_LT2 256  // (128 -> 256 threads for the 2049..4096-point classes of single-scan calls: C2 p50 0.143 -> 0.134 ms)
 #endif
 #ifndef RPW_LB64
-#define RPW_LB64 8  // resident blocks per SM the 64-thread fit kernels are compiled for
+#define RPW_LB64 10  // resident blocks per SM the 64-thread fit kernels are compiled for (8 / 9 / 10 / 11 / 12: 1.830 / 1.821 / 1.814 / 1.813 / 1.811 ms per 512 C2 scans)
 #endif
 #ifndef RPW_STREAM_THREADS
 // (256 threads, four blocks per SM: C4 1.51 -> 1.56 ms per 64 scans, C5 1.52 -> 1.54, C2 the same; 1024 threads, one block:
@@ -1401,7 +1401,7 @@ __device__ __forceinline__ FitSmem carve_smem(unsigned char* raw, int cap, int w
 template <int TT, bool EXACT, bool REPLAY>
 // (the 512-thread kernel of the reference-order build is compiled for one block per SM: its sequential sums run in ONE warp,
 // whose register ring of chunks in flight spilled at the 64 registers two resident blocks allow)
-__global__ void __launch_bounds__(TT, (TT <= 32 ? RPW_LB32 : TT <= 64 ? RPW_LB64 : TT <= 128 ? (REPLAY ? RPW_LB128_REPLAY : RPW_LB128) : TT <= 256 ? (REPLAY ? RPW_LB256_REPLAY : 3) : (REPLAY ? RPW_LB512_REPLAY : (TT > 512 ? 1 : 2))))
+__global__ void __launch_bounds__(TT, (TT <= 32 ? RPW_LB32 : TT <= 64 ? (REPLAY ? 8 : RPW_LB64) : TT <= 128 ? (REPLAY ? RPW_LB128_REPLAY : RPW_LB128) : TT <= 256 ? (REPLAY ? RPW_LB256_REPLAY : 3) : (REPLAY ? RPW_LB512_REPLAY : (TT > 512 ? 1 : 2))))
 rpw_fit_roots_kernel(FitArgs A, int cls, int cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // The class's work list and its length are read together (independent addresses, one latency).
