@@ -170,7 +170,7 @@ int rpw_capacity(const rpw_handle* h, size_t* max_total_points, size_t* max_batc
  *     is taken on the reference's bits: labels, node records (centroid, normal, residual, iteration counts) and
  *     clouds are IDENTICAL to the reference's strict-IEEE build, including the bistable and never-converging
  *     patches that amplify last-bit differences (tests/test_gpu_parity.py).  The sums are dependent chains
- *     (one lane per sum), so this mode is about eight times slower on batches (34.7 k against 272 k scans/s per B200);
+ *     (one lane per sum), so this mode is about eight times slower on batches (34 k against 278 k scans/s per B200);
  *     it is the verification mode.
  * Environment override at rpw_create: RPW_PLANE_SOLVER=0|1|2|3. */
 #define RPW_SOLVER_EIGEN_QR 0
