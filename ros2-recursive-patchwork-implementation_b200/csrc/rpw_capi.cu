@@ -656,13 +656,18 @@ static int run_group(rpw_handle* h, rpw_handle::Lane& L, cudaStream_t st, const 
     const uint64_t* d_so = h->d_scan_off + b0;
     const uint32_t* d_cb = h->d_chunk_base + b0;
     uint32_t* d_ps = h->d_patch_start + b0 * (size_t)(h->P + 1);
+    // calls of one or two scans: 1024-thread blocks for K1 / K2 (four points per thread instead of sixteen), as long as the
+    // scatter's per-warp offset tables (32 warps x P words) stay within the default shared-memory limit
+    static const char* bin_wide_env = getenv("RPW_BIN_WIDE");
+    const bool bin_wide = bin_wide_env ? atoi(bin_wide_env) != 0 : (profile == 1 && h->P <= 256);
+    const int bin_threads = bin_wide ? 1024 : kBinThreads;
     { ProfScope ps(h, 0);
-      RPW_CUDA(h, launch_bin(st, lay, d_pts, d_so, d_cb, h->zm, h->d_keys, d_labels, h->d_blk_hist, L.d_cls_count, h->fusion_arg, max_chunks, (int)nb)); }
+      RPW_CUDA(h, launch_bin(st, lay, d_pts, d_so, d_cb, h->zm, h->d_keys, d_labels, h->d_blk_hist, L.d_cls_count, h->fusion_arg, max_chunks, (int)nb, bin_threads)); }
     { ProfScope ps(h, 1);
       RPW_CUDA(h, launch_offsets(st, d_so, d_cb, h->d_blk_hist, d_ps, L.d_cls_count, L.d_cls_list, h->cls_cap, h->P, (int)nb, profile)); }
     { ProfScope ps(h, 2);
       RPW_CUDA(h, launch_scatter(st, lay, d_pts, d_so, d_cb, h->d_keys, h->d_blk_hist, d_ps, h->d_sortedA,
-                                 h->P, h->fusion_arg, max_chunks, (int)nb)); }
+                                 h->P, h->fusion_arg, max_chunks, (int)nb, bin_threads)); }
     FitArgs A;
     A.sortedA = h->d_sortedA;
     A.bufB = h->d_bufB; A.bufC = h->d_bufC; A.gmask = h->d_gmask;

@@ -36,8 +36,10 @@ __device__ __forceinline__ void load_xyz(const float* __restrict__ pts, uint64_t
     }
 }
 
-template <bool VEC4>
-__global__ void __launch_bounds__(kBinThreads) rpw_bin_kernel(const float* __restrict__ pts, PointLayout lay, const uint64_t* __restrict__ scan_off,
+// THREADS: kBinThreads for batches (sixteen points per thread); 1024 for calls of one or two scans (four points per thread:
+// a single scan is 30 blocks on 148 SMs, and what it waits for is the length of a thread's own loop, not throughput).
+template <bool VEC4, int THREADS>
+__global__ void __launch_bounds__(THREADS) rpw_bin_kernel(const float* __restrict__ pts, PointLayout lay, const uint64_t* __restrict__ scan_off,
                                                              const uint32_t* __restrict__ chunk_base, ZoneModel zm,
                                                              uint16_t* __restrict__ keys, uint8_t* __restrict__ labels,
                                                              uint32_t* __restrict__ blk_hist, uint32_t* __restrict__ cls_count,
@@ -52,12 +54,12 @@ __global__ void __launch_bounds__(kBinThreads) rpw_bin_kernel(const float* __res
     const uint32_t base = (uint32_t)chunk * kBinChunk;
     if (base >= n) return;
     const int P = zm.num_patches;
-    for (int p = threadIdx.x; p < P; p += kBinThreads) s_hist[p] = 0;
+    for (int p = threadIdx.x; p < P; p += THREADS) s_hist[p] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
 #pragma unroll 4
-    for (int k = 0; k < kBinChunk / kBinThreads; ++k) {
-        const uint32_t i = base + k * kBinThreads + threadIdx.x;
+    for (int k = 0; k < kBinChunk / THREADS; ++k) {
+        const uint32_t i = base + k * THREADS + threadIdx.x;
         uint16_t key = kKeyDropped;
         const bool valid = i < n;
         if (valid) {
@@ -76,7 +78,7 @@ __global__ void __launch_bounds__(kBinThreads) rpw_bin_kernel(const float* __res
     }
     __syncthreads();
     uint32_t* out = blk_hist + ((size_t)chunk_base[b] + chunk) * P;
-    for (int p = threadIdx.x; p < P; p += kBinThreads) out[p] = s_hist[p];
+    for (int p = threadIdx.x; p < P; p += THREADS) out[p] = s_hist[p];
 }
 
 // =============================================================================================
@@ -173,13 +175,13 @@ __global__ void __launch_bounds__(256) rpw_offsets_kernel(const uint64_t* __rest
 // =============================================================================================
 // (64 registers, four blocks per SM.  Forcing five blocks changes nothing, six and more spill the key registers:
 // 0.343 / 0.397 / 0.459 ms per 512 scans for 5 / 6 / 8.)
-template <bool VEC4>
-__global__ void __launch_bounds__(kBinThreads) rpw_scatter_kernel(const float* __restrict__ pts, PointLayout lay, const uint64_t* __restrict__ scan_off,
+template <bool VEC4, int THREADS>
+__global__ void __launch_bounds__(THREADS) rpw_scatter_kernel(const float* __restrict__ pts, PointLayout lay, const uint64_t* __restrict__ scan_off,
                                                                  const uint32_t* __restrict__ chunk_base,
                                                                  const uint16_t* __restrict__ keys, const uint32_t* __restrict__ blk_hist,
                                                                  const uint32_t* __restrict__ patch_start, float4* __restrict__ sorted, int P, const FusionTable* __restrict__ fusion) {
     extern __shared__ uint32_t s_off[];  // [warps][P]
-    constexpr int kWarps = kBinThreads / 32;
+    constexpr int kWarps = THREADS / 32;
     constexpr int kPerWarp = kBinChunk / kWarps;
     const int b = blockIdx.y, chunk = blockIdx.x;
     const uint64_t off = scan_off[b];
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(kBinThreads) rpw_scatter_kernel(const float* _
     const uint32_t base = (uint32_t)chunk * kBinChunk;
     if (base >= n) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < kWarps * P; i += kBinThreads) s_off[i] = 0;
+    for (int i = threadIdx.x; i < kWarps * P; i += THREADS) s_off[i] = 0;
     __syncthreads();
     uint32_t* my = s_off + warp * P;
     const uint32_t wbase = base + warp * kPerWarp;
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(kBinThreads) rpw_scatter_kernel(const float* _
     // phase 2: exclusive prefix over warps + block offset + patch offset
     const uint32_t* bh = blk_hist + ((size_t)chunk_base[b] + chunk) * P;
     const uint32_t* ps = patch_start + (size_t)b * (P + 1);
-    for (int p = threadIdx.x; p < P; p += kBinThreads) {
+    for (int p = threadIdx.x; p < P; p += THREADS) {
         uint32_t run = ps[p] + bh[p];
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) {
@@ -557,11 +559,16 @@ __global__ void rpw_atan2_kernel(const float* __restrict__ y, const float* __res
 // =============================================================================================
 cudaError_t launch_bin(cudaStream_t st, const PointLayout& lay, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
                        const ZoneModel& zm, uint16_t* keys, uint8_t* labels, uint32_t* blk_hist, uint32_t* cls_count,
-                       const FusionTable* fusion, int max_chunks, int batch) {
+                       const FusionTable* fusion, int max_chunks, int batch, int threads) {
     dim3 grid(max_chunks, batch);
     const size_t smem = (size_t)zm.num_patches * 4;
-    if (lay.vec4) rpw_bin_kernel<true><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, zm, keys, labels, blk_hist, cls_count, fusion);
-    else rpw_bin_kernel<false><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, zm, keys, labels, blk_hist, cls_count, fusion);
+    if (threads == 1024) {
+        if (lay.vec4) rpw_bin_kernel<true, 1024><<<grid, 1024, smem, st>>>(pts, lay, scan_off, chunk_base, zm, keys, labels, blk_hist, cls_count, fusion);
+        else rpw_bin_kernel<false, 1024><<<grid, 1024, smem, st>>>(pts, lay, scan_off, chunk_base, zm, keys, labels, blk_hist, cls_count, fusion);
+    } else {
+        if (lay.vec4) rpw_bin_kernel<true, kBinThreads><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, zm, keys, labels, blk_hist, cls_count, fusion);
+        else rpw_bin_kernel<false, kBinThreads><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, zm, keys, labels, blk_hist, cls_count, fusion);
+    }
     return cudaGetLastError();
 }
 
@@ -574,11 +581,16 @@ cudaError_t launch_offsets(cudaStream_t st, const uint64_t* scan_off, const uint
 
 cudaError_t launch_scatter(cudaStream_t st, const PointLayout& lay, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
                            const uint16_t* keys, const uint32_t* blk_hist, const uint32_t* patch_start, float4* sorted,
-                           int P, const FusionTable* fusion, int max_chunks, int batch) {
+                           int P, const FusionTable* fusion, int max_chunks, int batch, int threads) {
     dim3 grid(max_chunks, batch);
-    const size_t smem = (size_t)(kBinThreads / 32) * P * 4;
-    if (lay.vec4) rpw_scatter_kernel<true><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, keys, blk_hist, patch_start, sorted, P, fusion);
-    else rpw_scatter_kernel<false><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, keys, blk_hist, patch_start, sorted, P, fusion);
+    const size_t smem = (size_t)(threads / 32) * P * 4;
+    if (threads == 1024) {
+        if (lay.vec4) rpw_scatter_kernel<true, 1024><<<grid, 1024, smem, st>>>(pts, lay, scan_off, chunk_base, keys, blk_hist, patch_start, sorted, P, fusion);
+        else rpw_scatter_kernel<false, 1024><<<grid, 1024, smem, st>>>(pts, lay, scan_off, chunk_base, keys, blk_hist, patch_start, sorted, P, fusion);
+    } else {
+        if (lay.vec4) rpw_scatter_kernel<true, kBinThreads><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, keys, blk_hist, patch_start, sorted, P, fusion);
+        else rpw_scatter_kernel<false, kBinThreads><<<grid, kBinThreads, smem, st>>>(pts, lay, scan_off, chunk_base, keys, blk_hist, patch_start, sorted, P, fusion);
+    }
     return cudaGetLastError();
 }
 

@@ -67,12 +67,12 @@ cudaError_t fit_configure(int smem_cap, int* blocks_per_sm);
 
 cudaError_t launch_bin(cudaStream_t st, const PointLayout& lay, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
                        const ZoneModel& zm, uint16_t* keys, uint8_t* labels, uint32_t* blk_hist, uint32_t* cls_count,
-                       const FusionTable* fusion, int max_chunks, int batch);
+                       const FusionTable* fusion, int max_chunks, int batch, int threads);
 cudaError_t launch_offsets(cudaStream_t st, const uint64_t* scan_off, const uint32_t* chunk_base, uint32_t* blk_hist,
                            uint32_t* patch_start, uint32_t* cls_count, uint4* cls_list, uint32_t cls_cap, int P, int batch, int profile);
 cudaError_t launch_scatter(cudaStream_t st, const PointLayout& lay, const float* pts, const uint64_t* scan_off, const uint32_t* chunk_base,
                            const uint16_t* keys, const uint32_t* blk_hist, const uint32_t* patch_start, float4* sorted,
-                           int P, const FusionTable* fusion, int max_chunks, int batch);
+                           int P, const FusionTable* fusion, int max_chunks, int batch, int threads);
 cudaError_t launch_compact(cudaStream_t st, const PointLayout& lay, const float* pts, const uint8_t* labels, const uint64_t* scan_off,
                            const uint32_t* chunk_base, uint32_t* cnt, const FusionTable* fusion, float* ground, float* nonground,
                            uint32_t* scan_counts, int max_chunks, int batch, int packed = 0);
