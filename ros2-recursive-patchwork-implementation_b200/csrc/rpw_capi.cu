@@ -1163,7 +1163,7 @@ int rpw_last_clouds(rpw_handle* h, float* ground_xyz, float* nonground_xyz, int 
     const int max_chunks = (int)((max_n + kBinChunk - 1) / kBinChunk);
     nvtxRangePushA("rpw K4 result assembly");
     const cudaError_t ek4 = launch_compact(h->stream, h->last_lay, h->last_pts, h->last_labels, h->d_scan_off, h->d_chunk_base, h->d_cmp_cnt,
-                                           h->last_fused ? h->d_fusion : nullptr, dg, dng, h->d_scan_counts, max_chunks, (int)batch);
+                                           h->last_fused ? h->d_fusion : nullptr, dg, dng, h->d_scan_counts, max_chunks, (int)batch, 0, batch <= 2 ? 1024 : kBinThreads);
     nvtxRangePop();
     RPW_CUDA(h, ek4);
     h->launches += 2;
@@ -1339,7 +1339,7 @@ int rpw_segment_clouds_view(rpw_handle* h, const float* xyz, size_t n, size_t st
     if (rc != RPW_OK) return rc;
     const int max_chunks = (int)((n + kBinChunk - 1) / kBinChunk);
     RPW_CUDA(h, launch_compact(h->stream, lay, h->d_in, h->d_labels, h->d_scan_off, h->d_chunk_base, h->d_cmp_cnt, nullptr,
-                               h->d_cloud_g, h->d_cloud_g, h->d_scan_counts, max_chunks, 1, /*packed*/1));
+                               h->d_cloud_g, h->d_cloud_g, h->d_scan_counts, max_chunks, 1, /*packed*/1, /*threads*/1024));
     h->launches += 2;
     uint8_t* lab_dst = labels_out && is_pinned(labels_out) ? labels_out : h->h_stage_labels;
     if (labels_out) RPW_CUDA(h, cudaMemcpyAsync(lab_dst, h->d_labels, n, cudaMemcpyDeviceToHost, h->stream));

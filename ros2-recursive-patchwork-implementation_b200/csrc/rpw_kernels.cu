@@ -264,7 +264,8 @@ __global__ void __launch_bounds__(THREADS) rpw_scatter_kernel(const float* __res
 // coordinates (the same fuse_point as K1); ego and non-finite points appear in neither cloud.
 // Cloud slot i of scan b is record (scan_off[b] + i) of the output buffers.
 // =============================================================================================
-__global__ void __launch_bounds__(kBinThreads) rpw_compact_count_kernel(const uint8_t* __restrict__ labels, const uint64_t* __restrict__ scan_off,
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) rpw_compact_count_kernel(const uint8_t* __restrict__ labels, const uint64_t* __restrict__ scan_off,
                                                                        const uint32_t* __restrict__ chunk_base, uint32_t* __restrict__ cnt) {
     __shared__ uint32_t s_c[3];
     const int b = blockIdx.y, chunk = blockIdx.x;
@@ -276,8 +277,8 @@ __global__ void __launch_bounds__(kBinThreads) rpw_compact_count_kernel(const ui
     __syncthreads();
     uint32_t c0 = 0, c1 = 0, c2 = 0;
 #pragma unroll 4
-    for (int k = 0; k < kBinChunk / kBinThreads; ++k) {
-        const uint32_t i = base + k * kBinThreads + threadIdx.x;
+    for (int k = 0; k < kBinChunk / THREADS; ++k) {
+        const uint32_t i = base + k * THREADS + threadIdx.x;
         const uint32_t l = i < n ? labels[off + i] : 255u;
         c0 += l == 0; c1 += l == 1; c2 += l == 2;
     }
@@ -292,13 +293,13 @@ __global__ void __launch_bounds__(kBinThreads) rpw_compact_count_kernel(const ui
     if (threadIdx.x < 3) cnt[((size_t)chunk_base[b] + chunk) * 4 + threadIdx.x] = s_c[threadIdx.x];
 }
 
-template <bool VEC4>
-__global__ void __launch_bounds__(kBinThreads) rpw_compact_scatter_kernel(const float* __restrict__ pts, PointLayout lay, const uint8_t* __restrict__ labels,
+template <bool VEC4, int THREADS>
+__global__ void __launch_bounds__(THREADS) rpw_compact_scatter_kernel(const float* __restrict__ pts, PointLayout lay, const uint8_t* __restrict__ labels,
                                                                          const uint64_t* __restrict__ scan_off, const uint32_t* __restrict__ chunk_base,
                                                                          const uint32_t* __restrict__ cnt, const FusionTable* __restrict__ fusion,
                                                                          float* __restrict__ ground, float* __restrict__ nonground,
                                                                          uint32_t* __restrict__ scan_counts, int packed) {
-    constexpr int kWarps = kBinThreads / 32;
+    constexpr int kWarps = THREADS / 32;
     constexpr int kPerWarp = kBinChunk / kWarps;
     __shared__ uint32_t s_base[5];          // ground, non-ground, beyond bases of this chunk; [3] label-0, [4] label-1 total of the scan
     __shared__ uint32_t s_warp[kWarps][3];  // per-warp counts, then exclusive offsets
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(kBinThreads) rpw_compact_scatter_kernel(const 
         const int chunks = (int)((n + kBinChunk - 1) / kBinChunk);
         const uint32_t* c = cnt + (size_t)chunk_base[b] * 4;
         uint32_t g = 0, ng = 0, by = 0, ng_all = 0, g_all = 0, by_all = 0;
-        for (int q = threadIdx.x; q < chunks; q += kBinThreads) {
+        for (int q = threadIdx.x; q < chunks; q += THREADS) {
             const uint32_t a0 = c[q * 4 + 0], a1 = c[q * 4 + 1], a2 = c[q * 4 + 2];
             if (q < chunk) { ng += a0; g += a1; by += a2; }
             ng_all += a0; g_all += a1; by_all += a2;
@@ -596,13 +597,19 @@ cudaError_t launch_scatter(cudaStream_t st, const PointLayout& lay, const float*
 
 cudaError_t launch_compact(cudaStream_t st, const PointLayout& lay, const float* pts, const uint8_t* labels, const uint64_t* scan_off,
                            const uint32_t* chunk_base, uint32_t* cnt, const FusionTable* fusion, float* ground, float* nonground,
-                           uint32_t* scan_counts, int max_chunks, int batch, int packed) {
+                           uint32_t* scan_counts, int max_chunks, int batch, int packed, int threads) {
     dim3 grid(max_chunks, batch);
     cudaError_t e = cudaMemsetAsync(scan_counts, 0, (size_t)batch * 2 * sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
-    rpw_compact_count_kernel<<<grid, kBinThreads, 0, st>>>(labels, scan_off, chunk_base, cnt);
-    if (lay.vec4) rpw_compact_scatter_kernel<true><<<grid, kBinThreads, 0, st>>>(pts, lay, labels, scan_off, chunk_base, cnt, fusion, ground, nonground, scan_counts, packed);
-    else rpw_compact_scatter_kernel<false><<<grid, kBinThreads, 0, st>>>(pts, lay, labels, scan_off, chunk_base, cnt, fusion, ground, nonground, scan_counts, packed);
+    if (threads == 1024) {  // calls of one or two scans: four points per thread instead of sixteen, like K1 / K2
+        rpw_compact_count_kernel<1024><<<grid, 1024, 0, st>>>(labels, scan_off, chunk_base, cnt);
+        if (lay.vec4) rpw_compact_scatter_kernel<true, 1024><<<grid, 1024, 0, st>>>(pts, lay, labels, scan_off, chunk_base, cnt, fusion, ground, nonground, scan_counts, packed);
+        else rpw_compact_scatter_kernel<false, 1024><<<grid, 1024, 0, st>>>(pts, lay, labels, scan_off, chunk_base, cnt, fusion, ground, nonground, scan_counts, packed);
+        return cudaGetLastError();
+    }
+    rpw_compact_count_kernel<kBinThreads><<<grid, kBinThreads, 0, st>>>(labels, scan_off, chunk_base, cnt);
+    if (lay.vec4) rpw_compact_scatter_kernel<true, kBinThreads><<<grid, kBinThreads, 0, st>>>(pts, lay, labels, scan_off, chunk_base, cnt, fusion, ground, nonground, scan_counts, packed);
+    else rpw_compact_scatter_kernel<false, kBinThreads><<<grid, kBinThreads, 0, st>>>(pts, lay, labels, scan_off, chunk_base, cnt, fusion, ground, nonground, scan_counts, packed);
     return cudaGetLastError();
 }
 

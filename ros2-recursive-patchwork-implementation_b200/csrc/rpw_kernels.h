@@ -75,7 +75,7 @@ cudaError_t launch_scatter(cudaStream_t st, const PointLayout& lay, const float*
                            int P, const FusionTable* fusion, int max_chunks, int batch, int threads);
 cudaError_t launch_compact(cudaStream_t st, const PointLayout& lay, const float* pts, const uint8_t* labels, const uint64_t* scan_off,
                            const uint32_t* chunk_base, uint32_t* cnt, const FusionTable* fusion, float* ground, float* nonground,
-                           uint32_t* scan_counts, int max_chunks, int batch, int packed = 0);
+                           uint32_t* scan_counts, int max_chunks, int batch, int packed = 0, int threads = kBinThreads);
 cudaError_t launch_bev(cudaStream_t st, int mode, const float* a, uint32_t n_a, const float* b, uint32_t n_b, int width, int height,
                        float x_min, float y_min, float x_scale, float y_scale, uint32_t* owner, uint8_t* bgr);
 cudaError_t launch_obstacles(cudaStream_t st, const float* nonground_xyz, uint32_t n, float target, float tol, float ego, uint32_t* cnt,
